@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — BEV frames/s of the point-cloud -> BEV front end (voxelize + PFN + scatter) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one batch of synthetic frames (BASELINE.json configs[1]: KITTI-shaped
+frames, batch 16, x 0..80 / y +-40 @ 0.1 m -> 800x800 canvas, [128,128,128] PFN, fp32 forward, eval-mode BN).
+N > 1: one process per GPU (torchrun), frames shard by rank (weak scaling: every rank runs its own batch of 16),
+no data-path collective; barrier + synchronize on both sides, device time via CUDA events, max over ranks.
+
+Keys beyond the base contract: `roofline` (dominant kernel, algorithmic bytes / event time vs MEASURED_PEAKS.json),
+`kernels` (per-kernel breakdown), `cpu_baseline` (oracle port timed on this box's host cores), `e2e` (same metric
+through the C-ABI host entry: pinned host points -> H2D -> K1,K2,K3 -> D2H of the per-frame pillar counts).
+`--impl reference` times the oracle port (the reference's CPU path cannot be installed: mmcv/mmdet3d absent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bev_frames_per_sec_voxelize_pfn_scatter"
+UNIT = "frames/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name: str, rank: int, batch=None, n=None):
+    from mask_bev_b200.synthetic import CONFIGS, encoder_kwargs, gen_batch
+    cfg = CONFIGS[name]
+    B = cfg["batch"] if batch is None else batch
+    frames = gen_batch(name, batch=B, n=n, first_frame=rank * B)
+    return cfg, encoder_kwargs(name), frames
+
+
+def make_encoder(kwargs, device):
+    """Random-init weights of the configured architecture (no checkpoints offline): oracle-side randomisation so the
+    oracle and the product share them."""
+    import torch
+    import mask_bev_b200 as M
+    from oracle import oracle as O
+    enc = M.MaskBevEncoder(**kwargs)
+    pfn = O.make_pfn_oracle(in_channels=kwargs["pc_point_dim"], feat_channels=kwargs["feat_channels"],
+                            with_distance=True, voxel_size=[kwargs["voxel_size_x"], kwargs["voxel_size_y"], kwargs["voxel_size_z"]],
+                            point_cloud_range=[kwargs["x_range"][0], kwargs["y_range"][0], kwargs["z_range"][0],
+                                               kwargs["x_range"][1], kwargs["y_range"][1], kwargs["z_range"][1]])
+    O.randomise_pfn(pfn, seed=0)
+    enc._voxel_encoder.load_state_dict(pfn.state_dict())
+    return enc.to(device).eval(), pfn.eval()
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's CPU path (serial C voxelizer + dense torch-CPU PFN + scatter)
+# ------------------------------------------------------------------------------------------------------
+def cpu_path_once(frames, kwargs, pfn):
+    import torch
+    from oracle import oracle as O
+    geo = O.encoder_geometry(kwargs["x_range"], kwargs["y_range"], kwargs["z_range"], kwargs["voxel_size_x"],
+                             kwargs["voxel_size_y"], kwargs["voxel_size_z"])
+    vs, ns, cs = [], [], []
+    for b, fr in enumerate(frames):
+        f, _ = O.filter_in_range_c(fr, kwargs["x_range"], kwargs["y_range"], kwargs["z_range"])
+        v, c, n, _ = O.hard_voxelize_c(f, geo["voxel_size"], geo["point_cloud_range"], kwargs["max_num_points"],
+                                       250000, want_kept=False)
+        vs.append(v); ns.append(n)
+        cs.append(np.concatenate([np.full((len(c), 1), b, np.int32), c], 1))
+    voxels, nump, coors = np.concatenate(vs), np.concatenate(ns), np.concatenate(cs)
+    with torch.no_grad():
+        feats = pfn(torch.from_numpy(voxels), torch.from_numpy(nump), torch.from_numpy(coors)).numpy()
+    return O.scatter_np(feats, coors, len(frames), geo["ny"], geo["nx"])
+
+
+def time_cpu(frames, kwargs, pfn, budget_s=20.0, min_reps=2, max_reps=10):
+    cpu_path_once(frames[:1], kwargs, pfn)  # warm-up (page-in, thread pools)
+    ts = []
+    t_all = time.perf_counter()
+    while len(ts) < max_reps and (len(ts) < min_reps or time.perf_counter() - t_all < budget_s):
+        t0 = time.perf_counter()
+        cpu_path_once(frames, kwargs, pfn)
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), len(ts)
+
+
+def run_reference_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build_c_oracle()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_frames = 2
+    cfg, kwargs, frames = build_workload(args.workload, 0, batch=sample_frames)
+    _, pfn = make_encoder_cpu_only(kwargs)
+    for _ in range(max(args.warmup, 1)):
+        cpu_path_once(frames[:1], kwargs, pfn)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_path_once(frames, kwargs, pfn)
+    dt = time.perf_counter() - t0
+    fps = sample_frames * args.steps / dt
+    sample = (f"{sample_frames} frames of the {cfg['batch']}-frame batch per step; serial C voxelizer (mmcv's CPU kernel "
+              f"is serial) + dense torch-CPU PFN over all P*T slots + scatter, torch threads={cores}")
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, cfg, sample_frames),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "oracle port: the reference's own CPU path (mmcv==2.0.0 / mmdet3d==1.1.0) is not installable offline"}
+    print(json.dumps(line), flush=True)
+
+
+def make_encoder_cpu_only(kwargs):
+    from oracle import oracle as O
+    pfn = O.make_pfn_oracle(in_channels=kwargs["pc_point_dim"], feat_channels=kwargs["feat_channels"],
+                            with_distance=True, voxel_size=[kwargs["voxel_size_x"], kwargs["voxel_size_y"], kwargs["voxel_size_z"]],
+                            point_cloud_range=[kwargs["x_range"][0], kwargs["y_range"][0], kwargs["z_range"][0],
+                                               kwargs["x_range"][1], kwargs["y_range"][1], kwargs["z_range"][1]])
+    O.randomise_pfn(pfn, seed=0)
+    return None, pfn.eval()
+
+
+def workload_config(name, cfg, batch_per_gpu):
+    return {"workload": name, "frames_per_gpu_per_step": batch_per_gpu, "points_per_frame": cfg["n"],
+            "point_feats": cfg["C"], "x_range": list(cfg["x_range"]), "y_range": list(cfg["y_range"]),
+            "voxel_size": cfg["voxel_size"], "max_num_points": cfg["T"], "pfn_feat_channels": list(cfg["feat_channels"]),
+            "bn_mode": "eval", "l2_policy": "per-step working set (canvas) is >> the 126 MB L2: no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def ev_time(fn, iters, stream_sync):
+    import torch
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream_sync()
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    e.synchronize()
+    return s.elapsed_time(e) / iters  # ms
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mask_bev_b200 import _lib
+    from mask_bev_b200.runtime import FusedEncoderRunner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, kwargs, frames = build_workload(args.workload, rank)
+    B = len(frames)
+    enc, pfn_cpu = make_encoder(kwargs, dev)
+    runner = FusedEncoderRunner(enc, [len(f) for f in frames], dev)
+    host = torch.from_numpy(np.concatenate(frames, 0)).pin_memory()
+    runner.points_dev.copy_(host)
+    counts_host = torch.empty((B + 1,), dtype=torch.int32).pin_memory()
+    sync = lambda: torch.cuda.synchronize(dev)  # noqa: E731
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        sync()
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(args.warmup):
+        runner.run_device()
+    barrier()
+    l0 = _lib.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        runner.run_device()
+    e.record()
+    barrier()
+    ms = s.elapsed_time(e)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end to end through the host entry (`e2e`) ----
+    for _ in range(max(1, args.warmup // 2)):
+        runner.run_host(host)
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(args.steps):
+        runner.run_host(host)
+        counts_host.copy_(runner.pillar_base, non_blocking=True)
+    e2.record()
+    barrier()
+    ms2 = s2.elapsed_time(e2)
+    t = torch.tensor([ms, ms2], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms2 = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel breakdown and roofline (rank 0) ----
+    peak, peak_src = _peaks()
+    iters = max(3, min(args.steps, 10))
+    runner.run_device(); sync()
+    base = runner.pillar_base.cpu().numpy()
+    P = int(base[-1])
+    nk = int(runner.num_points[:P].sum().item())
+    N = runner.total
+    C, T, G, Co = runner.C, runner.geo.max_points, runner.ny * runner.nx, runner.c_out
+    t_vox = ev_time(runner.run_voxelize, iters, sync)
+    t_pfn = ev_time(runner.run_pfn, iters, sync)
+    t_sc = ev_time(runner.run_scatter, iters, sync)
+    # algorithmic bytes per launch (per frame x frames in the batch; DESIGN.md "Roofline accounting")
+    by_vox = N * C * 4 + N * 4 + P * 20
+    by_pfn = nk * (C * 4 + 4) + P * 20 + P * Co * 4
+    by_sc = P * Co * 4 + P * 16 + B * G * Co * 4
+    units = [l.units for l in enc._voxel_encoder.pfn_layers]
+    ins = [l.linear.in_features for l in enc._voxel_encoder.pfn_layers]
+    mac_row = sum(i * u for i, u in zip(ins, units))
+    fl_pfn = 2.0 * mac_row * (nk + P)
+    kernels = {
+        "K1_voxelize": {"ms": t_vox, "alg_bytes": by_vox, "gbs": by_vox / t_vox / 1e6, "frac_hbm": by_vox / t_vox / 1e6 / peak},
+        "K2_pfn": {"ms": t_pfn, "alg_bytes": by_pfn, "gbs": by_pfn / t_pfn / 1e6, "frac_hbm": by_pfn / t_pfn / 1e6 / peak,
+                   "alg_tflops_upstream_equiv": fl_pfn / t_pfn / 1e9, "fp32_fma_peak_tflops": 74.4},
+        "K3_scatter": {"ms": t_sc, "alg_bytes": by_sc, "gbs": by_sc / t_sc / 1e6, "frac_hbm": by_sc / t_sc / 1e6 / peak},
+    }
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    roof = {"kernel": "K3_scatter (k_scatter)", "bound": "hbm", "achieved": kernels["K3_scatter"]["gbs"], "peak": peak,
+            "unit": "GB/s", "frac": kernels["K3_scatter"]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+            "launch_ms": t_sc, "dominant_by_time": dom,
+            "share_of_step": t_sc / (t_vox + t_pfn + t_sc)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roof["traffic"] = json.load(open(prof)).get("K3_scatter_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- CPU baseline: oracle port on this box's host cores, bounded sample ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build_c_oracle()
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        nfr = 2
+        tcpu, reps = time_cpu(frames[:nfr], kwargs, pfn_cpu, budget_s=15.0)
+        cpu = {"value": nfr / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{nfr} frames of this workload x {reps} reps (median); serial C voxelizer + dense torch-CPU PFN "
+                         f"(threads={cores}) + scatter"}
+    fps = world * B * args.steps / (ms * 1e-3)
+    fps2 = world * B * args.steps / (ms2 * 1e-3)
+    line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, cfg, B),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": fps2, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
+                    "d2h_bytes_per_step": int(counts_host.numel() * 4),
+                    "what": "mbev_encode_batch_host: pinned host points -> H2D -> K1,K2,K3 -> canvas in HBM (where the "
+                            "reference's consumer reads it) + D2H of per-frame pillar counts"},
+            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+            "pillars_per_step": P, "kept_points_per_step": nk, "points_per_step": N}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kitti_b16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,193 @@
+/*
+ * mask_bev_b200 — C ABI of the B200-native point-cloud -> BEV front end.
+ *
+ * Drop-in boundary for MaskBEV's encoder path
+ *   /root/reference/mask_bev/models/encoders/mask_bev_encoders.py:69-75 (construction),
+ *   :95-111 (voxelize), :113-117 (range filter), :119-120 (encode), :122-123 (middle_encode).
+ * The reference binds this path through two compiled/third-party interfaces that are NOT in its tree:
+ *   mmcv==2.0.0   mmcv.ops.Voxelization -> ext_module.hard_voxelize_forward      (Dockerfile:25)
+ *   mmdet3d==1.1.0 PillarFeatureNet / PFNLayer / PointPillarsScatter (torch ops)  (Dockerfile:28)
+ * Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _host. The caller (PyTorch) owns every
+ *     buffer, including the workspace; the library never allocates or frees device memory and keeps no
+ *     global state. All work is enqueued on `stream`; no entry point synchronises.
+ *   - Return value: 0 ok; negative = MbevStatus (bad argument / unsupported shape / workspace too small);
+ *     positive = cudaError_t of a failed launch. No exceptions cross this boundary.
+ *   - `stream` is a cudaStream_t passed as void* so that this header needs no CUDA include.
+ */
+#ifndef MASK_BEV_B200_H_
+#define MASK_BEV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MBEV_API __attribute__((visibility("default")))
+#else
+#define MBEV_API
+#endif
+
+#define MBEV_ABI_VERSION 1
+#define MBEV_MAX_BATCH 128  /* frames per call */
+#define MBEV_MAX_LAYERS 4   /* PFN layers */
+#define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
+#define MBEV_MAX_POINT_DIM 8
+
+typedef enum MbevStatus {
+  MBEV_OK = 0,
+  MBEV_ERR_BAD_ARG = -1,
+  MBEV_ERR_UNSUPPORTED = -2,
+  MBEV_ERR_WORKSPACE = -3,
+  MBEV_ERR_NO_DEVICE = -4
+} MbevStatus;
+
+/* Voxel-layer geometry: the arguments of mmcv.ops.Voxelization(voxel_size, point_cloud_range,
+ * max_num_points, max_voxels, deterministic=True) as built at mask_bev_encoders.py:67-69, all float32
+ * exactly as `torch.tensor(voxel_size)` / `torch.tensor(coors_range)` hand them to the compiled op. */
+typedef struct MbevGeometry {
+  float range[6];       /* x0,y0,z0,x1,y1,z1 */
+  float voxel[3];       /* vx,vy,vz */
+  int32_t grid[3];      /* nx,ny,nz = round((hi-lo)/vs) in float32 */
+  int32_t max_points;   /* T */
+  int32_t max_voxels;   /* V (per frame) */
+  int32_t num_feats;    /* C: floats per point row */
+  int32_t strict_filter; /* 1: apply mask_bev_encoders.py:113-117 (lo < v < hi, strict) before the voxel test */
+} MbevGeometry;
+
+/* One PFN stack: mmdet3d PillarFeatureNet(in_channels, feat_channels, with_distance, with_cluster_center,
+ * with_voxel_center, voxel_size, point_cloud_range, norm_cfg=BN1d(eps 1e-3, momentum 0.01), mode='max',
+ * legacy=True) as built at mask_bev_encoders.py:70-72. */
+typedef struct MbevPfnParams {
+  int32_t num_layers;
+  int32_t in_dim[MBEV_MAX_LAYERS];   /* in_0 = C+3+vcd+dist ; in_l = 2*units_{l-1} */
+  int32_t units[MBEV_MAX_LAYERS];    /* PFNLayer.units */
+  const float *weight[MBEV_MAX_LAYERS]; /* pfn_layers.l.linear.weight  (units_l, in_l) row-major */
+  const float *scale[MBEV_MAX_LAYERS];  /* eval: gamma/sqrt(running_var+eps) ; train: written by the library */
+  const float *shift[MBEV_MAX_LAYERS];  /* eval: beta - running_mean*scale   ; train: written by the library */
+  int32_t with_cluster_center, with_voxel_center, with_distance, legacy;
+  int32_t voxel_center_dims;         /* 3 (mmdet3d 1.1.0) or 2 (mmdet3d 0.x fossil, mask_bev_encoders.py:165-166) */
+  float vx, vy, vz, x_offset, y_offset, z_offset; /* float32(vx), float32(vx/2 + x0) ... */
+} MbevPfnParams;
+
+/* Version / capability probes (host only, no GPU needed). */
+MBEV_API int mbev_abi_version(void);
+MBEV_API const char *mbev_build_info(void);
+MBEV_API const char *mbev_status_string(int status);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  hard voxelisation of a batch of frames.
+ * Replaces: per-frame `_filter_in_range` + `mmcv.ops.Voxelization.forward` + batch-index padding
+ *           (mask_bev_encoders.py:95-111; mmcv hard_voxelize_forward, deterministic=True).
+ *   points            (total_points, C) float32, frames concatenated
+ *   frame_offsets_host (batch+1) int64 HOST array, row offsets of each frame in `points`
+ *   cell_table        (batch * nz*ny*nx) int32 OUT: global pillar id of each cell, -1 = empty
+ *                     (the occupancy mask and the scatter's inverse map)
+ *   coors             (pillar_capacity, 4) int32 OUT (b, z, y, x)
+ *   num_points        (pillar_capacity) int32 OUT, 1..T
+ *   kept_idx          (pillar_capacity, T) int32 OUT: row in `points` of slot t; slots >= num_points undefined
+ *   pillar_base       (batch+1) int32 OUT: first global pillar id of each frame; [batch] = total P
+ * Pillars are numbered frame by frame, inside a frame in order of first appearance; slots in input order.
+ * pillar_capacity must be >= min(total_points, batch*V).
+ * ---------------------------------------------------------------------------------------------- */
+MBEV_API int mbev_voxelize_workspace_bytes(const MbevGeometry *geo, int batch, int64_t total_points, size_t *bytes);
+MBEV_API int mbev_voxelize(const float *points, const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
+                  int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
+                  int32_t *pillar_base, int64_t pillar_capacity, void *workspace, size_t workspace_bytes,
+                  void *stream);
+
+/* Materialise the zero-padded (P, T, C) voxel tensor that mmcv's op returns (voxels_out) and, optionally,
+ * the -1 padded kept-index matrix rebased to frame-local rows. num_pillars_dev: device int32 (total P). */
+MBEV_API int mbev_gather_voxels(const float *points, const int32_t *kept_idx, const int32_t *num_points,
+                       const int32_t *num_pillars_dev, int64_t pillar_capacity, int T, int C, float *voxels,
+                       void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  pillar feature net forward (decorate -> L x (Linear, BN, ReLU, max over T [, concat]) ).
+ * Replaces: mmdet3d PillarFeatureNet.forward / PFNLayer.forward (mask_bev_encoders.py:119-120).
+ *   rows       float32 row store: either `points` (sparse mode, kept_idx != NULL) or the padded voxel tensor
+ *              (P,T,C) (dense mode, kept_idx == NULL; row of slot (p,t) is p*T+t)
+ *   num_pillars_dev  device int32: number of pillars to process (no host sync on the fused path)
+ *   feats      (pillar_capacity, units[L-1]) float32 OUT
+ * Eval mode uses params->scale/shift (BatchNorm folded with running statistics).
+ * Train mode (mbev_pfn_forward_train) computes batch statistics over all P*T slots exactly as BatchNorm1d
+ * does on the padded tensor, writes the folded scale/shift it used into `scale_shift_out`
+ * (L x 2 x MBEV_MAX_UNITS floats) and mean / biased variance into `batch_stats_out` (same shape) so the
+ * host can update running statistics with momentum 0.01 and the unbiased variance.
+ * ---------------------------------------------------------------------------------------------- */
+MBEV_API int mbev_pfn_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity, int train,
+                             size_t *bytes);
+MBEV_API int mbev_pfn_forward(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
+                     const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity, int T,
+                     const MbevPfnParams *params, float *feats, void *workspace, size_t workspace_bytes,
+                     void *stream);
+MBEV_API int mbev_pfn_forward_train(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
+                           const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity, int T,
+                           const MbevPfnParams *params, const float *const *gamma, const float *const *beta,
+                           float eps, float *feats, float *scale_shift_out, float *batch_stats_out,
+                           void *workspace, size_t workspace_bytes, void *stream);
+/* Backward of the train- or eval-mode forward w.r.t. the parameters (raw points carry no gradient,
+ * SURVEY.md §3.4; the reference gets this from autograd over the dense op sequence).
+ *   gamma        HOST array of L device pointers: pfn_layers.l.norm.weight
+ *   scale_shift  (L,2,MBEV_MAX_UNITS) folded scale/shift the forward used (forward_train output, or the eval fold)
+ *   batch_stats  (L,2,MBEV_MAX_UNITS) mean / variance the forward normalised with (batch or running)
+ *   train        1: BatchNorm batch-statistics backward (mean/var depend on the rows); 0: frozen statistics
+ *   dfeats       (pillar_capacity, units[L-1])
+ * Outputs (HOST arrays of L device pointers): dweight[l] (units_l, in_l), dgamma[l], dbeta[l] (units_l).
+ * Reductions use a fixed order: results are run-to-run identical. */
+MBEV_API int mbev_pfn_backward_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity,
+                                               size_t *bytes);
+MBEV_API int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
+                               const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity, int T,
+                               const MbevPfnParams *params, const float *const *gamma, const float *scale_shift,
+                               const float *batch_stats, float eps, int train, const float *dfeats,
+                               float *const *dweight, float *const *dgamma, float *const *dbeta, void *workspace,
+                               size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  scatter to the dense BEV canvas, one streaming pass (zeros and features written exactly once).
+ * Replaces: mmdet3d PointPillarsScatter.forward_batch (mask_bev_encoders.py:122-123).
+ *   cell_table (batch * ny*nx) int32: pillar id per cell or -1 (from mbev_voxelize or mbev_build_cell_table)
+ *   canvas     (batch, C_out, ny, nx) float32 OUT, NCHW contiguous (the reference's layout)
+ * K3' backward: dfeats[p, :] = dcanvas[b, :, y, x].
+ * ---------------------------------------------------------------------------------------------- */
+MBEV_API int mbev_build_cell_table(const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity,
+                          int batch, int ny, int nx, int32_t *cell_table, void *stream);
+MBEV_API int mbev_scatter_forward(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny, int nx,
+                         float *canvas, void *stream);
+MBEV_API int mbev_scatter_backward(const float *dcanvas, const int32_t *cell_table, int batch, int c_out, int ny,
+                          int nx, float *dfeats, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused batch entry (additive): K1 -> K2(eval) -> K3 on one stream, no host sync.
+ * Equivalent to MaskBevEncoder.forward (mask_bev_encoders.py:77-91) without the trailing LayerNorm.
+ * ---------------------------------------------------------------------------------------------- */
+MBEV_API int mbev_encode_batch_workspace_bytes(const MbevGeometry *geo, const MbevPfnParams *params, int batch,
+                                      int64_t total_points, int64_t pillar_capacity, size_t *bytes);
+MBEV_API int mbev_encode_batch(const float *points, const int64_t *frame_offsets_host, int batch,
+                      const MbevGeometry *geo, const MbevPfnParams *params, int32_t *cell_table,
+                      int32_t *coors, int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
+                      int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* Same, with HOST input: copies `points_host` (pinned or pageable) to `points_dev` on `stream` first.
+ * This is the call bench.py's e2e leg times. */
+MBEV_API int mbev_encode_batch_host(const float *points_host, float *points_dev, const int64_t *frame_offsets_host,
+                           int batch, const MbevGeometry *geo, const MbevPfnParams *params,
+                           int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
+                           int32_t *pillar_base, int64_t pillar_capacity, float *feats, float *canvas,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* Launch counter: number of library kernels enqueued by this process since load (for bench.py's
+ * `gpu_launches`). Thread-safe. */
+MBEV_API int64_t mbev_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MASK_BEV_B200_H_ */

@@ -1,0 +1,98 @@
+// C-ABI glue: version probes, launch counter, and the fused batch entry K1 -> K2(eval) -> K3.
+#include "common.cuh"
+
+namespace mbev {
+std::atomic<int64_t> g_launches{0};
+}
+
+using namespace mbev;
+
+extern "C" int mbev_abi_version(void) { return MBEV_ABI_VERSION; }
+
+extern "C" const char *mbev_build_info(void) {
+  return "mask_bev_b200 sm_100a nvcc " __DATE__ " " __TIME__;
+}
+
+extern "C" const char *mbev_status_string(int status) {
+  switch (status) {
+    case MBEV_OK: return "ok";
+    case MBEV_ERR_BAD_ARG: return "bad argument";
+    case MBEV_ERR_UNSUPPORTED: return "unsupported shape or configuration";
+    case MBEV_ERR_WORKSPACE: return "workspace too small";
+    case MBEV_ERR_NO_DEVICE: return "no CUDA device";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+  return "unknown status";
+}
+
+extern "C" int64_t mbev_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+struct FusedWs {
+  size_t vox_off, vox_bytes, pfn_off, pfn_bytes, total;
+};
+
+int fused_ws(const MbevGeometry *geo, const MbevPfnParams *params, int batch, int64_t total_points,
+             int64_t pillar_capacity, FusedWs *w) {
+  size_t vb = 0, pb = 0;
+  int st = mbev_voxelize_workspace_bytes(geo, batch, total_points, &vb);
+  if (st) return st;
+  st = mbev_pfn_workspace_bytes(params, geo->max_points, pillar_capacity, 0, &pb);
+  if (st) return st;
+  w->vox_off = 0;
+  w->vox_bytes = vb;
+  w->pfn_off = align_up(vb);
+  w->pfn_bytes = pb;
+  w->total = w->pfn_off + align_up(pb);
+  return MBEV_OK;
+}
+}  // namespace
+
+extern "C" int mbev_encode_batch_workspace_bytes(const MbevGeometry *geo, const MbevPfnParams *params, int batch,
+                                                 int64_t total_points, int64_t pillar_capacity, size_t *bytes) {
+  if (!geo || !params || !bytes) return MBEV_ERR_BAD_ARG;
+  FusedWs w;
+  const int st = fused_ws(geo, params, batch, total_points, pillar_capacity, &w);
+  if (st) return st;
+  *bytes = w.total;
+  return MBEV_OK;
+}
+
+extern "C" int mbev_encode_batch(const float *points, const int64_t *frame_offsets_host, int batch,
+                                 const MbevGeometry *geo, const MbevPfnParams *params, int32_t *cell_table,
+                                 int32_t *coors, int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
+                                 int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
+                                 size_t workspace_bytes, void *stream) {
+  if (!geo || !params || !frame_offsets_host || !workspace || !feats || !canvas) return MBEV_ERR_BAD_ARG;
+  if (geo->grid[2] != 1) return MBEV_ERR_UNSUPPORTED;  // pillars: one cell along z (mask_bev_module.py:62)
+  FusedWs w;
+  int st = fused_ws(geo, params, batch, frame_offsets_host[batch], pillar_capacity, &w);
+  if (st) return st;
+  if (workspace_bytes < w.total) return MBEV_ERR_WORKSPACE;
+  char *ws = static_cast<char *>(workspace);
+  st = mbev_voxelize(points, frame_offsets_host, batch, geo, cell_table, coors, num_points, kept_idx, pillar_base,
+                     pillar_capacity, ws + w.vox_off, w.vox_bytes, stream);
+  if (st) return st;
+  st = mbev_pfn_forward(points, geo->num_feats, kept_idx, num_points, coors, pillar_base + batch, pillar_capacity,
+                        geo->max_points, params, feats, ws + w.pfn_off, w.pfn_bytes, stream);
+  if (st) return st;
+  return mbev_scatter_forward(feats, cell_table, batch, params->units[params->num_layers - 1], geo->grid[1],
+                              geo->grid[0], canvas, stream);
+}
+
+extern "C" int mbev_encode_batch_host(const float *points_host, float *points_dev, const int64_t *frame_offsets_host,
+                                      int batch, const MbevGeometry *geo, const MbevPfnParams *params,
+                                      int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
+                                      int32_t *pillar_base, int64_t pillar_capacity, float *feats, float *canvas,
+                                      void *workspace, size_t workspace_bytes, void *stream) {
+  if (!geo || !frame_offsets_host || batch < 1 || batch > MBEV_MAX_BATCH) return MBEV_ERR_BAD_ARG;
+  const int64_t total = frame_offsets_host[batch];
+  if (total > 0) {
+    if (!points_host || !points_dev) return MBEV_ERR_BAD_ARG;
+    MBEV_CUDA(cudaMemcpyAsync(points_dev, points_host, sizeof(float) * static_cast<size_t>(total) * geo->num_feats,
+                              cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  }
+  return mbev_encode_batch(points_dev, frame_offsets_host, batch, geo, params, cell_table, coors, num_points,
+                           kept_idx, pillar_base, pillar_capacity, feats, canvas, workspace, workspace_bytes, stream);
+}

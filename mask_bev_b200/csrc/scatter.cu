@@ -1,0 +1,191 @@
+// K3 / K3' — pillar features <-> dense BEV canvas (sm_100a).
+//
+// Replaces mmdet3d PointPillarsScatter.forward_batch (mask_bev_encoders.py:122-123), which per frame does
+// memset + boolean select (host sync) + transposed index_put + stack: the canvas is written ~3x and read
+// once. Here the canvas (B, C, ny*nx) fp32 NCHW is written exactly once by a persistent streaming kernel
+// that walks the cell table (cell -> pillar id, -1 empty): every 16-byte store carries either zeros or
+// features, so DRAM traffic = canvas bytes + table + the occupied feature rows (HBM-bound, write-only).
+// The backward is the gather dfeats[p,:] = dcanvas[b,:,y,x] driven by the same table.
+#include "common.cuh"
+
+namespace mbev {
+namespace {
+
+constexpr int kCells = 128;    // cells per tile: one warp-wide float4 store covers a whole tile row (512 B)
+constexpr int kThreads = 256;  // 8 warps; warp w owns channels w, w+8, ...
+
+// smem: feature rows of the occupied cells of this tile, [kCells][C+1] (odd pitch: conflict-free column reads)
+__global__ void __launch_bounds__(kThreads)
+k_scatter(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
+          const int tiles_per_frame, const int num_tiles, float *__restrict__ canvas) {
+  extern __shared__ float s_rows[];
+  __shared__ int s_pid[kCells];
+  __shared__ int s_any;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pitch = C + 1;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_frame;
+    const int g0 = (tile - b * tiles_per_frame) * kCells;
+    __syncthreads();  // previous iteration's readers are done with s_pid / s_rows
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    if (tid < kCells) {
+      const int g = g0 + tid;
+      const int pid = (g < G) ? __ldg(table + static_cast<size_t>(b) * G + g) : -1;
+      s_pid[tid] = pid;
+      if (pid >= 0) s_any = 1;
+    }
+    __syncthreads();
+    const bool any = s_any != 0;
+    if (any) {
+      // stage occupied rows: one warp per cell, coalesced 128-bit reads of the (C) row
+      for (int c = warp; c < kCells; c += kThreads / 32) {
+        const int pid = s_pid[c];
+        if (pid < 0) continue;
+        const float *src = feats + static_cast<size_t>(pid) * C;
+        float *dst = s_rows + c * pitch;
+        for (int k = lane; k < C; k += 32) dst[k] = __ldg(src + k);
+      }
+      __syncthreads();
+    }
+    // lane owns cells 4*lane .. 4*lane+3 of the tile
+    const int c0 = lane * 4;
+    const int p0 = s_pid[c0], p1 = s_pid[c0 + 1], p2 = s_pid[c0 + 2], p3 = s_pid[c0 + 3];
+    const bool mine = (p0 >= 0) | (p1 >= 0) | (p2 >= 0) | (p3 >= 0);
+    const int g = g0 + c0;
+    float *out = canvas + (static_cast<size_t>(b) * C) * G + g;
+    if (g + 3 < G) {
+      for (int ch = warp; ch < C; ch += kThreads / 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mine) {
+          if (p0 >= 0) v.x = s_rows[(c0 + 0) * pitch + ch];
+          if (p1 >= 0) v.y = s_rows[(c0 + 1) * pitch + ch];
+          if (p2 >= 0) v.z = s_rows[(c0 + 2) * pitch + ch];
+          if (p3 >= 0) v.w = s_rows[(c0 + 3) * pitch + ch];
+        }
+        st_global_v4_stream(out + static_cast<size_t>(ch) * G, v);
+      }
+    } else if (g < G) {  // ragged tail of the frame
+      for (int ch = warp; ch < C; ch += kThreads / 32) {
+        for (int k = 0; k < 4 && g + k < G; ++k) {
+          const int p = s_pid[c0 + k];
+          out[static_cast<size_t>(ch) * G + k] = (p >= 0) ? s_rows[(c0 + k) * pitch + ch] : 0.f;
+        }
+      }
+    }
+  }
+}
+
+// Generic fallback when G is not a multiple of 4 (plane rows are then not 16-byte aligned).
+__global__ void __launch_bounds__(kThreads)
+k_scatter_scalar(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
+                 const long long total, float *__restrict__ canvas) {
+  for (long long e = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * kThreads) {
+    const int g = static_cast<int>(e % G);
+    const long long bc = e / G;
+    const int ch = static_cast<int>(bc % C);
+    const int b = static_cast<int>(bc / C);
+    const int pid = __ldg(table + static_cast<size_t>(b) * G + g);
+    canvas[e] = pid >= 0 ? __ldg(feats + static_cast<size_t>(pid) * C + ch) : 0.f;
+  }
+}
+
+// K3' : one warp per occupied cell, lanes over channels.
+__global__ void __launch_bounds__(kThreads)
+k_gather_bwd(const float *__restrict__ dcanvas, const int *__restrict__ table, const int C, const int G,
+             const int tiles_per_frame, const int num_tiles, float *__restrict__ dfeats) {
+  __shared__ int s_pid[kCells];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_frame;
+    const int g0 = (tile - b * tiles_per_frame) * kCells;
+    __syncthreads();
+    if (tid < kCells) {
+      const int g = g0 + tid;
+      s_pid[tid] = (g < G) ? __ldg(table + static_cast<size_t>(b) * G + g) : -1;
+    }
+    __syncthreads();
+    for (int c = warp; c < kCells; c += kThreads / 32) {
+      const int pid = s_pid[c];
+      if (pid < 0) continue;
+      const float *src = dcanvas + (static_cast<size_t>(b) * C) * G + (g0 + c);
+      float *dst = dfeats + static_cast<size_t>(pid) * C;
+      for (int ch = lane; ch < C; ch += 32) dst[ch] = __ldg(src + static_cast<size_t>(ch) * G);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_build_table(const int *__restrict__ coors, const int *__restrict__ num_pillars, const int batch, const int ny,
+              const int nx, int *__restrict__ table) {
+  const int P = *num_pillars;
+  for (int p = blockIdx.x * kThreads + threadIdx.x; p < P; p += gridDim.x * kThreads) {
+    const int4 c = reinterpret_cast<const int4 *>(coors)[p];  // (b, z, y, x)
+    if (c.x < 0 || c.x >= batch || c.z < 0 || c.z >= ny || c.w < 0 || c.w >= nx) continue;
+    table[(static_cast<size_t>(c.x) * ny + c.z) * nx + c.w] = p;
+  }
+}
+
+}  // namespace
+}  // namespace mbev
+
+using namespace mbev;
+
+extern "C" int mbev_build_cell_table(const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity,
+                                     int batch, int ny, int nx, int32_t *cell_table, void *stream_) {
+  if (!cell_table || !num_pillars_dev || batch < 1 || ny < 1 || nx < 1) return MBEV_ERR_BAD_ARG;
+  if (static_cast<int64_t>(batch) * ny * nx > 0x7fffffffLL) return MBEV_ERR_UNSUPPORTED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MBEV_CUDA(cudaMemsetAsync(cell_table, 0xff, sizeof(int32_t) * static_cast<size_t>(batch) * ny * nx, stream));
+  if (pillar_capacity <= 0) return MBEV_OK;
+  if (!coors) return MBEV_ERR_BAD_ARG;
+  const int blocks = static_cast<int>(std::min<int64_t>((pillar_capacity + kThreads - 1) / kThreads, kNumSMs * 8));
+  k_build_table<<<blocks, kThreads, 0, stream>>>(coors, num_pillars_dev, batch, ny, nx, cell_table);
+  MBEV_CHECK_LAUNCH();
+  return MBEV_OK;
+}
+
+extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny,
+                                    int nx, float *canvas, void *stream_) {
+  if (!cell_table || !canvas || batch < 1 || c_out < 1 || ny < 1 || nx < 1) return MBEV_ERR_BAD_ARG;
+  const int64_t G64 = static_cast<int64_t>(ny) * nx;
+  if (G64 * batch > 0x7fffffffLL) return MBEV_ERR_UNSUPPORTED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int G = static_cast<int>(G64);
+  const size_t smem = sizeof(float) * kCells * (static_cast<size_t>(c_out) + 1);
+  if ((G & 3) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 15) == 0 && smem <= 200 * 1024) {
+    const int tiles_per_frame = (G + kCells - 1) / kCells;
+    const int num_tiles = tiles_per_frame * batch;
+    static bool attr_done = false;  // idempotent; a benign race sets the same value twice
+    if (!attr_done) {
+      MBEV_CUDA(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+    const int blocks = std::min(num_tiles, kNumSMs * per_sm);
+    k_scatter<<<blocks, kThreads, smem, stream>>>(feats, cell_table, c_out, G, tiles_per_frame, num_tiles, canvas);
+  } else {
+    const long long total = static_cast<long long>(batch) * c_out * G;
+    const int blocks = static_cast<int>(std::min<long long>((total + kThreads - 1) / kThreads, kNumSMs * 16));
+    k_scatter_scalar<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, total, canvas);
+  }
+  MBEV_CHECK_LAUNCH();
+  return MBEV_OK;
+}
+
+extern "C" int mbev_scatter_backward(const float *dcanvas, const int32_t *cell_table, int batch, int c_out, int ny,
+                                     int nx, float *dfeats, void *stream_) {
+  if (!dcanvas || !cell_table || !dfeats || batch < 1 || c_out < 1 || ny < 1 || nx < 1) return MBEV_ERR_BAD_ARG;
+  const int64_t G64 = static_cast<int64_t>(ny) * nx;
+  if (G64 * batch > 0x7fffffffLL) return MBEV_ERR_UNSUPPORTED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int G = static_cast<int>(G64);
+  const int tiles_per_frame = (G + kCells - 1) / kCells;
+  const int num_tiles = tiles_per_frame * batch;
+  const int blocks = std::min(num_tiles, kNumSMs * 8);
+  k_gather_bwd<<<blocks, kThreads, 0, stream>>>(dcanvas, cell_table, c_out, G, tiles_per_frame, num_tiles, dfeats);
+  MBEV_CHECK_LAUNCH();
+  return MBEV_OK;
+}

@@ -1,0 +1,96 @@
+"""Serving-style runner for the fused path: every buffer preallocated once, one C-ABI call per batch
+(``mbev_encode_batch`` for device-resident points, ``mbev_encode_batch_host`` for pinned host points), no host
+synchronisation, no allocator traffic. This is what bench.py times; ``MaskBevEncoder.forward`` is the
+autograd-aware equivalent.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from . import functional as F_
+from ._lib import check, ptr
+
+
+class FusedEncoderRunner:
+    def __init__(self, encoder, frame_sizes: Sequence[int], device: torch.device):
+        self.enc = encoder
+        self.device = torch.device(device)
+        self.lib = _lib.load()
+        self.sizes = [int(s) for s in frame_sizes]
+        self.B = len(self.sizes)
+        C = encoder._voxel_encoder.raw_in_channels
+        self.C = C
+        self.geo = encoder._voxel_layer._geometry(C, strict_filter=True)
+        self.off, self.total = F_._offsets(self.sizes)
+        self.cap = F_.pillar_capacity(self.geo, self.sizes)
+        self.ny, self.nx = encoder._num_voxel_y, encoder._num_voxel_x
+        self.c_out = encoder._out_features
+        dev = self.device
+        T = self.geo.max_points
+        cells = self.ny * self.nx
+        self.points_dev = torch.empty((self.total, C), dtype=torch.float32, device=dev)
+        self.cell_table = torch.empty((self.B, cells), dtype=torch.int32, device=dev)
+        self.coors = torch.empty((self.cap, 4), dtype=torch.int32, device=dev)
+        self.num_points = torch.empty((self.cap,), dtype=torch.int32, device=dev)
+        self.kept_idx = torch.empty((self.cap, T), dtype=torch.int32, device=dev)
+        self.pillar_base = torch.zeros((self.B + 1,), dtype=torch.int32, device=dev)
+        self.feats = torch.empty((self.cap, self.c_out), dtype=torch.float32, device=dev)
+        self.canvas = torch.empty((self.B, self.c_out, self.ny, self.nx), dtype=torch.float32, device=dev)
+        self.refresh_params()
+        nbytes = ctypes.c_size_t()
+        check(self.lib.mbev_encode_batch_workspace_bytes(ctypes.byref(self.geo), ctypes.byref(self.params), self.B,
+                                                         self.total, self.cap, ctypes.byref(nbytes)),
+              "encode_batch_workspace_bytes")
+        self.ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
+
+    def refresh_params(self) -> None:
+        """Re-fold the eval-mode BatchNorm after a weight update."""
+        net = self.enc._voxel_encoder
+        self._weights = [F_._f32c(l.linear.weight) for l in net.pfn_layers]
+        self._scales, self._shifts, self._ss, _ = net._folded()
+        self.params = F_._pfn_struct(net._config(), self._weights, self._scales, self._shifts)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def run_device(self, points: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """points: (sum N_i, C) float32 on the device (defaults to the runner's own resident copy)."""
+        p = self.points_dev if points is None else points
+        check(self.lib.mbev_encode_batch(ptr(p), self.off, self.B, ctypes.byref(self.geo), ctypes.byref(self.params),
+                                         ptr(self.cell_table), ptr(self.coors), ptr(self.num_points),
+                                         ptr(self.kept_idx), ptr(self.pillar_base), self.cap, ptr(self.feats),
+                                         ptr(self.canvas), ptr(self.ws), self.ws.numel(), self._stream()),
+              "encode_batch")
+        return self.canvas
+
+    def run_host(self, points_host: torch.Tensor) -> torch.Tensor:
+        """points_host: (sum N_i, C) float32 HOST tensor (pinned for an asynchronous copy)."""
+        check(self.lib.mbev_encode_batch_host(ptr(points_host), ptr(self.points_dev), self.off, self.B,
+                                              ctypes.byref(self.geo), ctypes.byref(self.params),
+                                              ptr(self.cell_table), ptr(self.coors), ptr(self.num_points),
+                                              ptr(self.kept_idx), ptr(self.pillar_base), self.cap, ptr(self.feats),
+                                              ptr(self.canvas), ptr(self.ws), self.ws.numel(), self._stream()),
+              "encode_batch_host")
+        return self.canvas
+
+    # stage-by-stage entry points (per-kernel timing in bench.py)
+    def run_voxelize(self):
+        nb = ctypes.c_size_t()
+        check(self.lib.mbev_voxelize_workspace_bytes(ctypes.byref(self.geo), self.B, self.total, ctypes.byref(nb)), "ws")
+        check(self.lib.mbev_voxelize(ptr(self.points_dev), self.off, self.B, ctypes.byref(self.geo),
+                                     ptr(self.cell_table), ptr(self.coors), ptr(self.num_points), ptr(self.kept_idx),
+                                     ptr(self.pillar_base), self.cap, ptr(self.ws), nb.value, self._stream()), "voxelize")
+
+    def run_pfn(self):
+        check(self.lib.mbev_pfn_forward(ptr(self.points_dev), self.C, ptr(self.kept_idx), ptr(self.num_points),
+                                        ptr(self.coors), ptr(self.pillar_base[self.B:]), self.cap, self.geo.max_points,
+                                        ctypes.byref(self.params), ptr(self.feats), ptr(self.ws), self.ws.numel(),
+                                        self._stream()), "pfn_forward")
+
+    def run_scatter(self):
+        check(self.lib.mbev_scatter_forward(ptr(self.feats), ptr(self.cell_table), self.B, self.c_out, self.ny,
+                                            self.nx, ptr(self.canvas), self._stream()), "scatter_forward")

