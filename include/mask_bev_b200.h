@@ -133,7 +133,8 @@ MBEV_API int mbev_pfn_forward_train(const float *rows, int C, const int32_t *kep
                            void *workspace, size_t workspace_bytes, void *stream);
 /* Backward of the train- or eval-mode forward w.r.t. the parameters (raw points carry no gradient,
  * SURVEY.md §3.4; the reference gets this from autograd over the dense op sequence).
- *   gamma        HOST array of L device pointers: pfn_layers.l.norm.weight
+ *   rows_capacity_hint  upper bound of the compact row count R = sum_p (n_p + [n_p < T]) used to size the
+ *                       workspace (e.g. total_points + pillar_capacity); <= 0 means pillar_capacity * (T+1)
  *   scale_shift  (L,2,MBEV_MAX_UNITS) folded scale/shift the forward used (forward_train output, or the eval fold)
  *   batch_stats  (L,2,MBEV_MAX_UNITS) mean / variance the forward normalised with (batch or running)
  *   train        1: BatchNorm batch-statistics backward (mean/var depend on the rows); 0: frozen statistics
@@ -141,10 +142,10 @@ MBEV_API int mbev_pfn_forward_train(const float *rows, int C, const int32_t *kep
  * Outputs (HOST arrays of L device pointers): dweight[l] (units_l, in_l), dgamma[l], dbeta[l] (units_l).
  * Reductions use a fixed order: results are run-to-run identical. */
 MBEV_API int mbev_pfn_backward_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity,
-                                               size_t *bytes);
+                                               int64_t rows_capacity_hint, size_t *bytes);
 MBEV_API int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
                                const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity, int T,
-                               const MbevPfnParams *params, const float *const *gamma, const float *scale_shift,
+                               int64_t rows_capacity_hint, const MbevPfnParams *params, const float *scale_shift,
                                const float *batch_stats, float eps, int train, const float *dfeats,
                                float *const *dweight, float *const *dgamma, float *const *dbeta, void *workspace,
                                size_t workspace_bytes, void *stream);

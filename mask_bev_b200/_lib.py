@@ -52,9 +52,9 @@ SIGNATURES = {
     "mbev_pfn_forward": (c_int, [_v, c_int, _v, _v, _v, _v, c_int64, c_int, _P, _v, _v, c_size_t, _v]),
     "mbev_pfn_forward_train": (c_int, [_v, c_int, _v, _v, _v, _v, c_int64, c_int, _P, POINTER(_PTRS),
                                        POINTER(_PTRS), c_float, _v, _v, _v, _v, c_size_t, _v]),
-    "mbev_pfn_backward_workspace_bytes": (c_int, [_P, c_int, c_int64, POINTER(c_size_t)]),
-    "mbev_pfn_backward": (c_int, [_v, c_int, _v, _v, _v, _v, c_int64, c_int, _P, POINTER(_PTRS), _v, _v, c_float,
-                                  c_int, _v, POINTER(_PTRS), POINTER(_PTRS), POINTER(_PTRS), _v, c_size_t, _v]),
+    "mbev_pfn_backward_workspace_bytes": (c_int, [_P, c_int, c_int64, c_int64, POINTER(c_size_t)]),
+    "mbev_pfn_backward": (c_int, [_v, c_int, _v, _v, _v, _v, c_int64, c_int, c_int64, _P, _v, _v, c_float, c_int, _v,
+                                  POINTER(_PTRS), POINTER(_PTRS), POINTER(_PTRS), _v, c_size_t, _v]),
     "mbev_build_cell_table": (c_int, [_v, _v, c_int64, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_forward": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_backward": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, _v]),

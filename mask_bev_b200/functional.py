@@ -224,26 +224,26 @@ def pfn_forward_train(rows, kept_idx, num_points, coors, num_pillars_dev, capaci
 
 
 def pfn_backward(rows, kept_idx, num_points, coors, num_pillars_dev, capacity, T, cfg: PfnConfig, weights,
-                 gammas, scale_shift, batch_stats, train: bool, dfeats):
-    """Parameter gradients of the PFN: lists (dweight[l], dgamma[l], dbeta[l])."""
+                 scale_shift, batch_stats, train: bool, dfeats, rows_capacity: int = 0):
+    """Parameter gradients of the PFN: lists (dweight[l], dgamma[l], dbeta[l]).
+    rows_capacity: host-side bound of the compact row count (real rows + one virtual row per padded pillar)."""
     lib = _lib.load()
     dev = rows.device
     L = len(cfg.units)
     weights = [_f32c(w) for w in weights]
-    gammas = [_f32c(g) for g in gammas]
     params = _pfn_struct(cfg, weights, None, None)
     nbytes = ctypes.c_size_t()
-    check(lib.mbev_pfn_backward_workspace_bytes(ctypes.byref(params), T, capacity, ctypes.byref(nbytes)),
-          "pfn_backward_workspace_bytes")
+    check(lib.mbev_pfn_backward_workspace_bytes(ctypes.byref(params), T, capacity, rows_capacity,
+                                                ctypes.byref(nbytes)), "pfn_backward_workspace_bytes")
     ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
     dws = [torch.empty((cfg.units[l], cfg.in_dims[l]), dtype=torch.float32, device=dev) for l in range(L)]
     dgs = [torch.empty((cfg.units[l],), dtype=torch.float32, device=dev) for l in range(L)]
     dbs = [torch.empty((cfg.units[l],), dtype=torch.float32, device=dev) for l in range(L)]
     dfeats = _f32c(dfeats)
-    g_arr, dw_arr, dg_arr, db_arr = ptr_array(gammas), ptr_array(dws), ptr_array(dgs), ptr_array(dbs)
+    dw_arr, dg_arr, db_arr = ptr_array(dws), ptr_array(dgs), ptr_array(dbs)
     with torch.cuda.device(dev):
         check(lib.mbev_pfn_backward(ptr(rows), cfg.in_channels, ptr(kept_idx), ptr(num_points), ptr(coors),
-                                    ptr(num_pillars_dev), capacity, T, ctypes.byref(params), ctypes.byref(g_arr),
+                                    ptr(num_pillars_dev), capacity, T, rows_capacity, ctypes.byref(params),
                                     ptr(scale_shift), ptr(batch_stats), cfg.eps, int(train), ptr(dfeats),
                                     ctypes.byref(dw_arr), ctypes.byref(dg_arr), ctypes.byref(db_arr), ptr(ws),
                                     ws.numel(), _stream()), "pfn_backward")

@@ -56,8 +56,11 @@ class _PfnFunction(torch.autograd.Function):
                                         scales, shifts)
         ctx.net, ctx.cfg, ctx.training, ctx.capacity, ctx.T = net, cfg, training, capacity, T
         ctx.save_for_backward(rows, kept_idx if kept_idx is not None else torch.empty(0, device=rows.device),
-                              num_points, coors, npil_dev, scale_shift, batch_stats, *weights, *gammas)
+                              num_points, coors, npil_dev, scale_shift, batch_stats, *weights)
         ctx.has_kept = kept_idx is not None
+        # compact row bound without a host sync: every real row is a stored point (<= rows.shape[0] of them) and
+        # there is at most one virtual row per pillar
+        ctx.rows_capacity = int(min(capacity * (T + 1), rows.shape[0] + capacity))
         return feats
 
     @staticmethod
@@ -65,10 +68,10 @@ class _PfnFunction(torch.autograd.Function):
         saved = ctx.saved_tensors
         rows, kept_idx, num_points, coors, npil_dev, scale_shift, batch_stats = saved[:7]
         L = len(ctx.cfg.units)
-        weights, gammas = saved[7:7 + L], saved[7 + L:7 + 2 * L]
+        weights = saved[7:7 + L]
         dws, dgs, dbs = F_.pfn_backward(rows, kept_idx if ctx.has_kept else None, num_points, coors, npil_dev,
-                                        ctx.capacity, ctx.T, ctx.cfg, weights, gammas, scale_shift, batch_stats,
-                                        ctx.training, dfeats)
+                                        ctx.capacity, ctx.T, ctx.cfg, weights, scale_shift, batch_stats,
+                                        ctx.training, dfeats, ctx.rows_capacity)
         return (None,) * 8 + tuple(dws) + tuple(dgs) + tuple(dbs)
 
 

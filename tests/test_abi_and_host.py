@@ -1,0 +1,127 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mask_bev_b200.h declares (no compute calls), the
+host-side mirror keeps the reference's interface and state-dict keys, CPU inputs are rejected loudly, and the
+reference's own encoder file imports unchanged against the shims."""
+import ctypes
+import importlib
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from helpers import ROOT, ref_test_kwargs
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "mask_bev_b200.h")).read()
+    return sorted(set(re.findall(r"MBEV_API[^;(]*?\b(mbev_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mask_bev_b200 import _lib
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(syms)
+    assert lib.mbev_abi_version() == _lib.ABI_VERSION
+    assert b"sm_100a" in lib.mbev_build_info()
+    assert lib.mbev_status_string(-2) == b"unsupported shape or configuration"
+
+
+def test_struct_layout_matches_header():
+    from mask_bev_b200 import _lib
+    assert ctypes.sizeof(_lib.MbevGeometry) == 6 * 4 + 3 * 4 + 3 * 4 + 4 * 4
+    p = _lib.MbevPfnParams
+    assert p.in_dim.offset == 4 and p.units.offset == 20 and p.weight.offset == 40
+    assert p.scale.offset == 72 and p.shift.offset == 104 and p.with_cluster_center.offset == 136
+    assert ctypes.sizeof(p) == 136 + 5 * 4 + 6 * 4 + 4  # trailing pad to 8
+
+
+def test_argument_validation_without_gpu():
+    """Pure host-side checks of the ABI return codes (no kernel is launched)."""
+    from mask_bev_b200 import _lib
+    from mask_bev_b200 import functional as F_
+    lib = _lib.load()
+    geo = F_.make_geometry([0.16, 0.16, 40], [-40, -40, -20, 40, 40, 20], 32, 250000, 4, True)
+    assert list(geo.grid) == [500, 500, 1]
+    n = ctypes.c_size_t()
+    assert lib.mbev_voxelize_workspace_bytes(ctypes.byref(geo), 2, 1000, ctypes.byref(n)) == 0 and n.value > 16000
+    assert lib.mbev_voxelize_workspace_bytes(ctypes.byref(geo), 0, 1000, ctypes.byref(n)) == -1
+    assert lib.mbev_voxelize_workspace_bytes(ctypes.byref(geo), 129, 1000, ctypes.byref(n)) == -1
+    geo.num_feats = 2
+    assert lib.mbev_voxelize_workspace_bytes(ctypes.byref(geo), 1, 10, ctypes.byref(n)) == -2
+    with pytest.raises(_lib.MbevError):
+        _lib.check(-3, "x")
+
+
+def test_state_dict_keys_and_shapes_match_upstream():
+    import mask_bev_b200 as M
+    enc = M.MaskBevEncoder(**ref_test_kwargs(feat_channels=(128, 128, 128), T=32))
+    sd = enc.state_dict()
+    exp = {"_voxel_encoder.pfn_layers.0.linear.weight": (64, 11), "_voxel_encoder.pfn_layers.1.linear.weight": (64, 128),
+           "_voxel_encoder.pfn_layers.2.linear.weight": (128, 128), "_voxel_encoder.pfn_layers.0.norm.weight": (64,),
+           "_voxel_encoder.pfn_layers.2.norm.running_var": (128,), "_voxel_encoder.pfn_layers.1.norm.num_batches_tracked": (),
+           "_layer_norm.weight": (128, 500, 500), "_layer_norm.bias": (128, 500, 500)}
+    for k, shp in exp.items():
+        assert k in sd and tuple(sd[k].shape) == shp, k
+    assert len(sd) == 3 * 6 + 2
+    bn = enc._voxel_encoder.pfn_layers[0].norm
+    assert bn.eps == 1e-3 and bn.momentum == 0.01
+    assert enc._voxel_layer.max_voxels == (250000, 250000) and enc._voxel_layer.deterministic
+    assert enc._voxel_layer.grid_size.tolist() == [500, 500, 1]
+    assert (enc._num_voxel_x, enc._num_voxel_y) == (500, 500)
+    # oracle module has the same keys -> checkpoints are interchangeable
+    from oracle import oracle as O
+    pfn = O.make_pfn_oracle(in_channels=4, feat_channels=(128, 128, 128), with_distance=True)
+    assert set(pfn.state_dict()) == {k[len("_voxel_encoder."):] for k in sd if k.startswith("_voxel_encoder.")}
+
+
+def test_cpu_tensors_are_rejected_no_fallback():
+    import mask_bev_b200 as M
+    enc = M.MaskBevEncoder(**ref_test_kwargs())
+    with pytest.raises(M.MbevError, match="no CPU path"):
+        enc([torch.zeros(10, 4)])
+    with pytest.raises(M.MbevError):
+        enc._voxel_layer(torch.zeros(10, 4))
+    with pytest.raises(M.MbevError):
+        enc.middle_encode(torch.zeros(3, 64), torch.zeros(3, 4, dtype=torch.int32), 1)
+    with pytest.raises(NotImplementedError):
+        M.MaskBevEncoder(**{**ref_test_kwargs(), "encoding_type": "cosine"})
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mask_bev_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the oracle in tests only", ""), f"{f} mentions the oracle"
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/mask_bev/models/encoders/mask_bev_encoders.py"),
+                    reason="reference tree only exists in the build container")
+def test_reference_encoder_file_imports_unchanged_against_shims():
+    shim = os.path.join(ROOT, "mask_bev_b200", "shims")
+    saved = list(sys.path)
+    try:
+        sys.path.insert(0, shim)
+        sys.path.insert(0, "/root/reference")
+        for m in [m for m in sys.modules if m.split(".")[0] in ("mmcv", "mmdet3d", "mask_bev")]:
+            del sys.modules[m]
+        mod = importlib.import_module("mask_bev.models.encoders.mask_bev_encoders")
+        import mask_bev_b200 as M
+        assert mod.Voxelization is M.Voxelization and mod.PillarFeatureNet is M.PillarFeatureNet
+        enc = mod.MaskBevEncoder([128, 128, 128], (-40, 40), (-40, 40), (-20, 20), 0.16, 0.16, 40, 32, 'vanilla', 1,
+                                 encoder_params=dict(with_distance=True), pc_point_dim=4)
+        mine = M.MaskBevEncoder([128, 128, 128], (-40, 40), (-40, 40), (-20, 20), 0.16, 0.16, 40, 32, 'vanilla', 1,
+                                encoder_params=dict(with_distance=True), pc_point_dim=4)
+        assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == \
+               {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    finally:
+        sys.path[:] = saved
+        for m in [m for m in sys.modules if m.split(".")[0] in ("mmcv", "mmdet3d", "mask_bev")]:
+            del sys.modules[m]

@@ -136,8 +136,10 @@ def test_encoder_forward_fused_vs_oracle(chans, T, C):
     # full forward incl. nn.LayerNorm([C,ny,nx], eps=1e-3) (mask_bev_encoders.py:92)
     with torch.no_grad():
         full = enc([torch.from_numpy(f).to(DEV) for f in frames])
-        ln = torch.nn.functional.layer_norm(torch.from_numpy(ref), ref.shape[1:], eps=1e-3)
-    assert_close(full.cpu().numpy(), ln.numpy(), tol=2e-5, what="forward with LayerNorm")
+        ln = torch.nn.functional.layer_norm(torch.from_numpy(ref).double(), ref.shape[1:], eps=1e-3)
+    # the LayerNorm is still torch's own CUDA kernel here (row f1 of SURVEY.md §8 is "next"): its fp32 moments over
+    # C*ny*nx = 16-32 M mostly-zero elements are ~2e-4 off the float64 value, so this only checks the wiring
+    assert_close(full.cpu().numpy(), ln.numpy(), tol=1e-3, what="forward with LayerNorm")
 
 
 @pytest.mark.parametrize("chans", [(64,), (128, 128, 128), (16, 32, 64)])

@@ -1,0 +1,186 @@
+"""CPU: pin the oracle. Golden vectors, three voxelizer restatements that must agree, two PFN
+restatements that must agree (dense upstream op sequence vs float64 virtual-row form), A.5 invariants."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from helpers import O, ref_test_kwargs
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+VOX = [O.hard_voxelize_py, O.hard_voxelize_np, O.hard_voxelize_c]
+
+
+def _geo(x=(-40, 40), y=(-40, 40), z=(-20, 20), vs=0.16):
+    return O.encoder_geometry(x, y, z, vs, vs, z[1] - z[0])
+
+
+@pytest.mark.parametrize("name", ["a6_v250000", "a6_v2"])
+@pytest.mark.parametrize("fn", VOX)
+def test_golden_a6(name, fn):
+    g = json.load(open(os.path.join(GOLD, name + ".json")))
+    pts = np.asarray(g["points"], dtype=np.float32)
+    f, src = O.filter_in_range(pts, g["x_range"], g["y_range"], g["z_range"])
+    assert src.tolist() == [0, 1, 3, 4, 5, 7, 8]   # pt 2 fails -40 < -40, pt 6 fails z
+    geo = _geo()
+    v, c, n, k = fn(f, geo["voxel_size"], geo["point_cloud_range"], g["max_num_points"], g["max_voxels"])
+    k = np.where(k >= 0, src[np.clip(k, 0, None)], -1)
+    assert c.tolist() == g["coors_zyx"]
+    assert n.tolist() == g["num_points"]
+    assert k.tolist() == g["kept_idx"]
+    assert v.shape == (len(n), g["max_num_points"], 4)
+    assert np.array_equal(v[0, 1], pts[3]) and np.array_equal(v[1, 0], pts[4])
+
+
+def test_grid_sizes_agree_with_reference_int():
+    """mask_bev_encoders.py:63-64 int() vs mmcv round(float32): must agree for every configured geometry."""
+    for (x, y, vs, n) in [((-40, 40), (-40, 40), 0.16, 500), ((0, 80), (-40, 40), 0.1, 800), ((-40, 40), (-40, 40), 0.1, 800),
+                          ((0, 70.4), (-40, 40), 0.16, 440), ((-51.2, 51.2), (-51.2, 51.2), 0.1, 1024),
+                          ((-75.2, 75.2), (-75.2, 75.2), 0.32, 470)]:
+        geo = _geo(x, y, (-20, 20), vs)
+        assert geo["nx"] == n
+        assert O.grid_size(geo["point_cloud_range"], geo["voxel_size"])[:2] == (geo["nx"], geo["ny"])
+
+
+def test_float32_edge_semantics():
+    """39.999996 passes the strict filter for (+-40, 0.16) but maps to cell 500 and is dropped by the voxelizer."""
+    p = np.array([[39.999996, 0, 0, 0], [0, 0, 0, 0]], np.float32)
+    f, src = O.filter_in_range(p, (-40, 40), (-40, 40), (-20, 20))
+    assert len(f) == 2
+    geo = _geo()
+    for fn in VOX:
+        _, c, n, k = fn(f, geo["voxel_size"], geo["point_cloud_range"], 32, 100)
+        assert c.tolist() == [[0, 250, 250]] and k[0, 0] == 1
+
+
+def test_c_filter_matches_numpy():
+    from mask_bev_b200.synthetic import gen_frame
+    fr = gen_frame(50000, 4, 3)
+    fr[:5] = np.nan
+    a, ia = O.filter_in_range(fr, (0, 70.4), (-40, 40), (-3, 1))
+    b, ib = O.filter_in_range_c(fr, (0, 70.4), (-40, 40), (-3, 1))
+    assert np.array_equal(ia, ib) and np.array_equal(a, b)
+
+
+@settings(max_examples=40, deadline=None)
+@given(n=st.integers(0, 400), T=st.integers(1, 6), V=st.integers(1, 60), seed=st.integers(0, 10 ** 6),
+       spread=st.sampled_from([0.5, 3.0, 45.0]))
+def test_voxelizers_agree_and_invariants(n, T, V, seed, spread):
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-spread, spread, (n, 4)).astype(np.float32)
+    geo = _geo()
+    outs = [fn(pts, geo["voxel_size"], geo["point_cloud_range"], T, V) for fn in VOX]
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    v, c, nump, k = outs[0]
+    P = len(nump)
+    assert P <= V and ((nump >= 1) & (nump <= T)).all()
+    assert len(np.unique(c, axis=0)) == P                       # coords unique
+    if P:
+        assert (np.diff(k[:, 0]) > 0).all()                      # first-appearance order
+        assert ((k >= 0).sum(1) == nump).all()
+        assert nump.sum() <= n
+
+
+def _rand_pillars(rng, P, T, C, geo):
+    nump = rng.integers(1, T + 1, P).astype(np.int32)
+    lin = rng.choice(geo["nx"] * geo["ny"], P, replace=False)
+    coors = np.stack([rng.integers(0, 2, P), np.zeros(P, int), lin // geo["nx"], lin % geo["nx"]], 1).astype(np.int32)
+    cx = (coors[:, 3] + 0.5) * geo["voxel_size"][0] + geo["point_cloud_range"][0]
+    cy = (coors[:, 2] + 0.5) * geo["voxel_size"][1] + geo["point_cloud_range"][1]
+    v = rng.normal(0, 0.05, (P, T, C)).astype(np.float32)
+    v[:, :, 0] += cx[:, None]
+    v[:, :, 1] += cy[:, None]
+    v *= (np.arange(T)[None, :] < nump[:, None])[:, :, None]
+    return v, nump, coors
+
+
+@pytest.mark.parametrize("training", [False, True])
+@pytest.mark.parametrize("chans", [(64,), (16, 32, 64), (128, 128, 128)])
+def test_pfn_dense_vs_sparse_virtual_row(chans, training):
+    """A.4 identity: dense P*T computation == N_k real rows + one weighted virtual row per pillar."""
+    rng = np.random.default_rng(1)
+    geo = _geo()
+    P, T, C = 300, 32, 4
+    v, nump, coors = _rand_pillars(rng, P, T, C, geo)
+    nump[:5] = T                                                   # some full pillars: no virtual row
+    v[:5] = rng.normal(0, 1, (5, T, C)).astype(np.float32)
+    pfn = O.make_pfn_oracle(in_channels=C, feat_channels=chans, with_distance=True, voxel_size=geo["voxel_size"],
+                            point_cloud_range=geo["point_cloud_range"], dtype=torch.float64)
+    O.randomise_pfn(pfn, seed=2)
+    pfn.train(training)
+    sd = {k: t.clone() for k, t in pfn.state_dict().items()}
+    with torch.no_grad():
+        dense = pfn(torch.from_numpy(v).double(), torch.from_numpy(nump), torch.from_numpy(coors)).numpy()
+    L = len(chans)
+    W = [sd[f"pfn_layers.{l}.linear.weight"].numpy() for l in range(L)]
+    bn = [dict(weight=sd[f"pfn_layers.{l}.norm.weight"].numpy(), bias=sd[f"pfn_layers.{l}.norm.bias"].numpy(),
+               running_mean=sd[f"pfn_layers.{l}.norm.running_mean"].numpy(),
+               running_var=sd[f"pfn_layers.{l}.norm.running_var"].numpy()) for l in range(L)]
+    sparse, stats = O.pfn_sparse_np(v, nump, coors, W, bn, geo["voxel_size"], geo["point_cloud_range"], T, training)
+    err = np.abs(dense - sparse).max() / np.abs(dense).max()
+    assert err < 1e-6, err   # float64 both sides; the only fp32 step is upstream's pillar-centre arithmetic
+    if training:   # BatchNorm1d momentum update with the unbiased variance over M = P*T slots
+        M = P * T
+        for l in range(L):
+            rm = 0.99 * sd[f"pfn_layers.{l}.norm.running_mean"].numpy() + 0.01 * stats[l][0]
+            rv = 0.99 * sd[f"pfn_layers.{l}.norm.running_var"].numpy() + 0.01 * stats[l][1] * M / (M - 1)
+            assert np.allclose(pfn.pfn_layers[l].norm.running_mean.numpy(), rm, rtol=1e-6, atol=1e-9)
+            assert np.allclose(pfn.pfn_layers[l].norm.running_var.numpy(), rv, rtol=1e-6, atol=1e-9)
+
+
+def test_legacy_aliasing_and_decoration_layout():
+    """A.3: channels 0..2 of the decorated vector equal the centre offset (7..9); distance = ||centre offset||."""
+    rng = np.random.default_rng(3)
+    geo = _geo()
+    v, nump, coors = _rand_pillars(rng, 50, 8, 4, geo)
+    pfn = O.make_pfn_oracle(in_channels=4, feat_channels=(64,), with_distance=True, voxel_size=geo["voxel_size"],
+                            point_cloud_range=geo["point_cloud_range"])
+    d = pfn.decorate(torch.from_numpy(v), torch.from_numpy(nump), torch.from_numpy(coors)).numpy()
+    assert d.shape == (50, 8, 11)
+    assert np.array_equal(d[..., 0:3], d[..., 7:10])
+    assert np.allclose(d[..., 10], np.linalg.norm(d[..., 7:10], axis=-1), rtol=1e-6)
+    pad = ~(np.arange(8)[None, :] < nump[:, None])
+    assert (d[pad] == 0).all()
+    assert np.array_equal(d[..., 3], v[..., 3])
+
+
+def test_scatter_invariants():
+    rng = np.random.default_rng(4)
+    P, C, ny, nx = 200, 8, 30, 20
+    lin = rng.choice(2 * ny * nx, P, replace=False)
+    coors = np.stack([lin // (ny * nx), np.zeros(P, int), (lin % (ny * nx)) // nx, lin % nx], 1).astype(np.int32)
+    feat = rng.normal(size=(P, C)).astype(np.float32)
+    canvas = O.scatter_np(feat, coors, 2, ny, nx)
+    occ = O.occupancy_np(coors, 2, ny, nx)
+    assert occ.sum() == P
+    assert (canvas[~np.broadcast_to(occ[:, None], canvas.shape)] == 0).all()
+    assert np.array_equal(canvas[coors[:, 0], :, coors[:, 2], coors[:, 3]], feat)
+    # C restatement agrees
+    lib = O._load_c()
+    out = np.zeros_like(canvas)
+    lib.mbev_oracle_scatter(feat.ctypes.data, coors.ctypes.data, P, C, 2, ny, nx, out.ctypes.data)
+    assert np.array_equal(out, canvas)
+
+
+def test_encoder_oracle_shapes_like_reference_tests():
+    """Restates mask_bev_test/models/semantic_kitti/test_point_mask_encoders.py:37-73 on synthetic frames."""
+    from mask_bev_b200.synthetic import gen_frame
+    kw = ref_test_kwargs()
+    orc = O.MaskBevEncoderOracle(feat_channels=kw["feat_channels"], x_range=kw["x_range"], y_range=kw["y_range"],
+                                 z_range=kw["z_range"], voxel_size_x=.16, voxel_size_y=.16, voxel_size_z=40,
+                                 max_num_points=100, pc_point_dim=4, with_distance=True)
+    frames = [gen_frame(8000, 4, 1), gen_frame(9000, 4, 2)]
+    voxels, nump, coors, kept = orc.voxelize(frames)
+    V = len(nump)
+    assert voxels.shape == (V, 100, 4) and nump.shape == (V,) and coors.shape == (V, 4)
+    assert ((nump >= 0) & (nump <= 100)).all() and (coors >= 0).all() and (coors[:, 0] <= 2).all()
+    assert (coors[:, 3] <= 500).all() and (coors[:, 2] <= 500).all() and (coors[:, 1] < 1).all()
+    with torch.no_grad():
+        feats = orc.encode(voxels, nump, coors)
+        assert feats.shape == (V, 64)
+        assert orc.forward(frames).shape == (2, 64, 500, 500)
