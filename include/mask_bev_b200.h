@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 1
+#define MBEV_ABI_VERSION 2
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -73,7 +73,11 @@ typedef struct MbevPfnParams {
   int32_t with_cluster_center, with_voxel_center, with_distance, legacy;
   int32_t voxel_center_dims;         /* 3 (mmdet3d 1.1.0) or 2 (mmdet3d 0.x fossil, mask_bev_encoders.py:165-166) */
   float vx, vy, vz, x_offset, y_offset, z_offset; /* float32(vx), float32(vx/2 + x0) ... */
+  int32_t gemm_path; /* forward Linear layers: MBEV_GEMM_AUTO (tcgen05 3xTF32 when the stack fits it, else fp32 FMA),
+                        MBEV_GEMM_FMA, MBEV_GEMM_TCGEN05 (MBEV_ERR_UNSUPPORTED if the stack does not fit) */
 } MbevPfnParams;
+
+enum { MBEV_GEMM_AUTO = 0, MBEV_GEMM_FMA = 1, MBEV_GEMM_TCGEN05 = 2 };
 
 /* Version / capability probes (host only, no GPU needed). */
 MBEV_API int mbev_abi_version(void);
@@ -119,9 +123,13 @@ MBEV_API int mbev_gather_voxels(const float *points, const int32_t *kept_idx, co
  * does on the padded tensor, writes the folded scale/shift it used into `scale_shift_out`
  * (L x 2 x MBEV_MAX_UNITS floats) and mean / biased variance into `batch_stats_out` (same shape) so the
  * host can update running statistics with momentum 0.01 and the unbiased variance.
+ * Two device implementations share this contract (params->gemm_path): the Linear layers either run on the
+ * tcgen05 tensor cores with every product split 3xTF32 (fp32-accurate: hi*hi + hi*lo + lo*hi in an fp32 TMEM
+ * accumulator), or on the fp32 FMA pipe. mbev_pfn_path() reports which one a call would take.
  * ---------------------------------------------------------------------------------------------- */
 MBEV_API int mbev_pfn_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity, int train,
                              size_t *bytes);
+MBEV_API int mbev_pfn_path(const MbevPfnParams *params, int T); /* MBEV_GEMM_FMA / MBEV_GEMM_TCGEN05, or < 0 */
 MBEV_API int mbev_pfn_forward(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
                      const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity, int T,
                      const MbevPfnParams *params, float *feats, void *workspace, size_t workspace_bytes,

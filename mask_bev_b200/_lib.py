@@ -13,7 +13,8 @@ MAX_BATCH = 128
 MAX_LAYERS = 4
 MAX_UNITS = 128
 MAX_POINT_DIM = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
+GEMM_AUTO, GEMM_FMA, GEMM_TCGEN05 = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libmask_bev_b200.so")
@@ -32,7 +33,8 @@ class MbevPfnParams(ctypes.Structure):
                 ("with_cluster_center", c_int32), ("with_voxel_center", c_int32), ("with_distance", c_int32),
                 ("legacy", c_int32), ("voxel_center_dims", c_int32),
                 ("vx", c_float), ("vy", c_float), ("vz", c_float),
-                ("x_offset", c_float), ("y_offset", c_float), ("z_offset", c_float)]
+                ("x_offset", c_float), ("y_offset", c_float), ("z_offset", c_float),
+                ("gemm_path", c_int32)]
 
 
 _PTRS = c_void_p * MAX_LAYERS
@@ -49,6 +51,7 @@ SIGNATURES = {
     "mbev_voxelize": (c_int, [_v, POINTER(c_int64), c_int, _G, _v, _v, _v, _v, _v, c_int64, _v, c_size_t, _v]),
     "mbev_gather_voxels": (c_int, [_v, _v, _v, _v, c_int64, c_int, c_int, _v, _v]),
     "mbev_pfn_workspace_bytes": (c_int, [_P, c_int, c_int64, c_int, POINTER(c_size_t)]),
+    "mbev_pfn_path": (c_int, [_P, c_int]),
     "mbev_pfn_forward": (c_int, [_v, c_int, _v, _v, _v, _v, c_int64, c_int, _P, _v, _v, c_size_t, _v]),
     "mbev_pfn_forward_train": (c_int, [_v, c_int, _v, _v, _v, _v, c_int64, c_int, _P, POINTER(_PTRS),
                                        POINTER(_PTRS), c_float, _v, _v, _v, _v, c_size_t, _v]),

@@ -20,7 +20,10 @@
 // STATS mode for layer s = 0..L-1 (layers < s applied with the statistics already known, layer s only
 // accumulates sum / sum-of-squares in fp64, fixed reduction order => run-to-run identical), then once in
 // FULL mode.
+#include <algorithm>
+
 #include "common.cuh"
+#include "pfn_tc.cuh"
 
 namespace mbev {
 namespace {
@@ -531,22 +534,57 @@ int launch_pfn(const Plan &pl, const float *rows, const int32_t *kept_idx, const
   return MBEV_OK;
 }
 
+// Which implementation runs the Linear layers of this stack: MBEV_GEMM_TCGEN05 / MBEV_GEMM_FMA, or < 0.
+int select_path(const MbevPfnParams *p, int C, int T) {
+  if (!p) return MBEV_ERR_BAD_ARG;
+  if (p->gemm_path == MBEV_GEMM_FMA) return MBEV_GEMM_FMA;
+  tc::Plan tp;
+  const int st = tc::make_plan(p, C, T, nullptr, &tp);
+  if (st == MBEV_OK) return MBEV_GEMM_TCGEN05;
+  if (st == MBEV_ERR_UNSUPPORTED && p->gemm_path == MBEV_GEMM_AUTO) return MBEV_GEMM_FMA;
+  return st;
+}
+
+int raw_point_dim(const MbevPfnParams *p) {
+  // C only affects D0 consistency, which in_dim[0] pins: recover it from in_dim[0]
+  const int extra = (p->with_cluster_center ? 3 : 0) + (p->with_voxel_center ? p->voxel_center_dims : 0) +
+                    (p->with_distance ? 1 : 0);
+  return p->in_dim[0] - extra;
+}
+
 }  // namespace
 }  // namespace mbev
 
 using namespace mbev;
 
+extern "C" int mbev_pfn_path(const MbevPfnParams *params, int T) {
+  if (!params) return MBEV_ERR_BAD_ARG;
+  const int path = select_path(params, raw_point_dim(params), T);
+  if (path == MBEV_GEMM_FMA) {  // validate the stack against the FMA kernel's own limits
+    Plan pl;
+    const int st = make_plan(params, raw_point_dim(params), T, nullptr, &pl);
+    if (st) return st;
+  }
+  return path;
+}
+
 extern "C" int mbev_pfn_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity, int train,
                                         size_t *bytes) {
   (void)pillar_capacity;
   (void)train;
-  if (!bytes) return MBEV_ERR_BAD_ARG;
+  if (!bytes || !params) return MBEV_ERR_BAD_ARG;
+  const int C = raw_point_dim(params);
+  const int path = select_path(params, C, T);
+  if (path < 0) return path;
+  if (path == MBEV_GEMM_TCGEN05) {
+    tc::Plan tp;
+    const int st = tc::make_plan(params, C, T, nullptr, &tp);
+    if (st) return st;
+    *bytes = tp.ws_bytes;
+    return MBEV_OK;
+  }
   Plan pl;
-  // C only affects D0 consistency, which in_dim[0] pins: recover it from in_dim[0]
-  if (!params) return MBEV_ERR_BAD_ARG;
-  const int extra = (params->with_cluster_center ? 3 : 0) + (params->with_voxel_center ? params->voxel_center_dims : 0) +
-                    (params->with_distance ? 1 : 0);
-  const int st = make_plan(params, params->in_dim[0] - extra, T, nullptr, &pl);
+  const int st = make_plan(params, C, T, nullptr, &pl);
   if (st) return st;
   *bytes = pl.ws_bytes;
   return MBEV_OK;
@@ -560,6 +598,22 @@ extern "C" int mbev_pfn_forward(const float *rows, int C, const int32_t *kept_id
   if (pillar_capacity <= 0) return MBEV_OK;
   if (!rows) return MBEV_ERR_BAD_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int path = select_path(params, C, T);
+  if (path < 0) return path;
+  if (path == MBEV_GEMM_TCGEN05) {
+    tc::Plan tp;
+    int st = tc::make_plan(params, C, T, workspace, &tp);
+    if (st) return st;
+    if (workspace_bytes < tp.ws_bytes) return MBEV_ERR_WORKSPACE;
+    for (int l = 0; l < tp.k.L; ++l) {
+      if (!params->scale[l] || !params->shift[l]) return MBEV_ERR_BAD_ARG;
+      tp.k.scale[l] = params->scale[l];
+      tp.k.shift[l] = params->shift[l];
+    }
+    st = tc::launch_prep(params, tp, stream);
+    if (st) return st;
+    return tc::launch(tp, rows, kept_idx, num_points, coors, num_pillars_dev, feats, -1, stream);
+  }
   Plan pl;
   int st = make_plan(params, C, T, workspace, &pl);
   if (st) return st;
@@ -585,6 +639,32 @@ extern "C" int mbev_pfn_forward_train(const float *rows, int C, const int32_t *k
   if (pillar_capacity <= 0) return MBEV_OK;
   if (!rows) return MBEV_ERR_BAD_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int path = select_path(params, C, T);
+  if (path < 0) return path;
+  if (path == MBEV_GEMM_TCGEN05) {
+    tc::Plan tp;
+    int st = tc::make_plan(params, C, T, workspace, &tp);
+    if (st) return st;
+    if (workspace_bytes < tp.ws_bytes) return MBEV_ERR_WORKSPACE;
+    st = tc::launch_prep(params, tp, stream);
+    if (st) return st;
+    for (int l = 0; l < tp.k.L; ++l) {
+      if (!gamma[l] || !beta[l]) return MBEV_ERR_BAD_ARG;
+      tp.k.scale[l] = scale_shift_out + (2 * l) * MBEV_MAX_UNITS;
+      tp.k.shift[l] = scale_shift_out + (2 * l + 1) * MBEV_MAX_UNITS;
+    }
+    for (int s = 0; s < tp.k.L; ++s) {
+      st = tc::launch(tp, rows, kept_idx, num_points, coors, num_pillars_dev, feats, s, stream);
+      if (st) return st;
+      const int U = tp.k.U[s];
+      k_stats_finalize<<<(U + 127) / 128, 128, 0, stream>>>(
+          tp.k.partials, tp.grid, tp.k.um, U, num_pillars_dev, T, gamma[s], beta[s], eps,
+          scale_shift_out + (2 * s) * MBEV_MAX_UNITS, scale_shift_out + (2 * s + 1) * MBEV_MAX_UNITS,
+          batch_stats_out + (2 * s) * MBEV_MAX_UNITS, batch_stats_out + (2 * s + 1) * MBEV_MAX_UNITS);
+      MBEV_CHECK_LAUNCH();
+    }
+    return tc::launch(tp, rows, kept_idx, num_points, coors, num_pillars_dev, feats, -1, stream);
+  }
   Plan pl;
   int st = make_plan(params, C, T, workspace, &pl);
   if (st) return st;

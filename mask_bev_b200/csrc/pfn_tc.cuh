@@ -1,0 +1,695 @@
+// K2-TC — pillar feature net forward on the 5th-generation tensor cores (tcgen05 / TMEM, sm_100a).
+//
+// Same contract as k_pfn in pfn.cu (mmdet3d PillarFeatureNet.forward / PFNLayer.forward as called from
+// mask_bev_encoders.py:119-120): compact rows = stored points + one weighted virtual row per
+// padded pillar, every activation on chip, HBM traffic = gathered points in + (pillar, C_out) features out.
+// What changes is where the Linear layers run:
+//
+//   * one CTA per SM, 128 threads = 128 TMEM lanes = one chunk of <= 128 rows (whole pillars, greedily packed
+//     from the CTA's contiguous pillar range). Thread r owns row r from decoration to the last layer.
+//   * layer input A (128 x K_l) lives in TENSOR MEMORY, written by its owning thread with tcgen05.st; the
+//     weights B = nn.Linear.weight (U_l x K_l, K-major — the layout PyTorch already stores) stay resident in
+//     shared memory for the whole kernel (one cp.async.bulk per CTA); D (128 x U_l fp32) accumulates in TMEM.
+//     tcgen05.mma.cta_group::1.kind::tf32, A from TMEM, B through a no-swizzle K-major shared-memory descriptor.
+//   * fp32 parity (1e-5) rules out plain TF32, so every product is split 3xTF32:  a = ah + al, w = wh + wl
+//     (each part exactly representable in TF32, round-to-nearest), D = al*wh + ah*wl + ah*wh in the fp32
+//     accumulator. The dropped al*wl term is ~2^-22 relative. 3 MMAs per K-step at 2048 MAC/clk/SM is still
+//     ~9x the fp32 FMA pipe (128 MAC/clk/SM).
+//   * the concat [x || max_p] is kept as upstream has it (K_l = 2 U_{l-1}): the per-pillar max is replicated
+//     into the second K-half of each row of A, so the pillar term rides in the same accumulator and the
+//     epilogue needs no per-pillar add.
+//   * epilogue per 32 columns: tcgen05.ld -> BN scale/shift + ReLU in registers -> (x half of next A: split,
+//     tcgen05.st) -> transpose through a 128x33 shared scratch -> one thread per column walks the rows of its
+//     pillars (segmented max, warp-uniform control flow) and writes the max back over the rows -> each row
+//     thread reads its pillar's max, splits it and stores the max half of the next A. Last layer: the column
+//     threads store the pillar max straight to HBM (coalesced 128 B per warp).
+//   * train mode: STATS launches accumulate sum / sum-of-squares of the pre-BN output of layer s in fp64 in the
+//     column phase (fixed order: static pillar partition -> run-to-run identical), as k_pfn does.
+//
+// Supported when every U_l is a multiple of 32 and <= 128, every K_l <= 128, T + 1 <= 128 and the weight image
+// fits shared memory ([128,128,128], [128,64,128], [64], ...). Other stacks run on the fp32-FMA kernel.
+#pragma once
+#include "common.cuh"
+
+namespace mbev {
+namespace tc {
+
+constexpr int kEpiThreads = 256;            // 8 epilogue warps
+constexpr int kThreads = kEpiThreads + 32;  // + the MMA issuer warp
+constexpr int kRows = 128;      // rows per chunk = TMEM lanes = MMA M
+constexpr int kPcap = 64;       // pillars per chunk (>= 128 / 2: a padded pillar has >= 2 rows)
+constexpr int kScrPitch = 33;   // transposition scratch [128][33] floats
+constexpr int kDecoPitch = 20;  // decorated layer-0 input staging [128][20] floats (float4-aligned, conflict-free)
+constexpr int kPtPitch = 8;
+constexpr int kK0Pad = 16;
+constexpr uint32_t kColAH = 0, kColAL = 128, kColD = 256, kTmemCols = 512;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct Kargs {
+  int L;
+  int K[MBEV_MAX_LAYERS];   // Linear.in_features
+  int Kp[MBEV_MAX_LAYERS];  // padded to a multiple of 8 (one tf32 MMA K-step)
+  int U[MBEV_MAX_LAYERS];
+  uint32_t w_off[MBEV_MAX_LAYERS][2];  // byte offset of the hi / lo weight image of layer l (global image == smem image)
+  uint32_t w_bytes;
+  const float *w_img;
+  const float *scale[MBEV_MAX_LAYERS];
+  const float *shift[MBEV_MAX_LAYERS];
+  int C, D0, T;
+  int cluster, vcenter, dist, legacy, vcd;
+  float vx, vy, vz, xo, yo, zo;
+  int um;
+  uint32_t o_scr, o_ss, o_tab, o_bar;  // byte offsets in dynamic shared memory
+  int smem_bytes;
+  int stat_layer;    // -1: full forward; s: accumulate the statistics of layer s and stop
+  double *partials;  // (gridDim.x, 2, um)
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]   (M = 128, N and dtypes from idesc; K = 8 for tf32)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+      "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2,
+// a/b K-major (bits 15,16 = 0), n_dim [17,23) = N>>3, m_dim [24,29) = M>>4.
+__device__ __forceinline__ uint32_t make_idesc(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(kRows >> 4) << 24);
+}
+// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): in 16-byte units the
+// operand is ((8,n),2):((1,SBO),LBO) — 8 rows x 16 B core matrices, SBO between 8-row groups, LBO between the
+// two 16-byte K-chunks of one K=8 step. version [46,48) = 1, layout_type [61,64) = 0.
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+#define MBEV_R8(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+#define MBEV_I8(v, o) "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
+
+// lane i of the warp <- 32 consecutive columns of TMEM lane (quadrant base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : MBEV_R8(v, 0), MBEV_R8(v, 8), MBEV_R8(v, 16), MBEV_R8(v, 24)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : MBEV_R8(v, 0), MBEV_R8(v, 8)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};" ::MBEV_I8(v, 0),
+      MBEV_I8(v, 8), MBEV_I8(v, 16), MBEV_I8(v, 24), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};" ::MBEV_I8(v, 0),
+      MBEV_I8(v, 8), "r"(taddr)
+      : "memory");
+}
+
+// x = hi + lo (+ <= 2^-22 |x|), both exactly representable in TF32 so the tensor core's own conversion is the identity
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = __fsub_rn(x, __uint_as_float(hi));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------------------
+// Warp roles: warps 0-7 = 256 epilogue threads (thread (row, h): row = 32*(warp&3)+lane owns TMEM lane `row`,
+// h = warp>>2 owns columns 16h..16h+15 of every 32-column slab); warp 8 = MMA issuer (one elected lane).
+// Handshakes: slab ring (8 mbarriers, 256 arrivals each): "a K-slab of the next layer's input is in TMEM";
+// bar_d[2] (tcgen05.commit): "the accumulator of a layer is complete"; accumulators alternate D0 / D1 so the
+// MMAs of layer l+1 start on the first finished K-slab while layer l's epilogue is still draining its D.
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, const int *__restrict__ num_points,
+         const int *__restrict__ coors, const int *__restrict__ num_pillars, float *__restrict__ feats,
+         const __grid_constant__ Kargs k) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = k.T;
+  float *s_scr = reinterpret_cast<float *>(smem_raw + k.o_scr);
+  float *s_pts = s_scr;                      // [128][8]   dead once the layer-0 input is built
+  float *s_deco = s_scr + kRows * kPtPitch;  // [128][20]
+  float *s_ss = reinterpret_cast<float *>(smem_raw + k.o_ss);  // [L][2][128]
+  int *s_n = reinterpret_cast<int *>(smem_raw + k.o_tab);      // [64]
+  int *s_prow0 = s_n + kPcap;                                  // [65] (+3 pad)
+  int *s_rinfo = s_prow0 + kPcap + 4;                          // [129] (+3 pad): first row of the row's pillar | pillar << 8
+  float *s_roww = reinterpret_cast<float *>(s_rinfo + kRows + 4);  // [128]
+  float *s_mean = s_roww + kRows;                              // [64][4]
+  float *s_ctr = s_mean + kPcap * 4;                           // [64][4]
+  int *s_misc = reinterpret_cast<int *>(s_ctr + kPcap * 4);    // [8]: scan carries, counts, [7] = continue flag
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + k.o_bar);  // [0] weights, [1..2] D ready, [3..10] slab ring
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 11);
+  const uint32_t bar_w = smem_u32(s_bar), bar_d = smem_u32(s_bar + 1), bar_slab = smem_u32(s_bar + 3);
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const int last_layer = (k.stat_layer >= 0) ? k.stat_layer : k.L - 1;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_d, 1);
+    mbar_init(bar_d + 8, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(bar_slab + 8 * i, kEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == kEpiThreads / 32) tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  for (int l = 0; l < k.L; ++l) {
+    if (k.stat_layer < 0 || l < k.stat_layer) {
+      for (int i = tid; i < k.U[l]; i += kThreads) {
+        s_ss[(2 * l) * MBEV_MAX_UNITS + i] = __ldg(k.scale[l] + i);
+        s_ss[(2 * l + 1) * MBEV_MAX_UNITS + i] = __ldg(k.shift[l] + i);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == kEpiThreads / 32) {
+    // =========================================== MMA issuer ===================================================
+    // every lane walks the handshakes (warp-uniform control flow); lane 0 alone issues copies, MMAs and commits
+    const bool leader = lane == 0;
+    if (leader) {
+      mbar_expect_tx(bar_w, k.w_bytes);  // weights: global image -> shared memory, resident for the whole kernel
+      for (uint32_t off = 0; off < k.w_bytes; off += 32768u)
+        bulk_g2s(smem_base + off, reinterpret_cast<const char *>(k.w_img) + off, min(32768u, k.w_bytes - off), bar_w);
+    }
+    __syncwarp();
+    mbar_wait(bar_w, 0);
+    uint32_t ev = 0;
+    for (;;) {
+      mbar_wait(bar_slab + 8 * (ev & 7), (ev >> 3) & 1);  // layer-0 input of the next chunk, or the stop signal
+      ++ev;
+      if (*reinterpret_cast<volatile int *>(s_misc + 7) == 0) break;
+      tc_fence_after();
+      for (int l = 0; l <= last_layer; ++l) {
+        const int U = k.U[l];
+        const uint32_t idesc = make_idesc(U);
+        const uint32_t lbo = static_cast<uint32_t>(U) * 16u, kstep = 2u * lbo;
+        const uint32_t d_col = tmem + kColD + ((l & 1) ? 128u : 0u);
+        const uint32_t bh = smem_base + k.w_off[l][0], bl = smem_base + k.w_off[l][1];
+        uint32_t acc = 0;
+        // K-slabs in the order the epilogue of layer l-1 finishes them: x(0), max(0), x(1), max(1), ...
+        const int nslab = (l == 0) ? 1 : 2 * (k.U[l - 1] >> 5);
+        for (int s = 0; s < nslab; ++s) {
+          int kcol, nks;
+          if (l == 0) {
+            kcol = 0;
+            nks = k.Kp[0] >> 3;
+          } else {
+            mbar_wait(bar_slab + 8 * (ev & 7), (ev >> 3) & 1);
+            ++ev;
+            tc_fence_after();
+            kcol = ((s & 1) ? k.U[l - 1] : 0) + 32 * (s >> 1);
+            nks = 4;
+          }
+          if (leader) {
+            const uint32_t koff = kstep * static_cast<uint32_t>(kcol >> 3);
+#pragma unroll 1
+            for (int j = 0; j < nks; ++j) {  // al*wh, ah*wl, ah*wh : small terms first
+              const uint64_t dh = make_bdesc(bh + koff + kstep * j, lbo, 128u);
+              const uint64_t dl = make_bdesc(bl + koff + kstep * j, lbo, 128u);
+              const uint32_t ac = static_cast<uint32_t>(kcol + 8 * j);
+              mma_tf32_ts(d_col, tmem + kColAL + ac, dh, idesc, acc);
+              mma_tf32_ts(d_col, tmem + kColAH + ac, dl, idesc, 1u);
+              mma_tf32_ts(d_col, tmem + kColAH + ac, dh, idesc, 1u);
+              acc = 1;
+            }
+          }
+          __syncwarp();
+        }
+        if (leader) tc_commit(bar_d + 8 * (l & 1));
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================================== epilogue warps ===============================================
+    const int row = ((warp & 3) << 5) | lane, h = warp >> 2;
+    const uint32_t tlane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);  // this warp's TMEM lane quadrant
+    const int P = *num_pillars;
+    const int p_begin = static_cast<int>(static_cast<int64_t>(P) * blockIdx.x / gridDim.x);
+    const int p_end = static_cast<int>(static_cast<int64_t>(P) * (blockIdx.x + 1) / gridDim.x);
+    uint32_t ev = 0, par_d0 = 0, par_d1 = 0;
+    double st1[4] = {0.0, 0.0, 0.0, 0.0}, st2[4] = {0.0, 0.0, 0.0, 0.0};
+
+    for (int p = p_begin; p < p_end;) {
+      epi_sync();  // previous chunk is done with the tables and the scratch
+      // ---- pack whole pillars p, p+1, ... into <= 128 rows (<= 64 pillars) ----------------------------------
+      const bool cand = tid < kPcap && p + tid < p_end;
+      const int n_i = cand ? __ldg(num_points + p + tid) : 0;
+      const int need = cand ? n_i + (n_i < T ? 1 : 0) : 0;
+      int incl = need;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31 && warp < 2) s_misc[warp] = incl;
+      epi_sync();
+      if (warp == 1) incl += s_misc[0];
+      const bool fits = cand && incl <= kRows;
+      const unsigned bal = __ballot_sync(0xffffffffu, fits);
+      if (lane == 0 && warp < 2) s_misc[4 + warp] = __popc(bal);
+      if (fits) {
+        s_n[tid] = n_i;
+        s_prow0[tid + 1] = incl;
+        const int r0 = incl - need;
+        for (int t = 0; t < need; ++t) s_rinfo[r0 + t] = r0 | (tid << 8);
+        const int4 c = __ldg(reinterpret_cast<const int4 *>(coors) + p + tid);  // (b, z, y, x)
+        // upstream: coors.type_as(features) * vx + x_offset — float32 multiply THEN add (no FMA contraction)
+        s_ctr[tid * 4 + 0] = __fadd_rn(__fmul_rn(static_cast<float>(c.w), k.vx), k.xo);
+        s_ctr[tid * 4 + 1] = __fadd_rn(__fmul_rn(static_cast<float>(c.z), k.vy), k.yo);
+        s_ctr[tid * 4 + 2] = __fadd_rn(__fmul_rn(static_cast<float>(c.y), k.vz), k.zo);
+      }
+      if (tid == 0) s_prow0[0] = 0;
+      epi_sync();
+      const int npil = s_misc[4] + s_misc[5];  // fits is prefix-closed: the count of leading pillars taken
+      const int nrows = s_prow0[npil];
+      if (tid == 0) s_rinfo[nrows] = nrows;  // sentinel: "a new pillar starts here"
+      // ---- gather this row's point (h == 0 threads) ---------------------------------------------------------
+      int pl = 0;
+      bool real = false;
+      if (h == 0) {
+        int n = 0, t = 0;
+        const bool inrange = row < nrows;
+        if (inrange) {
+          const int info = s_rinfo[row];
+          pl = info >> 8;
+          t = row - (info & 255);
+          n = s_n[pl];
+          real = t < n;
+        }
+        s_roww[row] = inrange ? (real ? 1.f : static_cast<float>(T - n)) : 0.f;
+        if (real) {
+          const size_t slot = static_cast<size_t>(p + pl) * T + t;
+          const int src = kept_idx ? __ldg(kept_idx + slot) : static_cast<int>(slot);
+          const float *pp = rows_src + static_cast<size_t>(src) * k.C;
+          float *dst = s_pts + row * kPtPitch;
+          if (k.C == 4) {
+            *reinterpret_cast<float4 *>(dst) = __ldg(reinterpret_cast<const float4 *>(pp));
+          } else {
+            for (int c = 0; c < k.C; ++c) dst[c] = __ldg(pp + c);
+          }
+        }
+      }
+      epi_sync();
+      if (tid < npil) {  // cluster mean: sum over the pillar's slots in slot order / num_points
+        const int n = s_n[tid];
+        const float *pp = s_pts + s_prow0[tid] * kPtPitch;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int t = 0; t < n; ++t) {
+          sx = __fadd_rn(sx, pp[t * kPtPitch + 0]);
+          sy = __fadd_rn(sy, pp[t * kPtPitch + 1]);
+          sz = __fadd_rn(sz, pp[t * kPtPitch + 2]);
+        }
+        const float fn = static_cast<float>(n);
+        s_mean[tid * 4 + 0] = __fdiv_rn(sx, fn);
+        s_mean[tid * 4 + 1] = __fdiv_rn(sy, fn);
+        s_mean[tid * 4 + 2] = __fdiv_rn(sz, fn);
+      }
+      epi_sync();
+      // ---- decoration -> layer-0 input row (staged through shared memory so that the registers are statically
+      //      indexed), split and stored to TMEM lanes ----------------------------------------------------------
+      if (h == 0) {
+        float *xd = s_deco + row * kDecoPitch;
+#pragma unroll
+        for (int d = 0; d < kK0Pad; ++d) xd[d] = 0.f;  // virtual rows, chunk padding and the K padding
+        if (real) {
+          const float *pp = s_pts + row * kPtPitch;
+          const float x = pp[0], y = pp[1], z = pp[2];
+          const float ex = __fsub_rn(x, s_ctr[pl * 4 + 0]), ey = __fsub_rn(y, s_ctr[pl * 4 + 1]),
+                      ez = __fsub_rn(z, s_ctr[pl * 4 + 2]);
+          const bool alias = k.vcenter && k.legacy;  // legacy: centre offset written in place over xyz
+          const float r0 = alias ? ex : x, r1 = alias ? ey : y, r2 = alias ? ez : z;
+          int d = 0;
+          xd[d++] = r0;
+          xd[d++] = r1;
+          xd[d++] = r2;
+          for (int c = 3; c < k.C; ++c) xd[d++] = pp[c];
+          if (k.cluster) {
+            xd[d++] = __fsub_rn(x, s_mean[pl * 4 + 0]);
+            xd[d++] = __fsub_rn(y, s_mean[pl * 4 + 1]);
+            xd[d++] = __fsub_rn(z, s_mean[pl * 4 + 2]);
+          }
+          if (k.vcenter) {
+            xd[d++] = ex;
+            xd[d++] = ey;
+            if (k.vcd > 2) xd[d++] = ez;
+          }
+          if (k.dist)
+            xd[d++] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)), __fmul_rn(r2, r2)));
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 v = *reinterpret_cast<const float4 *>(xd + 4 * j4);
+          split_tf32(v.x, hi[4 * j4 + 0], lo[4 * j4 + 0]);
+          split_tf32(v.y, hi[4 * j4 + 1], lo[4 * j4 + 1]);
+          split_tf32(v.z, hi[4 * j4 + 2], lo[4 * j4 + 2]);
+          split_tf32(v.w, hi[4 * j4 + 3], lo[4 * j4 + 3]);
+        }
+        tmem_st16(tlane + kColAH, hi);
+        tmem_st16(tlane + kColAL, lo);
+        tc_wait_st();
+      }
+      if (tid == 0) s_misc[7] = 1;
+      tc_fence_before();
+      mbar_arrive(bar_slab + 8 * (ev & 7));
+      ++ev;
+
+      // ---- layers -------------------------------------------------------------------------------------------
+      for (int l = 0; l <= last_layer; ++l) {
+        const int U = k.U[l];
+        const bool stats = (l == k.stat_layer);
+        const bool last = (l == k.L - 1);
+        const uint32_t d_col = kColD + ((l & 1) ? 128u : 0u);
+        if (l & 1) {
+          mbar_wait(bar_d + 8, par_d1);
+          par_d1 ^= 1u;
+        } else {
+          mbar_wait(bar_d, par_d0);
+          par_d0 ^= 1u;
+        }
+        tc_fence_after();
+        const int nq = U >> 5;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < nq) {
+            float a[16];
+            {
+              uint32_t v[16];
+              tmem_ld16(tlane + d_col + 32u * q + 16u * h, v);
+              tc_wait_ld();
+              if (stats) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) a[j] = __uint_as_float(v[j]);
+              } else {
+                const float4 *sc4 = reinterpret_cast<const float4 *>(s_ss + (2 * l) * MBEV_MAX_UNITS + 32 * q + 16 * h);
+                const float4 *sh4 = reinterpret_cast<const float4 *>(s_ss + (2 * l + 1) * MBEV_MAX_UNITS + 32 * q + 16 * h);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 sc = sc4[j4], sh = sh4[j4];
+                  a[4 * j4 + 0] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), sc.x, sh.x), 0.f);
+                  a[4 * j4 + 1] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y), 0.f);
+                  a[4 * j4 + 2] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z), 0.f);
+                  a[4 * j4 + 3] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w), 0.f);
+                }
+              }
+            }
+            if (!last && !stats) {  // x half of the next layer's input: K index = unit index
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) split_tf32(a[j], hi[j], lo[j]);
+              tmem_st16(tlane + kColAH + 32u * q + 16u * h, hi);
+              tmem_st16(tlane + kColAL + 32u * q + 16u * h, lo);
+              tc_wait_st();
+              tc_fence_before();
+              mbar_arrive(bar_slab + 8 * (ev & 7));
+              ++ev;
+            }
+            {
+              float *dst = s_scr + row * kScrPitch + 16 * h;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dst[j] = a[j];
+            }
+            epi_sync();
+            // column phase: thread (warp g, lane c) owns column 32q+c over the rows of pillars [npil*g/8, npil*(g+1)/8)
+            {
+              const int ra = s_prow0[(npil * warp) >> 3], rb = s_prow0[(npil * (warp + 1)) >> 3];
+              float *col = s_scr + lane;
+              if (stats) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int r = ra; r < rb; ++r) {
+                  const double y = static_cast<double>(col[r * kScrPitch]);
+                  const double w = static_cast<double>(s_roww[r]);
+                  s1 += w * y;
+                  s2 += w * y * y;
+                }
+                st1[q] += s1;
+                st2[q] += s2;
+              } else {
+                float mx = 0.f;  // post-ReLU values are >= 0
+                int first = ra;
+#pragma unroll 4
+                for (int r = ra; r < rb; ++r) {
+                  mx = fmaxf(mx, col[r * kScrPitch]);
+                  const int nxt = s_rinfo[r + 1];
+                  if ((nxt & 255) == r + 1) {  // r closes its pillar
+                    if (last) {
+                      const int pp = s_rinfo[r] >> 8;
+                      feats[static_cast<size_t>(p + pp) * U + 32 * q + lane] = mx;
+                    } else {
+                      col[first * kScrPitch] = mx;  // parked in the pillar's first row
+                    }
+                    mx = 0.f;
+                    first = r + 1;
+                  }
+                }
+              }
+            }
+            epi_sync();
+            if (!last && !stats) {  // max half of the next layer's input: K index = U + unit index
+              const int fr = row < nrows ? (s_rinfo[row] & 255) : row;  // chunk padding rows: any finite value
+              const float *src = s_scr + fr * kScrPitch + 16 * h;
+              float m[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) m[j] = src[j];
+              epi_sync();  // scratch may be overwritten by the next slab from here on
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) split_tf32(m[j], hi[j], lo[j]);
+              tmem_st16(tlane + kColAH + static_cast<uint32_t>(U) + 32u * q + 16u * h, hi);
+              tmem_st16(tlane + kColAL + static_cast<uint32_t>(U) + 32u * q + 16u * h, lo);
+              tc_wait_st();
+              tc_fence_before();
+              mbar_arrive(bar_slab + 8 * (ev & 7));
+              ++ev;
+            }
+          }
+        }
+      }
+      p += npil;
+    }
+    // stop signal for the MMA issuer
+    epi_sync();
+    if (tid == 0) s_misc[7] = 0;
+    mbar_arrive(bar_slab + 8 * (ev & 7));
+
+    if (k.stat_layer >= 0) {
+      // deterministic CTA reduction: the 8 warps' partials of each column are summed in warp order
+      double *red = reinterpret_cast<double *>(s_scr);  // [8][2][128] = 16 KB
+      const int U = k.U[k.stat_layer];
+      const int nq = U >> 5;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q < nq) {
+          red[(warp * 2 + 0) * MBEV_MAX_UNITS + 32 * q + lane] = st1[q];
+          red[(warp * 2 + 1) * MBEV_MAX_UNITS + 32 * q + lane] = st2[q];
+        }
+      }
+      epi_sync();
+      for (int u = tid; u < U; u += kEpiThreads) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          a += red[(g * 2 + 0) * MBEV_MAX_UNITS + u];
+          b += red[(g * 2 + 1) * MBEV_MAX_UNITS + u];
+        }
+        k.partials[(static_cast<size_t>(blockIdx.x) * 2 + 0) * k.um + u] = a;
+        k.partials[(static_cast<size_t>(blockIdx.x) * 2 + 1) * k.um + u] = b;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiThreads / 32) tmem_dealloc(tmem, kTmemCols);
+}
+
+// nn.Linear weights (U_l, K_l) -> hi / lo TF32 images in the UMMA K-major no-swizzle layout:
+// 16-byte unit (kchunk = kk/4, u) at ((kchunk * U + u) * 4 + kk%4) floats; K zero-padded to Kp.
+struct PrepArgs {
+  int L;
+  int K[MBEV_MAX_LAYERS], Kp[MBEV_MAX_LAYERS], U[MBEV_MAX_LAYERS];
+  const float *w[MBEV_MAX_LAYERS];
+  float *hi[MBEV_MAX_LAYERS], *lo[MBEV_MAX_LAYERS];
+};
+
+__global__ void k_prep_weights_tc(const PrepArgs a) {
+  const int l = blockIdx.y;
+  if (l >= a.L) return;
+  const int K = a.K[l], Kp = a.Kp[l], U = a.U[l];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < U * Kp; i += gridDim.x * blockDim.x) {
+    const int u = i / Kp, kk = i - u * Kp;
+    const float v = kk < K ? __ldg(a.w[l] + static_cast<size_t>(u) * K + kk) : 0.f;
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    const int idx = (((kk >> 2) * U + u) << 2) + (kk & 3);
+    a.hi[l][idx] = __uint_as_float(hi);
+    a.lo[l][idx] = __uint_as_float(lo);
+  }
+}
+
+struct Plan {
+  Kargs k;
+  PrepArgs prep;
+  size_t ws_bytes;
+  int grid;
+};
+
+// MBEV_OK when the stack fits the tensor-core kernel, MBEV_ERR_UNSUPPORTED when it must run on the FMA kernel.
+inline int make_plan(const MbevPfnParams *p, int C, int T, void *ws, Plan *out) {
+  if (!p || p->num_layers < 1 || p->num_layers > MBEV_MAX_LAYERS) return MBEV_ERR_BAD_ARG;
+  if (C < 3 || C > MBEV_MAX_POINT_DIM || T < 1) return MBEV_ERR_UNSUPPORTED;
+  if (T + 1 > kRows) return MBEV_ERR_UNSUPPORTED;  // a pillar and its virtual row must fit one chunk
+  Kargs &k = out->k;
+  k = Kargs();
+  PrepArgs &pa = out->prep;
+  pa = PrepArgs();
+  k.L = pa.L = p->num_layers;
+  k.C = C;
+  k.T = T;
+  k.cluster = p->with_cluster_center != 0;
+  k.vcenter = p->with_voxel_center != 0;
+  k.dist = p->with_distance != 0;
+  k.legacy = p->legacy != 0;
+  k.vcd = p->voxel_center_dims;
+  if (k.vcenter && k.vcd != 2 && k.vcd != 3) return MBEV_ERR_BAD_ARG;
+  k.D0 = C + (k.cluster ? 3 : 0) + (k.vcenter ? k.vcd : 0) + (k.dist ? 1 : 0);
+  if (k.D0 > kK0Pad) return MBEV_ERR_UNSUPPORTED;
+  k.vx = p->vx; k.vy = p->vy; k.vz = p->vz;
+  k.xo = p->x_offset; k.yo = p->y_offset; k.zo = p->z_offset;
+  int um = 0;
+  uint32_t off = 0;
+  for (int l = 0; l < k.L; ++l) {
+    const int U = p->units[l];
+    if (U < 32 || (U & 31) || U > MBEV_MAX_UNITS) return MBEV_ERR_UNSUPPORTED;
+    const int K = (l == 0) ? k.D0 : 2 * p->units[l - 1];
+    if (p->in_dim[l] != K) return MBEV_ERR_BAD_ARG;
+    const int Kp = (l == 0) ? kK0Pad : K;
+    if (Kp > 128 || (Kp & 7)) return MBEV_ERR_UNSUPPORTED;
+    k.U[l] = pa.U[l] = U;
+    k.K[l] = pa.K[l] = K;
+    k.Kp[l] = pa.Kp[l] = Kp;
+    for (int h = 0; h < 2; ++h) {
+      k.w_off[l][h] = off;
+      off += static_cast<uint32_t>(U) * Kp * 4u;
+    }
+    um = std::max(um, U);
+  }
+  k.um = um;
+  k.w_bytes = off;
+  // shared memory: [weights image][scratch 128x33][scale/shift][tables][barriers]
+  uint32_t o = off;
+  o = (o + 127u) & ~127u;
+  k.o_scr = o; o += kRows * kScrPitch * 4;
+  o = (o + 15u) & ~15u;
+  k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
+  k.o_tab = o; o += (kPcap + (kPcap + 4) + (kRows + 4) + kRows + kPcap * 4 + kPcap * 4 + 8) * 4;
+  o = (o + 15u) & ~15u;
+  k.o_bar = o; o += 11 * 8 + 8;
+  k.smem_bytes = static_cast<int>(o);
+  if (k.smem_bytes > kSmemLimit) return MBEV_ERR_UNSUPPORTED;
+  // workspace: weight image, per-CTA statistic partials
+  Carver cw(ws);
+  float *img = cw.take<float>(off / 4);
+  k.w_img = img;
+  for (int l = 0; l < k.L; ++l) {
+    pa.hi[l] = img ? img + k.w_off[l][0] / 4 : nullptr;
+    pa.lo[l] = img ? img + k.w_off[l][1] / 4 : nullptr;
+  }
+  out->grid = kNumSMs;
+  k.partials = cw.take<double>(static_cast<size_t>(out->grid) * 2 * um);
+  out->ws_bytes = cw.off;
+  return MBEV_OK;
+}
+
+inline int launch_prep(const MbevPfnParams *p, Plan &pl, cudaStream_t stream) {
+  for (int l = 0; l < pl.k.L; ++l) {
+    if (!p->weight[l]) return MBEV_ERR_BAD_ARG;
+    pl.prep.w[l] = p->weight[l];
+  }
+  k_prep_weights_tc<<<dim3(16, pl.k.L), 256, 0, stream>>>(pl.prep);
+  MBEV_CHECK_LAUNCH();
+  return MBEV_OK;
+}
+
+inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, const int32_t *num_points,
+                  const int32_t *coors, const int32_t *num_pillars_dev, float *feats, int stat_layer,
+                  cudaStream_t stream) {
+  Kargs k = pl.k;
+  k.stat_layer = stat_layer;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_done = true;
+  }
+  k_pfn_tc<<<pl.grid, kThreads, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, num_pillars_dev, feats, k);
+  MBEV_CHECK_LAUNCH();
+  return MBEV_OK;
+}
+
+}  // namespace tc
+}  // namespace mbev

@@ -148,6 +148,7 @@ class PfnConfig:
     y_offset: float
     z_offset: float
     eps: float = 1e-3
+    gemm_path: int = 0        # _lib.GEMM_AUTO / GEMM_FMA / GEMM_TCGEN05 (forward Linear layers)
 
 
 def _pfn_struct(cfg: PfnConfig, weights, scales, shifts) -> MbevPfnParams:
@@ -159,7 +160,7 @@ def _pfn_struct(cfg: PfnConfig, weights, scales, shifts) -> MbevPfnParams:
     for l in range(L):
         p.in_dim[l] = cfg.in_dims[l]
         p.units[l] = cfg.units[l]
-        p.weight[l] = weights[l].data_ptr()
+        p.weight[l] = weights[l].data_ptr() if weights[l] is not None else None
         p.scale[l] = scales[l].data_ptr() if scales is not None else None
         p.shift[l] = shifts[l].data_ptr() if shifts is not None else None
     p.with_cluster_center = int(cfg.with_cluster_center)
@@ -169,7 +170,18 @@ def _pfn_struct(cfg: PfnConfig, weights, scales, shifts) -> MbevPfnParams:
     p.voxel_center_dims = int(cfg.voxel_center_dims)
     p.vx, p.vy, p.vz = cfg.vx, cfg.vy, cfg.vz
     p.x_offset, p.y_offset, p.z_offset = cfg.x_offset, cfg.y_offset, cfg.z_offset
+    p.gemm_path = int(cfg.gemm_path)
     return p
+
+
+def pfn_path(cfg: PfnConfig, T: int) -> str:
+    """Which device implementation a forward with this stack takes: 'tcgen05' or 'fma'."""
+    lib = _lib.load()
+    params = _pfn_struct(cfg, [None] * len(cfg.units), None, None)
+    r = lib.mbev_pfn_path(ctypes.byref(params), int(T))
+    if r < 0:
+        check(r, "pfn_path")
+    return {_lib.GEMM_FMA: "fma", _lib.GEMM_TCGEN05: "tcgen05"}[r]
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:

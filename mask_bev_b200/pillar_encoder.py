@@ -7,6 +7,7 @@ their forward is never called. There is no CPU path.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -110,6 +111,8 @@ class PillarFeatureNet(nn.Module):
         self.y_offset = self.vy / 2 + point_cloud_range[1]
         self.z_offset = self.vz / 2 + point_cloud_range[2]
         self.point_cloud_range = point_cloud_range
+        # forward Linear layers: 'auto' (tcgen05 3xTF32 when the stack fits, else fp32 FMA), 'fma', 'tcgen05'
+        self.gemm_path = os.environ.get("MBEV_GEMM_PATH", "auto")
 
     # -- helpers ------------------------------------------------------------------------------------
     def _config(self) -> F_.PfnConfig:
@@ -119,7 +122,8 @@ class PillarFeatureNet(nn.Module):
             with_cluster_center=self._with_cluster_center, with_voxel_center=self._with_voxel_center,
             with_distance=self._with_distance, legacy=self.legacy, voxel_center_dims=self._voxel_center_dims,
             vx=self.vx, vy=self.vy, vz=self.vz, x_offset=self.x_offset, y_offset=self.y_offset,
-            z_offset=self.z_offset, eps=self.pfn_layers[0].norm.eps)
+            z_offset=self.z_offset, eps=self.pfn_layers[0].norm.eps,
+            gemm_path={"auto": 0, "fma": 1, "tcgen05": 2}[self.gemm_path])
 
     def _param_list(self):
         ls = self.pfn_layers
