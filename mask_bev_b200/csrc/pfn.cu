@@ -535,11 +535,11 @@ int launch_pfn(const Plan &pl, const float *rows, const int32_t *kept_idx, const
 }
 
 // Which implementation runs the Linear layers of this stack: MBEV_GEMM_TCGEN05 / MBEV_GEMM_FMA, or < 0.
-int select_path(const MbevPfnParams *p, int C, int T) {
+int select_path(const MbevPfnParams *p, int C, int T) {  // capacity-independent
   if (!p) return MBEV_ERR_BAD_ARG;
   if (p->gemm_path == MBEV_GEMM_FMA) return MBEV_GEMM_FMA;
   tc::Plan tp;
-  const int st = tc::make_plan(p, C, T, nullptr, &tp);
+  const int st = tc::make_plan(p, C, T, 1, nullptr, &tp);
   if (st == MBEV_OK) return MBEV_GEMM_TCGEN05;
   if (st == MBEV_ERR_UNSUPPORTED && p->gemm_path == MBEV_GEMM_AUTO) return MBEV_GEMM_FMA;
   return st;
@@ -570,15 +570,14 @@ extern "C" int mbev_pfn_path(const MbevPfnParams *params, int T) {
 
 extern "C" int mbev_pfn_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity, int train,
                                         size_t *bytes) {
-  (void)pillar_capacity;
-  (void)train;
+    (void)train;
   if (!bytes || !params) return MBEV_ERR_BAD_ARG;
   const int C = raw_point_dim(params);
   const int path = select_path(params, C, T);
   if (path < 0) return path;
   if (path == MBEV_GEMM_TCGEN05) {
     tc::Plan tp;
-    const int st = tc::make_plan(params, C, T, nullptr, &tp);
+    const int st = tc::make_plan(params, C, T, pillar_capacity, nullptr, &tp);
     if (st) return st;
     *bytes = tp.ws_bytes;
     return MBEV_OK;
@@ -602,7 +601,7 @@ extern "C" int mbev_pfn_forward(const float *rows, int C, const int32_t *kept_id
   if (path < 0) return path;
   if (path == MBEV_GEMM_TCGEN05) {
     tc::Plan tp;
-    int st = tc::make_plan(params, C, T, workspace, &tp);
+    int st = tc::make_plan(params, C, T, pillar_capacity, workspace, &tp);
     if (st) return st;
     if (workspace_bytes < tp.ws_bytes) return MBEV_ERR_WORKSPACE;
     for (int l = 0; l < tp.k.L; ++l) {
@@ -610,9 +609,9 @@ extern "C" int mbev_pfn_forward(const float *rows, int C, const int32_t *kept_id
       tp.k.scale[l] = params->scale[l];
       tp.k.shift[l] = params->shift[l];
     }
-    st = tc::launch_prep(params, tp, stream);
+    st = tc::launch_prep(params, tp, num_points, num_pillars_dev, stream);
     if (st) return st;
-    return tc::launch(tp, rows, kept_idx, num_points, coors, num_pillars_dev, feats, -1, stream);
+    return tc::launch(tp, rows, kept_idx, num_points, coors, feats, -1, stream);
   }
   Plan pl;
   int st = make_plan(params, C, T, workspace, &pl);
@@ -643,10 +642,10 @@ extern "C" int mbev_pfn_forward_train(const float *rows, int C, const int32_t *k
   if (path < 0) return path;
   if (path == MBEV_GEMM_TCGEN05) {
     tc::Plan tp;
-    int st = tc::make_plan(params, C, T, workspace, &tp);
+    int st = tc::make_plan(params, C, T, pillar_capacity, workspace, &tp);
     if (st) return st;
     if (workspace_bytes < tp.ws_bytes) return MBEV_ERR_WORKSPACE;
-    st = tc::launch_prep(params, tp, stream);
+    st = tc::launch_prep(params, tp, num_points, num_pillars_dev, stream);
     if (st) return st;
     for (int l = 0; l < tp.k.L; ++l) {
       if (!gamma[l] || !beta[l]) return MBEV_ERR_BAD_ARG;
@@ -654,7 +653,7 @@ extern "C" int mbev_pfn_forward_train(const float *rows, int C, const int32_t *k
       tp.k.shift[l] = scale_shift_out + (2 * l + 1) * MBEV_MAX_UNITS;
     }
     for (int s = 0; s < tp.k.L; ++s) {
-      st = tc::launch(tp, rows, kept_idx, num_points, coors, num_pillars_dev, feats, s, stream);
+      st = tc::launch(tp, rows, kept_idx, num_points, coors, feats, s, stream);
       if (st) return st;
       const int U = tp.k.U[s];
       k_stats_finalize<<<(U + 127) / 128, 128, 0, stream>>>(
@@ -663,7 +662,7 @@ extern "C" int mbev_pfn_forward_train(const float *rows, int C, const int32_t *k
           batch_stats_out + (2 * s) * MBEV_MAX_UNITS, batch_stats_out + (2 * s + 1) * MBEV_MAX_UNITS);
       MBEV_CHECK_LAUNCH();
     }
-    return tc::launch(tp, rows, kept_idx, num_points, coors, num_pillars_dev, feats, -1, stream);
+    return tc::launch(tp, rows, kept_idx, num_points, coors, feats, -1, stream);
   }
   Plan pl;
   int st = make_plan(params, C, T, workspace, &pl);

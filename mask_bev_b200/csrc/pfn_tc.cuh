@@ -171,20 +171,99 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
 
+// ---- row-balanced static partition ------------------------------------------------------------------------
+// Pillars are numbered in order of first appearance, so the heavy pillars of a frame come first: an equal-count
+// split leaves the CTAs 3x apart in rows. k_row_blocks sums the compact rows (n + [n < T]) of blocks of 128
+// pillars, k_row_bounds prefix-sums the blocks and gives CTA b the blocks whose prefix falls in
+// [R b / G, R (b+1) / G). Static and deterministic (train-mode statistics stay run-to-run identical).
+constexpr int kBlkPillars = 128;
+
+__global__ void k_row_blocks(const int *__restrict__ num_points, const int *__restrict__ num_pillars, const int T,
+                             const int nb, int *__restrict__ blocksum) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= nb) return;
+  const int lane = threadIdx.x & 31, P = *num_pillars;
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kBlkPillars / 32; ++i) {
+    const int p = j * kBlkPillars + i * 32 + lane;
+    if (p < P) {
+      const int n = __ldg(num_points + p);
+      s += n + (n < T ? 1 : 0);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) blocksum[j] = s;
+}
+
+// single CTA of 1024 threads; prefix[] has nb + 1 entries (global scratch)
+__global__ void k_row_bounds(const int *__restrict__ blocksum, const int nb, const int *__restrict__ num_pillars,
+                             const int G, int *__restrict__ prefix, int *__restrict__ bounds) {
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x;
+  const int per = (nb + 1023) / 1024;
+  const int j0 = min(nb, t * per), j1 = min(nb, j0 + per);
+  int s = 0;
+  for (int j = j0; j < j1; ++j) s += blocksum[j];
+  s_part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    const int v = t >= o ? s_part[t - o] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int run = s_part[t] - s;  // exclusive prefix of this thread's first block
+  for (int j = j0; j < j1; ++j) {
+    prefix[j] = run;
+    run += blocksum[j];
+  }
+  const int R = s_part[1023];
+  if (t == 0) prefix[nb] = R;
+  __threadfence_block();
+  __syncthreads();
+  const int P = *num_pillars;
+  for (int b = t; b <= G; b += 1024) {
+    int res;
+    if (b == 0) {
+      res = 0;
+    } else if (b == G) {
+      res = P;
+    } else {
+      const long long target = (static_cast<long long>(R) * b + G - 1) / G;
+      int lo = 0, hi = nb;  // first j with prefix[j] >= target
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] >= target) hi = mid; else lo = mid + 1;
+      }
+      res = static_cast<int>(min(static_cast<long long>(lo) * kBlkPillars, static_cast<long long>(P)));
+    }
+    bounds[b] = res;
+  }
+}
+
 // ---- kernel ---------------------------------------------------------------------------------------------------
-// Warp roles: warps 0-7 = 256 epilogue threads (thread (row, h): row = 32*(warp&3)+lane owns TMEM lane `row`,
-// h = warp>>2 owns columns 16h..16h+15 of every 32-column slab); warp 8 = MMA issuer (one elected lane).
-// Handshakes: slab ring (8 mbarriers, 256 arrivals each): "a K-slab of the next layer's input is in TMEM";
-// bar_d[2] (tcgen05.commit): "the accumulator of a layer is complete"; accumulators alternate D0 / D1 so the
-// MMAs of layer l+1 start on the first finished K-slab while layer l's epilogue is still draining its D.
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// Warp roles: warps 0-7 = 256 epilogue threads in two groups of 128 (group h = warp>>2 owns columns
+// 16h..16h+15 of every 32-column slab; inside a group thread `row` = 32*(warp&3)+lane owns TMEM lane `row`);
+// warp 8 = MMA issuer (one elected lane issues, all lanes walk the handshakes).
+// Handshakes: bar_x0 (256 arrivals): "layer-0 input of the next chunk is in TMEM" (or stop);
+// slab rings (2 groups x 8 mbarriers, 128 arrivals): "16 more K-columns of the next layer's input are in TMEM";
+// bar_d[2] (tcgen05.commit): "the accumulator of a layer is complete". Accumulators alternate D0 / D1 so the
+// MMAs of layer l+1 start on the first finished K-columns while layer l's epilogue is still draining its D.
+// The two groups only meet at chunk boundaries; in between each runs on its own named barrier, so one group's
+// shared-memory column walk overlaps the other's TMEM traffic.
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+__device__ __forceinline__ void grp_sync(int h) { asm volatile("bar.sync %0, 128;" ::"r"(h + 1) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+constexpr int kBarW = 0, kBarD = 1, kBarX0 = 3, kBarSlab = 4, kNumBars = 20;
+
 __global__ void __launch_bounds__(kThreads, 1)
 k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, const int *__restrict__ num_points,
-         const int *__restrict__ coors, const int *__restrict__ num_pillars, float *__restrict__ feats,
+         const int *__restrict__ coors, const int *__restrict__ bounds, float *__restrict__ feats,
          const __grid_constant__ Kargs k) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -195,14 +274,17 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
   float *s_ss = reinterpret_cast<float *>(smem_raw + k.o_ss);  // [L][2][128]
   int *s_n = reinterpret_cast<int *>(smem_raw + k.o_tab);      // [64]
   int *s_prow0 = s_n + kPcap;                                  // [65] (+3 pad)
-  int *s_rinfo = s_prow0 + kPcap + 4;                          // [129] (+3 pad): first row of the row's pillar | pillar << 8
-  float *s_roww = reinterpret_cast<float *>(s_rinfo + kRows + 4);  // [128]
+  int *s_rinfo = s_prow0 + kPcap + 4;                          // [128]: first row of the row's pillar | pillar << 8
+  int *s_rend = s_rinfo + kRows;                               // [128]: 1 = the row closes its pillar
+  float *s_roww = reinterpret_cast<float *>(s_rend + kRows);   // [128]
   float *s_mean = s_roww + kRows;                              // [64][4]
   float *s_ctr = s_mean + kPcap * 4;                           // [64][4]
   int *s_misc = reinterpret_cast<int *>(s_ctr + kPcap * 4);    // [8]: scan carries, counts, [7] = continue flag
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + k.o_bar);  // [0] weights, [1..2] D ready, [3..10] slab ring
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 11);
-  const uint32_t bar_w = smem_u32(s_bar), bar_d = smem_u32(s_bar + 1), bar_slab = smem_u32(s_bar + 3);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + k.o_bar);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + kNumBars);
+  const uint32_t bar0 = smem_u32(s_bar);
+  const uint32_t bar_w = bar0 + 8 * kBarW, bar_d = bar0 + 8 * kBarD, bar_x0 = bar0 + 8 * kBarX0,
+                 bar_slab = bar0 + 8 * kBarSlab;
   const uint32_t smem_base = smem_u32(smem_raw);
   const int last_layer = (k.stat_layer >= 0) ? k.stat_layer : k.L - 1;
 
@@ -210,7 +292,8 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
     mbar_init(bar_w, 1);
     mbar_init(bar_d, 1);
     mbar_init(bar_d + 8, 1);
-    for (int i = 0; i < 8; ++i) mbar_init(bar_slab + 8 * i, kEpiThreads);
+    mbar_init(bar_x0, kEpiThreads);
+    for (int i = 0; i < 16; ++i) mbar_init(bar_slab + 8 * i, kEpiThreads / 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -239,47 +322,57 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
     }
     __syncwarp();
     mbar_wait(bar_w, 0);
-    uint32_t ev = 0;
+    uint32_t ev = 0, par_x0 = 0;  // ev: events consumed per group ring (both rings advance together)
     for (;;) {
-      mbar_wait(bar_slab + 8 * (ev & 7), (ev >> 3) & 1);  // layer-0 input of the next chunk, or the stop signal
-      ++ev;
+      mbar_wait(bar_x0, par_x0);  // layer-0 input of the next chunk, or the stop signal
+      par_x0 ^= 1u;
       if (*reinterpret_cast<volatile int *>(s_misc + 7) == 0) break;
       tc_fence_after();
       for (int l = 0; l <= last_layer; ++l) {
         const int U = k.U[l];
         const uint32_t idesc = make_idesc(U);
-        const uint32_t lbo = static_cast<uint32_t>(U) * 16u, kstep = 2u * lbo;
+        const uint32_t lbo = static_cast<uint32_t>(U) * 16u;
         const uint32_t d_col = tmem + kColD + ((l & 1) ? 128u : 0u);
-        const uint32_t bh = smem_base + k.w_off[l][0], bl = smem_base + k.w_off[l][1];
+        // descriptors advance by one K-step (two 16-byte K-chunks = 2 * lbo bytes) = (2 * lbo) >> 4 in the address field
+        const uint64_t dh0 = make_bdesc(smem_base + k.w_off[l][0], lbo, 128u);
+        const uint64_t dl0 = make_bdesc(smem_base + k.w_off[l][1], lbo, 128u);
+        const uint64_t dstep = static_cast<uint64_t>(lbo >> 3);
         uint32_t acc = 0;
-        // K-slabs in the order the epilogue of layer l-1 finishes them: x(0), max(0), x(1), max(1), ...
-        const int nslab = (l == 0) ? 1 : 2 * (k.U[l - 1] >> 5);
-        for (int s = 0; s < nslab; ++s) {
-          int kcol, nks;
-          if (l == 0) {
-            kcol = 0;
-            nks = k.Kp[0] >> 3;
-          } else {
-            mbar_wait(bar_slab + 8 * (ev & 7), (ev >> 3) & 1);
-            ++ev;
-            tc_fence_after();
-            kcol = ((s & 1) ? k.U[l - 1] : 0) + 32 * (s >> 1);
-            nks = 4;
-          }
+        if (l == 0) {
           if (leader) {
-            const uint32_t koff = kstep * static_cast<uint32_t>(kcol >> 3);
+            const int nks = k.Kp[0] >> 3;
 #pragma unroll 1
             for (int j = 0; j < nks; ++j) {  // al*wh, ah*wl, ah*wh : small terms first
-              const uint64_t dh = make_bdesc(bh + koff + kstep * j, lbo, 128u);
-              const uint64_t dl = make_bdesc(bl + koff + kstep * j, lbo, 128u);
-              const uint32_t ac = static_cast<uint32_t>(kcol + 8 * j);
-              mma_tf32_ts(d_col, tmem + kColAL + ac, dh, idesc, acc);
-              mma_tf32_ts(d_col, tmem + kColAH + ac, dl, idesc, 1u);
-              mma_tf32_ts(d_col, tmem + kColAH + ac, dh, idesc, 1u);
+              mma_tf32_ts(d_col, tmem + kColAL + 8u * j, dh0 + dstep * j, idesc, acc);
+              mma_tf32_ts(d_col, tmem + kColAH + 8u * j, dl0 + dstep * j, idesc, 1u);
+              mma_tf32_ts(d_col, tmem + kColAH + 8u * j, dh0 + dstep * j, idesc, 1u);
               acc = 1;
             }
           }
-          __syncwarp();
+        } else {
+          // 16-column K-parts in the order the groups finish them: x(q) g0, x(q) g1, max(q) g0, max(q) g1
+          const int Up = k.U[l - 1];
+          const int nev = 2 * (Up >> 5);  // events per group ring in this layer
+          for (int e = 0; e < nev; ++e) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(bar_slab + 8 * (8 * g + ((ev + e) & 7)), ((ev + e) >> 3) & 1);
+              tc_fence_after();
+              if (leader) {
+                const uint32_t kcol = static_cast<uint32_t>(((e & 1) ? Up : 0) + 32 * (e >> 1) + 16 * g);
+                const uint64_t dh = dh0 + dstep * (kcol >> 3), dl = dl0 + dstep * (kcol >> 3);
+#pragma unroll
+                for (uint32_t j = 0; j < 2; ++j) {
+                  mma_tf32_ts(d_col, tmem + kColAL + kcol + 8u * j, dh + dstep * j, idesc, acc);
+                  mma_tf32_ts(d_col, tmem + kColAH + kcol + 8u * j, dl + dstep * j, idesc, 1u);
+                  mma_tf32_ts(d_col, tmem + kColAH + kcol + 8u * j, dh + dstep * j, idesc, 1u);
+                  acc = 1;
+                }
+              }
+              __syncwarp();
+            }
+          }
+          ev += nev;
         }
         if (leader) tc_commit(bar_d + 8 * (l & 1));
         __syncwarp();
@@ -289,11 +382,12 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
     // =========================================== epilogue warps ===============================================
     const int row = ((warp & 3) << 5) | lane, h = warp >> 2;
     const uint32_t tlane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);  // this warp's TMEM lane quadrant
-    const int P = *num_pillars;
-    const int p_begin = static_cast<int>(static_cast<int64_t>(P) * blockIdx.x / gridDim.x);
-    const int p_end = static_cast<int>(static_cast<int64_t>(P) * (blockIdx.x + 1) / gridDim.x);
+    const int p_begin = __ldg(bounds + blockIdx.x), p_end = __ldg(bounds + blockIdx.x + 1);
+    const uint32_t my_slab = bar_slab + 64u * h;
     uint32_t ev = 0, par_d0 = 0, par_d1 = 0;
     double st1[4] = {0.0, 0.0, 0.0, 0.0}, st2[4] = {0.0, 0.0, 0.0, 0.0};
+    // column-walk role inside the group: 16 columns x 8 pillar ranges
+    const int cw_c = lane & 15, cw_g = ((warp & 3) << 1) | (lane >> 4);
 
     for (int p = p_begin; p < p_end;) {
       epi_sync();  // previous chunk is done with the tables and the scratch
@@ -317,7 +411,10 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
         s_n[tid] = n_i;
         s_prow0[tid + 1] = incl;
         const int r0 = incl - need;
-        for (int t = 0; t < need; ++t) s_rinfo[r0 + t] = r0 | (tid << 8);
+        for (int t = 0; t < need; ++t) {
+          s_rinfo[r0 + t] = r0 | (tid << 8);
+          s_rend[r0 + t] = (t == need - 1);
+        }
         const int4 c = __ldg(reinterpret_cast<const int4 *>(coors) + p + tid);  // (b, z, y, x)
         // upstream: coors.type_as(features) * vx + x_offset — float32 multiply THEN add (no FMA contraction)
         s_ctr[tid * 4 + 0] = __fadd_rn(__fmul_rn(static_cast<float>(c.w), k.vx), k.xo);
@@ -328,8 +425,7 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
       epi_sync();
       const int npil = s_misc[4] + s_misc[5];  // fits is prefix-closed: the count of leading pillars taken
       const int nrows = s_prow0[npil];
-      if (tid == 0) s_rinfo[nrows] = nrows;  // sentinel: "a new pillar starts here"
-      // ---- gather this row's point (h == 0 threads) ---------------------------------------------------------
+      // ---- gather this row's point (group 0) ----------------------------------------------------------------
       int pl = 0;
       bool real = false;
       if (h == 0) {
@@ -417,8 +513,12 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
       }
       if (tid == 0) s_misc[7] = 1;
       tc_fence_before();
-      mbar_arrive(bar_slab + 8 * (ev & 7));
-      ++ev;
+      mbar_arrive(bar_x0);  // (the staging area aliased with the scratch is next written after D0 is ready)
+
+      // column-walk range of this thread: rows of pillars [npil*g/8, npil*(g+1)/8)
+      const int cw_pa = (npil * cw_g) >> 3;
+      const int cw_ra = s_prow0[cw_pa], cw_rb = s_prow0[(npil * (cw_g + 1)) >> 3];
+      const int fr = row < nrows ? (s_rinfo[row] & 255) : row;  // first row of this row's pillar (padding rows: self)
 
       // ---- layers -------------------------------------------------------------------------------------------
       for (int l = 0; l <= last_layer; ++l) {
@@ -467,7 +567,7 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
               tmem_st16(tlane + kColAL + 32u * q + 16u * h, lo);
               tc_wait_st();
               tc_fence_before();
-              mbar_arrive(bar_slab + 8 * (ev & 7));
+              mbar_arrive(my_slab + 8 * (ev & 7));
               ++ev;
             }
             {
@@ -475,14 +575,13 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
 #pragma unroll
               for (int j = 0; j < 16; ++j) dst[j] = a[j];
             }
-            epi_sync();
-            // column phase: thread (warp g, lane c) owns column 32q+c over the rows of pillars [npil*g/8, npil*(g+1)/8)
+            grp_sync(h);
+            // column walk: this thread owns column 32q+16h+cw_c over rows [cw_ra, cw_rb)
             {
-              const int ra = s_prow0[(npil * warp) >> 3], rb = s_prow0[(npil * (warp + 1)) >> 3];
-              float *col = s_scr + lane;
+              float *col = s_scr + 16 * h + cw_c;
               if (stats) {
                 double s1 = 0.0, s2 = 0.0;
-                for (int r = ra; r < rb; ++r) {
+                for (int r = cw_ra; r < cw_rb; ++r) {
                   const double y = static_cast<double>(col[r * kScrPitch]);
                   const double w = static_cast<double>(s_roww[r]);
                   s1 += w * y;
@@ -490,34 +589,39 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
                 }
                 st1[q] += s1;
                 st2[q] += s2;
-              } else {
+              } else if (last) {
                 float mx = 0.f;  // post-ReLU values are >= 0
-                int first = ra;
+                float *out = feats + static_cast<size_t>(p + cw_pa) * U + 32 * q + 16 * h + cw_c;
 #pragma unroll 4
-                for (int r = ra; r < rb; ++r) {
+                for (int r = cw_ra; r < cw_rb; ++r) {
                   mx = fmaxf(mx, col[r * kScrPitch]);
-                  const int nxt = s_rinfo[r + 1];
-                  if ((nxt & 255) == r + 1) {  // r closes its pillar
-                    if (last) {
-                      const int pp = s_rinfo[r] >> 8;
-                      feats[static_cast<size_t>(p + pp) * U + 32 * q + lane] = mx;
-                    } else {
-                      col[first * kScrPitch] = mx;  // parked in the pillar's first row
-                    }
+                  if (s_rend[r]) {
+                    *out = mx;
+                    out += U;
+                    mx = 0.f;
+                  }
+                }
+              } else {
+                float mx = 0.f;
+                int first = cw_ra;
+#pragma unroll 4
+                for (int r = cw_ra; r < cw_rb; ++r) {
+                  mx = fmaxf(mx, col[r * kScrPitch]);
+                  if (s_rend[r]) {
+                    col[first * kScrPitch] = mx;  // parked in the pillar's first row
                     mx = 0.f;
                     first = r + 1;
                   }
                 }
               }
             }
-            epi_sync();
+            grp_sync(h);
             if (!last && !stats) {  // max half of the next layer's input: K index = U + unit index
-              const int fr = row < nrows ? (s_rinfo[row] & 255) : row;  // chunk padding rows: any finite value
               const float *src = s_scr + fr * kScrPitch + 16 * h;
               float m[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) m[j] = src[j];
-              epi_sync();  // scratch may be overwritten by the next slab from here on
+              grp_sync(h);  // scratch may be overwritten by the next slab from here on
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) split_tf32(m[j], hi[j], lo[j]);
@@ -525,7 +629,7 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
               tmem_st16(tlane + kColAL + static_cast<uint32_t>(U) + 32u * q + 16u * h, lo);
               tc_wait_st();
               tc_fence_before();
-              mbar_arrive(bar_slab + 8 * (ev & 7));
+              mbar_arrive(my_slab + 8 * (ev & 7));
               ++ev;
             }
           }
@@ -536,18 +640,18 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
     // stop signal for the MMA issuer
     epi_sync();
     if (tid == 0) s_misc[7] = 0;
-    mbar_arrive(bar_slab + 8 * (ev & 7));
+    mbar_arrive(bar_x0);
 
     if (k.stat_layer >= 0) {
-      // deterministic CTA reduction: the 8 warps' partials of each column are summed in warp order
+      // deterministic CTA reduction: the 8 ranges' partials of each column are summed in range order
       double *red = reinterpret_cast<double *>(s_scr);  // [8][2][128] = 16 KB
       const int U = k.U[k.stat_layer];
       const int nq = U >> 5;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (q < nq) {
-          red[(warp * 2 + 0) * MBEV_MAX_UNITS + 32 * q + lane] = st1[q];
-          red[(warp * 2 + 1) * MBEV_MAX_UNITS + 32 * q + lane] = st2[q];
+          red[(cw_g * 2 + 0) * MBEV_MAX_UNITS + 32 * q + 16 * h + cw_c] = st1[q];
+          red[(cw_g * 2 + 1) * MBEV_MAX_UNITS + 32 * q + 16 * h + cw_c] = st2[q];
         }
       }
       epi_sync();
@@ -597,10 +701,14 @@ struct Plan {
   PrepArgs prep;
   size_t ws_bytes;
   int grid;
+  int nb;         // blocks of kBlkPillars pillars covering the capacity
+  int *blocksum;  // (nb)
+  int *prefix;    // (nb + 1)
+  int *bounds;    // (grid + 1) first pillar of each CTA
 };
 
 // MBEV_OK when the stack fits the tensor-core kernel, MBEV_ERR_UNSUPPORTED when it must run on the FMA kernel.
-inline int make_plan(const MbevPfnParams *p, int C, int T, void *ws, Plan *out) {
+inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capacity, void *ws, Plan *out) {
   if (!p || p->num_layers < 1 || p->num_layers > MBEV_MAX_LAYERS) return MBEV_ERR_BAD_ARG;
   if (C < 3 || C > MBEV_MAX_POINT_DIM || T < 1) return MBEV_ERR_UNSUPPORTED;
   if (T + 1 > kRows) return MBEV_ERR_UNSUPPORTED;  // a pillar and its virtual row must fit one chunk
@@ -647,9 +755,9 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, void *ws, Plan *out) 
   k.o_scr = o; o += kRows * kScrPitch * 4;
   o = (o + 15u) & ~15u;
   k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
-  k.o_tab = o; o += (kPcap + (kPcap + 4) + (kRows + 4) + kRows + kPcap * 4 + kPcap * 4 + 8) * 4;
+  k.o_tab = o; o += (kPcap + (kPcap + 4) + kRows + kRows + kRows + kPcap * 4 + kPcap * 4 + 8) * 4;
   o = (o + 15u) & ~15u;
-  k.o_bar = o; o += 11 * 8 + 8;
+  k.o_bar = o; o += kNumBars * 8 + 8;
   k.smem_bytes = static_cast<int>(o);
   if (k.smem_bytes > kSmemLimit) return MBEV_ERR_UNSUPPORTED;
   // workspace: weight image, per-CTA statistic partials
@@ -662,23 +770,34 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, void *ws, Plan *out) 
   }
   out->grid = kNumSMs;
   k.partials = cw.take<double>(static_cast<size_t>(out->grid) * 2 * um);
+  const int64_t nb = (std::max<int64_t>(pillar_capacity, 1) + kBlkPillars - 1) / kBlkPillars;
+  if (nb > (1 << 24)) return MBEV_ERR_UNSUPPORTED;
+  out->nb = static_cast<int>(nb);
+  out->blocksum = cw.take<int>(out->nb);
+  out->prefix = cw.take<int>(out->nb + 1);
+  out->bounds = cw.take<int>(out->grid + 1);
   out->ws_bytes = cw.off;
   return MBEV_OK;
 }
 
-inline int launch_prep(const MbevPfnParams *p, Plan &pl, cudaStream_t stream) {
+// weight images + the row-balanced CTA partition (once per forward call; shared by the STATS and FULL launches)
+inline int launch_prep(const MbevPfnParams *p, Plan &pl, const int32_t *num_points, const int32_t *num_pillars_dev,
+                       cudaStream_t stream) {
   for (int l = 0; l < pl.k.L; ++l) {
     if (!p->weight[l]) return MBEV_ERR_BAD_ARG;
     pl.prep.w[l] = p->weight[l];
   }
   k_prep_weights_tc<<<dim3(16, pl.k.L), 256, 0, stream>>>(pl.prep);
   MBEV_CHECK_LAUNCH();
+  k_row_blocks<<<(pl.nb + 7) / 8, 256, 0, stream>>>(num_points, num_pillars_dev, pl.k.T, pl.nb, pl.blocksum);
+  MBEV_CHECK_LAUNCH();
+  k_row_bounds<<<1, 1024, 0, stream>>>(pl.blocksum, pl.nb, num_pillars_dev, pl.grid, pl.prefix, pl.bounds);
+  MBEV_CHECK_LAUNCH();
   return MBEV_OK;
 }
 
 inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, const int32_t *num_points,
-                  const int32_t *coors, const int32_t *num_pillars_dev, float *feats, int stat_layer,
-                  cudaStream_t stream) {
+                  const int32_t *coors, float *feats, int stat_layer, cudaStream_t stream) {
   Kargs k = pl.k;
   k.stat_layer = stat_layer;
   static bool attr_done = false;
@@ -686,7 +805,7 @@ inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, co
     MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_done = true;
   }
-  k_pfn_tc<<<pl.grid, kThreads, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, num_pillars_dev, feats, k);
+  k_pfn_tc<<<pl.grid, kThreads, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k);
   MBEV_CHECK_LAUNCH();
   return MBEV_OK;
 }
