@@ -21,9 +21,10 @@
 // accumulates sum / sum-of-squares in fp64, fixed reduction order => run-to-run identical), then once in
 // FULL mode.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
-#include "pfn_tc.cuh"
+#include "pfn_tcw.cuh"
 
 namespace mbev {
 namespace {

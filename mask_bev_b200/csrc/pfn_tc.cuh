@@ -63,6 +63,7 @@ struct Kargs {
   int smem_bytes;
   int stat_layer;    // -1: full forward; s: accumulate the statistics of layer s and stop
   double *partials;  // (gridDim.x, 2, um)
+  int dbg;           // profiling knobs (MBEV_TC_DBG, developer only): results are wrong when non-zero
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -173,10 +174,10 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
 
 // ---- row-balanced static partition ------------------------------------------------------------------------
 // Pillars are numbered in order of first appearance, so the heavy pillars of a frame come first: an equal-count
-// split leaves the CTAs 3x apart in rows. k_row_blocks sums the compact rows (n + [n < T]) of blocks of 128
-// pillars, k_row_bounds prefix-sums the blocks and gives CTA b the blocks whose prefix falls in
+// split leaves the CTAs 3x apart in rows. k_row_blocks sums the compact rows (n + [n < T]) of blocks of 32
+// pillars, k_row_bounds prefix-sums the blocks and gives sub-range b (4 per CTA) the blocks whose prefix falls in
 // [R b / G, R (b+1) / G). Static and deterministic (train-mode statistics stay run-to-run identical).
-constexpr int kBlkPillars = 128;
+constexpr int kBlkPillars = 32;
 
 __global__ void k_row_blocks(const int *__restrict__ num_points, const int *__restrict__ num_pillars, const int T,
                              const int nb, int *__restrict__ blocksum) {
@@ -184,9 +185,9 @@ __global__ void k_row_blocks(const int *__restrict__ num_points, const int *__re
   if (j >= nb) return;
   const int lane = threadIdx.x & 31, P = *num_pillars;
   int s = 0;
-#pragma unroll
-  for (int i = 0; i < kBlkPillars / 32; ++i) {
-    const int p = j * kBlkPillars + i * 32 + lane;
+  static_assert(kBlkPillars == 32, "one pillar per lane");
+  {
+    const int p = j * kBlkPillars + lane;
     if (p < P) {
       const int n = __ldg(num_points + p);
       s += n + (n < T ? 1 : 0);
@@ -382,7 +383,7 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
     // =========================================== epilogue warps ===============================================
     const int row = ((warp & 3) << 5) | lane, h = warp >> 2;
     const uint32_t tlane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);  // this warp's TMEM lane quadrant
-    const int p_begin = __ldg(bounds + blockIdx.x), p_end = __ldg(bounds + blockIdx.x + 1);
+    const int p_begin = __ldg(bounds + 4 * blockIdx.x), p_end = __ldg(bounds + 4 * blockIdx.x + 4);  // 4 sub-ranges per CTA
     const uint32_t my_slab = bar_slab + 64u * h;
     uint32_t ev = 0, par_d0 = 0, par_d1 = 0;
     double st1[4] = {0.0, 0.0, 0.0, 0.0}, st2[4] = {0.0, 0.0, 0.0, 0.0};
@@ -704,7 +705,7 @@ struct Plan {
   int nb;         // blocks of kBlkPillars pillars covering the capacity
   int *blocksum;  // (nb)
   int *prefix;    // (nb + 1)
-  int *bounds;    // (grid + 1) first pillar of each CTA
+  int *bounds;    // (4 * grid + 1) first pillar of each quarter-CTA sub-range (k_pfn_tcw: one per TMEM lane quadrant)
 };
 
 // MBEV_OK when the stack fits the tensor-core kernel, MBEV_ERR_UNSUPPORTED when it must run on the FMA kernel.
@@ -757,7 +758,7 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capaci
   k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
   k.o_tab = o; o += (kPcap + (kPcap + 4) + kRows + kRows + kRows + kPcap * 4 + kPcap * 4 + 8) * 4;
   o = (o + 15u) & ~15u;
-  k.o_bar = o; o += kNumBars * 8 + 8;
+  k.o_bar = o; o += 40 * 8 + 8;  // k_pfn_tc uses 20 barriers, k_pfn_tcw up to 36
   k.smem_bytes = static_cast<int>(o);
   if (k.smem_bytes > kSmemLimit) return MBEV_ERR_UNSUPPORTED;
   // workspace: weight image, per-CTA statistic partials
@@ -775,7 +776,7 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capaci
   out->nb = static_cast<int>(nb);
   out->blocksum = cw.take<int>(out->nb);
   out->prefix = cw.take<int>(out->nb + 1);
-  out->bounds = cw.take<int>(out->grid + 1);
+  out->bounds = cw.take<int>(4 * out->grid + 1);
   out->ws_bytes = cw.off;
   return MBEV_OK;
 }
@@ -791,21 +792,7 @@ inline int launch_prep(const MbevPfnParams *p, Plan &pl, const int32_t *num_poin
   MBEV_CHECK_LAUNCH();
   k_row_blocks<<<(pl.nb + 7) / 8, 256, 0, stream>>>(num_points, num_pillars_dev, pl.k.T, pl.nb, pl.blocksum);
   MBEV_CHECK_LAUNCH();
-  k_row_bounds<<<1, 1024, 0, stream>>>(pl.blocksum, pl.nb, num_pillars_dev, pl.grid, pl.prefix, pl.bounds);
-  MBEV_CHECK_LAUNCH();
-  return MBEV_OK;
-}
-
-inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, const int32_t *num_points,
-                  const int32_t *coors, float *feats, int stat_layer, cudaStream_t stream) {
-  Kargs k = pl.k;
-  k.stat_layer = stat_layer;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_done = true;
-  }
-  k_pfn_tc<<<pl.grid, kThreads, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k);
+  k_row_bounds<<<1, 1024, 0, stream>>>(pl.blocksum, pl.nb, num_pillars_dev, 4 * pl.grid, pl.prefix, pl.bounds);
   MBEV_CHECK_LAUNCH();
   return MBEV_OK;
 }
