@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 2
+#define MBEV_ABI_VERSION 3
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -169,12 +169,26 @@ MBEV_API int mbev_build_cell_table(const int32_t *coors, const int32_t *num_pill
                           int batch, int ny, int nx, int32_t *cell_table, void *stream);
 MBEV_API int mbev_scatter_forward(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny, int nx,
                          float *canvas, void *stream);
+/* Two-kernel form of the same scatter (G = ny*nx a multiple of 8 and a 32-byte aligned canvas; probe with
+ * mbev_scatter_split_supported): fill_empty zeroes every 32-byte sector (8 cells of one channel plane) that holds
+ * no pillar and needs only the cell table, so it can run on a second stream while K2 computes; occupied writes
+ * the remaining sectors whole. Together they write every canvas byte exactly once. */
+MBEV_API int mbev_scatter_split_supported(int ny, int nx, const float *canvas);
+MBEV_API int mbev_scatter_fill_empty(const int32_t *cell_table, int batch, int c_out, int ny, int nx, float *canvas,
+                            void *stream);
+MBEV_API int mbev_scatter_occupied(const float *feats, const int32_t *coors, const int32_t *num_pillars_dev,
+                          int64_t pillar_capacity, const int32_t *cell_table, int batch, int c_out, int ny, int nx,
+                          float *canvas, void *stream);
 MBEV_API int mbev_scatter_backward(const float *dcanvas, const int32_t *cell_table, int batch, int c_out, int ny,
                           int nx, float *dfeats, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Fused batch entry (additive): K1 -> K2(eval) -> K3 on one stream, no host sync.
+ * Fused batch entry (additive): K1 -> K2(eval) -> K3, no host sync.
  * Equivalent to MaskBevEncoder.forward (mask_bev_encoders.py:77-91) without the trailing LayerNorm.
+ * aux_stream: optional second stream (NULL = everything on `stream`). When given and the canvas allows the
+ * two-kernel scatter, the zero-fill of the empty sectors runs on aux_stream concurrently with K2 (HBM-bound
+ * writes under a compute-bound kernel); the call forks and joins with events, so the caller only ever orders
+ * against `stream`.
  * ---------------------------------------------------------------------------------------------- */
 MBEV_API int mbev_encode_batch_workspace_bytes(const MbevGeometry *geo, const MbevPfnParams *params, int batch,
                                       int64_t total_points, int64_t pillar_capacity, size_t *bytes);
@@ -182,7 +196,7 @@ MBEV_API int mbev_encode_batch(const float *points, const int64_t *frame_offsets
                       const MbevGeometry *geo, const MbevPfnParams *params, int32_t *cell_table,
                       int32_t *coors, int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
                       int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
-                      size_t workspace_bytes, void *stream);
+                      size_t workspace_bytes, void *stream, void *aux_stream);
 
 /* Same, with HOST input: copies `points_host` (pinned or pageable) to `points_dev` on `stream` first.
  * This is the call bench.py's e2e leg times. */
@@ -190,7 +204,7 @@ MBEV_API int mbev_encode_batch_host(const float *points_host, float *points_dev,
                            int batch, const MbevGeometry *geo, const MbevPfnParams *params,
                            int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
                            int32_t *pillar_base, int64_t pillar_capacity, float *feats, float *canvas,
-                           void *workspace, size_t workspace_bytes, void *stream);
+                           void *workspace, size_t workspace_bytes, void *stream, void *aux_stream);
 
 /* Launch counter: number of library kernels enqueued by this process since load (for bench.py's
  * `gpu_launches`). Thread-safe. */

@@ -63,7 +63,7 @@ extern "C" int mbev_encode_batch(const float *points, const int64_t *frame_offse
                                  const MbevGeometry *geo, const MbevPfnParams *params, int32_t *cell_table,
                                  int32_t *coors, int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
                                  int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
-                                 size_t workspace_bytes, void *stream) {
+                                 size_t workspace_bytes, void *stream, void *aux_stream) {
   if (!geo || !params || !frame_offsets_host || !workspace || !feats || !canvas) return MBEV_ERR_BAD_ARG;
   if (geo->grid[2] != 1) return MBEV_ERR_UNSUPPORTED;  // pillars: one cell along z (mask_bev_module.py:62)
   FusedWs w;
@@ -74,18 +74,40 @@ extern "C" int mbev_encode_batch(const float *points, const int64_t *frame_offse
   st = mbev_voxelize(points, frame_offsets_host, batch, geo, cell_table, coors, num_points, kept_idx, pillar_base,
                      pillar_capacity, ws + w.vox_off, w.vox_bytes, stream);
   if (st) return st;
+  const int c_out = params->units[params->num_layers - 1], ny = geo->grid[1], nx = geo->grid[0];
+  const bool split = aux_stream && aux_stream != stream && mbev_scatter_split_supported(ny, nx, canvas);
+  cudaStream_t main_s = static_cast<cudaStream_t>(stream), aux_s = static_cast<cudaStream_t>(aux_stream);
+  cudaEvent_t e_fork = nullptr, e_join = nullptr;
+  int st_fill = MBEV_OK;
+  if (split) {  // fork: the zero-fill needs the cell table only
+    MBEV_CUDA(cudaEventCreateWithFlags(&e_fork, cudaEventDisableTiming));
+    MBEV_CUDA(cudaEventCreateWithFlags(&e_join, cudaEventDisableTiming));
+    st_fill = static_cast<int>(cudaEventRecord(e_fork, main_s));
+    if (!st_fill) st_fill = static_cast<int>(cudaStreamWaitEvent(aux_s, e_fork, 0));
+    if (!st_fill) st_fill = mbev_scatter_fill_empty(cell_table, batch, c_out, ny, nx, canvas, aux_stream);
+    if (!st_fill) st_fill = static_cast<int>(cudaEventRecord(e_join, aux_s));
+  }
   st = mbev_pfn_forward(points, geo->num_feats, kept_idx, num_points, coors, pillar_base + batch, pillar_capacity,
                         geo->max_points, params, feats, ws + w.pfn_off, w.pfn_bytes, stream);
+  if (split) {  // join (also on error, so that the two streams stay ordered); destruction is deferred by the runtime
+    const cudaError_t ej = cudaStreamWaitEvent(main_s, e_join, 0);
+    cudaEventDestroy(e_fork);
+    cudaEventDestroy(e_join);
+    if (st_fill) return st_fill;
+    if (ej != cudaSuccess) return static_cast<int>(ej);
+  }
   if (st) return st;
-  return mbev_scatter_forward(feats, cell_table, batch, params->units[params->num_layers - 1], geo->grid[1],
-                              geo->grid[0], canvas, stream);
+  if (split)
+    return mbev_scatter_occupied(feats, coors, pillar_base + batch, pillar_capacity, cell_table, batch, c_out, ny, nx,
+                                 canvas, stream);
+  return mbev_scatter_forward(feats, cell_table, batch, c_out, ny, nx, canvas, stream);
 }
 
 extern "C" int mbev_encode_batch_host(const float *points_host, float *points_dev, const int64_t *frame_offsets_host,
                                       int batch, const MbevGeometry *geo, const MbevPfnParams *params,
                                       int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
                                       int32_t *pillar_base, int64_t pillar_capacity, float *feats, float *canvas,
-                                      void *workspace, size_t workspace_bytes, void *stream) {
+                                      void *workspace, size_t workspace_bytes, void *stream, void *aux_stream) {
   if (!geo || !frame_offsets_host || batch < 1 || batch > MBEV_MAX_BATCH) return MBEV_ERR_BAD_ARG;
   const int64_t total = frame_offsets_host[batch];
   if (total > 0) {
@@ -94,5 +116,5 @@ extern "C" int mbev_encode_batch_host(const float *points_host, float *points_de
                               cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
   }
   return mbev_encode_batch(points_dev, frame_offsets_host, batch, geo, params, cell_table, coors, num_points,
-                           kept_idx, pillar_base, pillar_capacity, feats, canvas, workspace, workspace_bytes, stream);
+                           kept_idx, pillar_base, pillar_capacity, feats, canvas, workspace, workspace_bytes, stream, aux_stream);
 }

@@ -419,6 +419,17 @@ inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, co
     attr_done = true;
   }
   const int split = stat_layer < 0 ? tcw_split(k) : 0;
+  if (split) {
+    // k_pfn_tcw needs the weights, the [128][20] staging rows, scale/shift and the barriers — not the block
+    // kernel's transposition scratch and tables. Leaving a few KB of the SM's 228 KB unallocated lets small CTAs
+    // of another stream (the canvas zero-fill, K3a) run on the same SMs while this kernel computes.
+    uint32_t o = (k.w_bytes + 127u) & ~127u;
+    k.o_scr = o; o += kRows * kDecoPitch * 4 + 8 * 24 * 8;  // staging rows + the developer timestamp area
+    k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
+    k.o_tab = o; o += 16;
+    k.o_bar = o; o += 40 * 8 + 8;
+    k.smem_bytes = static_cast<int>(o);
+  }
   if (split == 4) {
     k_pfn_tcw<4><<<pl.grid, 17 * 32, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k);
   } else if (split == 2) {

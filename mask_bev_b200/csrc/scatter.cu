@@ -6,6 +6,8 @@
 // that walks the cell table (cell -> pillar id, -1 empty): every 16-byte store carries either zeros or
 // features, so DRAM traffic = canvas bytes + table + the occupied feature rows (HBM-bound, write-only).
 // The backward is the gather dfeats[p,:] = dcanvas[b,:,y,x] driven by the same table.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mbev {
@@ -72,6 +74,66 @@ k_scatter(const float *__restrict__ feats, const int *__restrict__ table, const 
           out[static_cast<size_t>(ch) * G + k] = (p >= 0) ? s_rows[(c0 + k) * pitch + ch] : 0.f;
         }
       }
+    }
+  }
+}
+
+// ---- two-kernel form used by the fused path: K3a needs only the cell table, so it streams the zeros of the
+// canvas while K2 (compute-bound, no DRAM traffic) runs on the main stream; K3b then writes the sectors that hold
+// at least one pillar. The unit is the 32-byte DRAM sector = 8 consecutive cells of one channel plane: every
+// sector is written exactly once, by exactly one of the two kernels, as a whole (no partial-sector read-modify-
+// write), so DRAM traffic stays canvas bytes + table + feature rows. Needs G % 8 == 0 and a 32-byte aligned canvas.
+constexpr int kFillCells = 128;  // cells per tile: lane owns 4 cells (16 B), a lane pair owns one sector per plane
+
+__global__ void __launch_bounds__(kThreads)
+k_fill_empty(const int *__restrict__ table, const int C, const int G, const int tiles_per_frame,
+             const int num_tiles, float *__restrict__ canvas) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_frame;
+    const int g = (tile - b * tiles_per_frame) * kFillCells + lane * 4;
+    int occ = 0;  // bit 0: some cell of my half-sector holds a pillar
+    if (g < G) {
+      const int4 a = __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g));
+      occ = ((a.x & a.y & a.z & a.w) >= 0) ? 1 : 0;
+    }
+    occ |= __shfl_xor_sync(0xffffffffu, occ, 1);  // the other half of the 32-byte sector
+    if (g >= G || occ) continue;                   // K3b owns sectors with a pillar
+    float *out = canvas + (static_cast<size_t>(b) * C) * G + g;
+    for (int ch = warp; ch < C; ch += nwarp) st_global_v4_stream(out + static_cast<size_t>(ch) * G, z);
+  }
+}
+
+// one warp per pillar; the pillar in the lowest occupied cell of a sector writes the sector for all channels:
+// lane pair (2j, 2j+1) = the two 16-byte halves of channel (16 i + j)'s sector, so every store instruction
+// covers 16 whole sectors
+__global__ void __launch_bounds__(kThreads)
+k_scatter_sectors(const float *__restrict__ feats, const int *__restrict__ coors, const int *__restrict__ num_pillars,
+                  const int *__restrict__ table, const int batch, const int C, const int ny, const int nx,
+                  float *__restrict__ canvas) {
+  const int lane = threadIdx.x & 31;
+  const int P = *num_pillars;
+  const int G = ny * nx;
+  const int nwarps = gridDim.x * (kThreads / 32);
+  const int half = lane & 1, j = lane >> 1;
+  for (int p = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); p < P; p += nwarps) {
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(coors) + p);  // (b, z, y, x)
+    if (c.x < 0 || c.x >= batch || c.z < 0 || c.z >= ny || c.w < 0 || c.w >= nx) continue;
+    const int g = c.z * nx + c.w;
+    const int gs = g & ~7;
+    const int mine = lane < 8 ? __ldg(table + static_cast<size_t>(c.x) * G + gs + lane) : -1;
+    const unsigned occ = __ballot_sync(0xffffffffu, mine >= 0) & 0xffu;
+    if ((__ffs(occ) - 1) != (g & 7)) continue;  // warp-uniform: another pillar of this sector writes it
+    int pid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pid[k] = __shfl_sync(0xffffffffu, mine, 4 * half + k);
+    float *out = canvas + (static_cast<size_t>(c.x) * C) * G + gs + 4 * half;
+    for (int ch = j; ch < C; ch += 16) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = pid[k] >= 0 ? __ldg(feats + static_cast<size_t>(pid[k]) * C + ch) : 0.f;
+      st_global_v4_stream(out + static_cast<size_t>(ch) * G, make_float4(v[0], v[1], v[2], v[3]));
     }
   }
 }
@@ -171,6 +233,46 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
     const int blocks = static_cast<int>(std::min<long long>((total + kThreads - 1) / kThreads, kNumSMs * 16));
     k_scatter_scalar<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, total, canvas);
   }
+  MBEV_CHECK_LAUNCH();
+  return MBEV_OK;
+}
+
+extern "C" int mbev_scatter_split_supported(int ny, int nx, const float *canvas) {
+  const int64_t G64 = static_cast<int64_t>(ny) * nx;
+  return (G64 % 8 == 0) && ((reinterpret_cast<uintptr_t>(canvas) & 31) == 0) ? 1 : 0;
+}
+
+extern "C" int mbev_scatter_fill_empty(const int32_t *cell_table, int batch, int c_out, int ny, int nx,
+                                       float *canvas, void *stream_) {
+  if (!cell_table || !canvas || batch < 1 || c_out < 1 || ny < 1 || nx < 1) return MBEV_ERR_BAD_ARG;
+  const int64_t G64 = static_cast<int64_t>(ny) * nx;
+  if (G64 * batch > 0x7fffffffLL || !mbev_scatter_split_supported(ny, nx, canvas)) return MBEV_ERR_UNSUPPORTED;
+  const int G = static_cast<int>(G64);
+  const int tiles_per_frame = (G + kFillCells - 1) / kFillCells;
+  const int num_tiles = tiles_per_frame * batch;
+  // a streaming writer needs few warps per SM to saturate HBM; keep its footprint small so that it can share the
+  // SMs with K2 without taking its issue slots
+  static const int fill_ctas = getenv("MBEV_FILL_CTAS") ? atoi(getenv("MBEV_FILL_CTAS")) : 2;
+  static const int fill_thr = getenv("MBEV_FILL_THREADS") ? atoi(getenv("MBEV_FILL_THREADS")) : kThreads;
+  const int blocks = std::min(num_tiles, kNumSMs * fill_ctas);
+  k_fill_empty<<<blocks, fill_thr, 0, static_cast<cudaStream_t>(stream_)>>>(cell_table, c_out, G, tiles_per_frame,
+                                                                           num_tiles, canvas);
+  MBEV_CHECK_LAUNCH();
+  return MBEV_OK;
+}
+
+extern "C" int mbev_scatter_occupied(const float *feats, const int32_t *coors, const int32_t *num_pillars_dev,
+                                     int64_t pillar_capacity, const int32_t *cell_table, int batch, int c_out,
+                                     int ny, int nx, float *canvas, void *stream_) {
+  if (!cell_table || !canvas || !num_pillars_dev || batch < 1 || c_out < 1 || ny < 1 || nx < 1) return MBEV_ERR_BAD_ARG;
+  if (pillar_capacity <= 0) return MBEV_OK;
+  if (!feats || !coors) return MBEV_ERR_BAD_ARG;
+  const int64_t G64 = static_cast<int64_t>(ny) * nx;
+  if (G64 * batch > 0x7fffffffLL || !mbev_scatter_split_supported(ny, nx, canvas)) return MBEV_ERR_UNSUPPORTED;
+  const int64_t want = (pillar_capacity + kThreads / 32 - 1) / (kThreads / 32);
+  const int blocks = static_cast<int>(std::min<int64_t>(want, kNumSMs * 16));
+  k_scatter_sectors<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      feats, coors, num_pillars_dev, cell_table, batch, c_out, ny, nx, canvas);
   MBEV_CHECK_LAUNCH();
   return MBEV_OK;
 }

@@ -47,6 +47,12 @@ class _PfnFunction(torch.autograd.Function):
         weights, gammas, betas = params[:L], params[L:2 * L], params[2 * L:]
         cfg = net._config()
         training = net.training
+        if not isinstance(ctx, _NullCtx) and cfg.gemm_path == 0:
+            # A backward will follow: K2' recomputes the activations on the fp32 FMA pipe, and the parameter
+            # gradients of a train-mode BatchNorm stack are ill-conditioned (torch's own fp32 autograd is ~2e-3 from
+            # float64 on the 3-layer stack). Use the FMA forward here so that the saved statistics are bit-consistent
+            # with what the backward recomputes; the tensor-core forward serves inference and no-grad calls.
+            cfg.gemm_path = 1
         if training:
             feats, scale_shift, batch_stats = F_.pfn_forward_train(rows, kept_idx, num_points, coors, npil_dev,
                                                                   capacity, T, cfg, weights, gammas, betas)

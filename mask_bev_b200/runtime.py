@@ -16,7 +16,7 @@ from ._lib import check, ptr
 
 
 class FusedEncoderRunner:
-    def __init__(self, encoder, frame_sizes: Sequence[int], device: torch.device):
+    def __init__(self, encoder, frame_sizes: Sequence[int], device: torch.device, overlap: bool = True):
         self.enc = encoder
         self.device = torch.device(device)
         self.lib = _lib.load()
@@ -46,6 +46,11 @@ class FusedEncoderRunner:
                                                          self.total, self.cap, ctypes.byref(nbytes)),
               "encode_batch_workspace_bytes")
         self.ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
+        # second stream for the zero-fill of the canvas (runs under K2); None = single-stream, one-pass scatter
+        self.aux = torch.cuda.Stream(device=dev) if overlap else None
+
+    def _aux(self):
+        return ctypes.c_void_p(self.aux.cuda_stream) if self.aux is not None else ctypes.c_void_p(None)
 
     def refresh_params(self) -> None:
         """Re-fold the eval-mode BatchNorm after a weight update."""
@@ -63,7 +68,7 @@ class FusedEncoderRunner:
         check(self.lib.mbev_encode_batch(ptr(p), self.off, self.B, ctypes.byref(self.geo), ctypes.byref(self.params),
                                          ptr(self.cell_table), ptr(self.coors), ptr(self.num_points),
                                          ptr(self.kept_idx), ptr(self.pillar_base), self.cap, ptr(self.feats),
-                                         ptr(self.canvas), ptr(self.ws), self.ws.numel(), self._stream()),
+                                         ptr(self.canvas), ptr(self.ws), self.ws.numel(), self._stream(), self._aux()),
               "encode_batch")
         return self.canvas
 
@@ -73,7 +78,8 @@ class FusedEncoderRunner:
                                               ctypes.byref(self.geo), ctypes.byref(self.params),
                                               ptr(self.cell_table), ptr(self.coors), ptr(self.num_points),
                                               ptr(self.kept_idx), ptr(self.pillar_base), self.cap, ptr(self.feats),
-                                              ptr(self.canvas), ptr(self.ws), self.ws.numel(), self._stream()),
+                                              ptr(self.canvas), ptr(self.ws), self.ws.numel(), self._stream(),
+                                              self._aux()),
               "encode_batch_host")
         return self.canvas
 
@@ -90,6 +96,23 @@ class FusedEncoderRunner:
                                         ptr(self.coors), ptr(self.pillar_base[self.B:]), self.cap, self.geo.max_points,
                                         ctypes.byref(self.params), ptr(self.feats), ptr(self.ws), self.ws.numel(),
                                         self._stream()), "pfn_forward")
+
+    def run_fill_empty(self):
+        check(self.lib.mbev_scatter_fill_empty(ptr(self.cell_table), self.B, self.c_out, self.ny, self.nx,
+                                               ptr(self.canvas), self._stream()), "scatter_fill_empty")
+
+    def run_scatter_occupied(self):
+        check(self.lib.mbev_scatter_occupied(ptr(self.feats), ptr(self.coors), ptr(self.pillar_base[self.B:]), self.cap,
+                                             ptr(self.cell_table), self.B, self.c_out, self.ny, self.nx,
+                                             ptr(self.canvas), self._stream()), "scatter_occupied")
+
+    def run_scatter_split(self):
+        """K3a (zero-fill of the empty sectors) + K3b (occupied sectors), back to back on one stream."""
+        check(self.lib.mbev_scatter_fill_empty(ptr(self.cell_table), self.B, self.c_out, self.ny, self.nx,
+                                               ptr(self.canvas), self._stream()), "scatter_fill_empty")
+        check(self.lib.mbev_scatter_occupied(ptr(self.feats), ptr(self.coors), ptr(self.pillar_base[self.B:]), self.cap,
+                                             ptr(self.cell_table), self.B, self.c_out, self.ny, self.nx,
+                                             ptr(self.canvas), self._stream()), "scatter_occupied")
 
     def run_scatter(self):
         check(self.lib.mbev_scatter_forward(ptr(self.feats), ptr(self.cell_table), self.B, self.c_out, self.ny,

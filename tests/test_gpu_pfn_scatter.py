@@ -178,3 +178,110 @@ def test_cpu_input_is_rejected_loudly():
     enc = M.MaskBevEncoder(**kw)
     with pytest.raises(M.MbevError):
         enc([torch.zeros(10, 4)])
+
+
+# ---- tcgen05 path vs fp32-FMA path, split scatter, two-stream runner -------------------------------------------
+@pytest.mark.parametrize("chans,expect", [((128, 128, 128), "tcgen05"), ((128, 64, 128), "tcgen05"), ((64,), "tcgen05"),
+                                          ((16, 32, 64), "fma"), ((256, 128, 128), "fma")])
+def test_pfn_path_selection(chans, expect):
+    """gemm_path='auto' picks the tensor-core kernel exactly for the stacks it supports (SURVEY.md §8a envelope)."""
+    from mask_bev_b200 import functional as F_
+    kw = ref_test_kwargs(feat_channels=chans, T=32)
+    enc, _ = encoder_pair(kw, seed=1)
+    assert F_.pfn_path(enc._voxel_encoder._config(), 32) == expect
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+@pytest.mark.parametrize("T", [32, 20, 64])
+def test_pfn_tcgen05_and_fma_paths_agree_with_oracle(mode, T):
+    """Both device implementations of the Linear layers (3xTF32 tensor cores / fp32 FMA) against the dense oracle,
+    eval and train BatchNorm; T=64 exercises the block-level tcgen05 kernel (pillars longer than a warp window)."""
+    kw = ref_test_kwargs(feat_channels=(128, 128, 128), T=T)
+    enc, orc = encoder_pair(kw, seed=11)
+    enc = enc.to(DEV)
+    (enc.train if mode == "train" else enc.eval)()
+    (orc.pfn.train if mode == "train" else orc.pfn.eval)()
+    voxels, nump, coors, _ = orc.voxelize(_frames(25000, 4, seeds=(5, 6)))
+    with torch.no_grad():
+        ref = orc.encode(voxels, nump, coors).numpy()
+    outs = {}
+    for path in ("tcgen05", "fma"):
+        enc._voxel_encoder.gemm_path = path
+        with torch.no_grad():
+            outs[path] = enc.encode(torch.from_numpy(voxels).to(DEV), torch.from_numpy(nump).to(DEV),
+                                    torch.from_numpy(coors).to(DEV)).cpu().numpy()
+        assert_close(outs[path], ref, tol=2e-5 if mode == "train" else FP32_REL_TOL, what=f"{path} {mode} T={T}")
+    assert_close(outs["tcgen05"], outs["fma"], tol=2e-5, what="tcgen05 vs fma")
+
+
+def test_pfn_tcgen05_run_to_run_identical():
+    kw = ref_test_kwargs(feat_channels=(128, 128, 128), T=32)
+    enc, orc = encoder_pair(kw, seed=12)
+    enc = enc.to(DEV).train()
+    voxels, nump, coors, _ = orc.voxelize(_frames(25000, 4, seeds=(7,)))
+    args = [torch.from_numpy(a).to(DEV) for a in (voxels, nump, coors)]
+    with torch.no_grad():
+        a = enc.encode(*args).clone()
+        b = enc.encode(*args).clone()
+    assert torch.equal(a, b), "fixed-order reductions: train-mode forward must be bit-identical run to run"
+
+
+def test_tcgen05_forced_on_unsupported_stack_fails_loudly():
+    import mask_bev_b200 as M
+    kw = ref_test_kwargs(feat_channels=(16, 32, 64), T=32)
+    enc, orc = encoder_pair(kw, seed=1)
+    enc = enc.to(DEV).eval()
+    enc._voxel_encoder.gemm_path = "tcgen05"
+    voxels, nump, coors, _ = orc.voxelize(_frames(5000, 4, seeds=(1,)))
+    with pytest.raises(M.MbevError):
+        enc.encode(torch.from_numpy(voxels).to(DEV), torch.from_numpy(nump).to(DEV), torch.from_numpy(coors).to(DEV))
+
+
+@pytest.mark.parametrize("rng,vs,expect_split", [((-40, 40), 0.16, True), ((-31.25, 31.25), 0.25, False)])
+def test_split_scatter_bit_identical_to_one_pass(rng, vs, expect_split):
+    """K3a (empty sectors) + K3b (occupied sectors) == one-pass K3, bit for bit; grids whose plane is not a
+    multiple of 8 cells report unsupported."""
+    from mask_bev_b200 import _lib
+    from mask_bev_b200._lib import check, ptr
+    import ctypes
+    lib = _lib.load()
+    kw = ref_test_kwargs(feat_channels=(64,), T=32, vs=vs, x_range=rng, y_range=rng)
+    enc, _ = encoder_pair(kw, seed=2)
+    enc = enc.to(DEV).eval()
+    frames = _frames(30000, 4, seeds=(1, 2, 3))
+    with torch.no_grad():
+        canvas, aux = enc.encode_batch([torch.from_numpy(f).to(DEV) for f in frames], return_aux=True)
+    B, C, ny, nx = canvas.shape
+    ok = lib.mbev_scatter_split_supported(ny, nx, ptr(canvas))
+    assert bool(ok) == expect_split == ((ny * nx) % 8 == 0)
+    if not ok:
+        return
+    out = torch.full_like(canvas, float("nan"))
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    table = aux.cell_table
+    check(lib.mbev_scatter_fill_empty(ptr(table), B, C, ny, nx, ptr(out), s), "fill_empty")
+    check(lib.mbev_scatter_occupied(ptr(aux.feats), ptr(aux.coors), ptr(aux.pillar_base[B:]), aux.coors.shape[0],
+                                    ptr(table), B, C, ny, nx, ptr(out), s), "occupied")
+    assert torch.equal(out, canvas)
+
+
+def test_runner_two_streams_matches_single_stream_and_oracle():
+    from mask_bev_b200.runtime import FusedEncoderRunner
+    kw = ref_test_kwargs(feat_channels=(128, 128, 128), T=32)
+    enc, orc = encoder_pair(kw, seed=13)
+    enc = enc.to(DEV).eval()
+    orc.pfn.eval()
+    frames = _frames(40000, 4, seeds=(21, 22, 23, 24))
+    pts = torch.from_numpy(np.concatenate(frames, 0)).to(DEV)
+    outs = []
+    for overlap in (True, False):
+        r = FusedEncoderRunner(enc, [len(f) for f in frames], torch.device(DEV), overlap=overlap)
+        r.canvas.fill_(float("nan"))
+        for _ in range(3):  # repeated calls reuse the buffers: forks / joins must stay ordered
+            out = r.run_device(pts)
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[1])
+    with torch.no_grad():
+        ref = orc.forward(frames).numpy()
+    assert_close(outs[0].cpu().numpy(), ref, what="runner canvas")
