@@ -230,7 +230,7 @@ def run_ours(args):
     cfg, kwargs, frames = build_workload(args.workload, rank)
     B = len(frames)
     enc, pfn_cpu = make_encoder(kwargs, dev)
-    runner = FusedEncoderRunner(enc, [len(f) for f in frames], dev, overlap=not args.no_overlap)
+    runner = FusedEncoderRunner(enc, [len(f) for f in frames], dev, overlap=args.overlap)
     host = torch.from_numpy(np.concatenate(frames, 0)).pin_memory()
     runner.points_dev.copy_(host)
     counts_host = torch.empty((B + 1,), dtype=torch.int32).pin_memory()
@@ -364,7 +364,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti_b16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="single stream, one-pass scatter (no K2 || K3a overlap)")
+    ap.add_argument("--overlap", action="store_true", help="two streams: K3a zero-fill under K2, then K3b (default: one stream, one-pass K3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -252,6 +252,14 @@ extern "C" int mbev_scatter_fill_empty(const int32_t *cell_table, int batch, int
   const int num_tiles = tiles_per_frame * batch;
   // a streaming writer needs few warps per SM to saturate HBM; keep its footprint small so that it can share the
   // SMs with K2 without taking its issue slots
+  static bool attr_done = false;
+  if (!attr_done) {
+    // same shared-memory / L1 split as the 200+ KB K2 kernels, so that the SM does not have to drain to switch
+    // configuration and the two kernels can be co-resident
+    MBEV_CUDA(cudaFuncSetAttribute(k_fill_empty, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    attr_done = true;
+  }
   static const int fill_ctas = getenv("MBEV_FILL_CTAS") ? atoi(getenv("MBEV_FILL_CTAS")) : 2;
   static const int fill_thr = getenv("MBEV_FILL_THREADS") ? atoi(getenv("MBEV_FILL_THREADS")) : kThreads;
   const int blocks = std::min(num_tiles, kNumSMs * fill_ctas);

@@ -6,5 +6,5 @@ timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out
 tail -3 gpurun_out/full_bench.err
 python -c "
 import json;d=json.load(open('gpurun_out/full_bench.json'));print('overlap', {k:round(v['ms'],4) for k,v in d['kernels'].items()}); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['gpu_launches'])"
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-overlap 2>/dev/null | python -c "
-import sys,json;d=json.loads(sys.stdin.read());print('no-overlap', d['ms_per_step'], d['value'], d['e2e']['value'])"
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --overlap 2>/dev/null | python -c "
+import sys,json;d=json.loads(sys.stdin.read());print('overlap-on', d['ms_per_step'], d['value'], d['e2e']['value'])"
