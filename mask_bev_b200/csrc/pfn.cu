@@ -24,7 +24,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
-#include "pfn_tcw.cuh"
+#include "pfn_tcw2.cuh"
 
 namespace mbev {
 namespace {

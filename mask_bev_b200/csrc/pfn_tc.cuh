@@ -175,7 +175,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
 // ---- row-balanced static partition ------------------------------------------------------------------------
 // Pillars are numbered in order of first appearance, so the heavy pillars of a frame come first: an equal-count
 // split leaves the CTAs 3x apart in rows. k_row_blocks sums the compact rows (n + [n < T]) of blocks of 32
-// pillars, k_row_bounds prefix-sums the blocks and gives sub-range b (4 per CTA) the blocks whose prefix falls in
+// pillars, k_row_bounds prefix-sums the blocks and gives sub-range b (8 per CTA) the blocks whose prefix falls in
 // [R b / G, R (b+1) / G). Static and deterministic (train-mode statistics stay run-to-run identical).
 constexpr int kBlkPillars = 32;
 
@@ -383,7 +383,7 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
     // =========================================== epilogue warps ===============================================
     const int row = ((warp & 3) << 5) | lane, h = warp >> 2;
     const uint32_t tlane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);  // this warp's TMEM lane quadrant
-    const int p_begin = __ldg(bounds + 4 * blockIdx.x), p_end = __ldg(bounds + 4 * blockIdx.x + 4);  // 4 sub-ranges per CTA
+    const int p_begin = __ldg(bounds + 8 * blockIdx.x), p_end = __ldg(bounds + 8 * blockIdx.x + 8);  // 8 sub-ranges per CTA
     const uint32_t my_slab = bar_slab + 64u * h;
     uint32_t ev = 0, par_d0 = 0, par_d1 = 0;
     double st1[4] = {0.0, 0.0, 0.0, 0.0}, st2[4] = {0.0, 0.0, 0.0, 0.0};
@@ -705,7 +705,7 @@ struct Plan {
   int nb;         // blocks of kBlkPillars pillars covering the capacity
   int *blocksum;  // (nb)
   int *prefix;    // (nb + 1)
-  int *bounds;    // (4 * grid + 1) first pillar of each quarter-CTA sub-range (k_pfn_tcw: one per TMEM lane quadrant)
+  int *bounds;    // (8 * grid + 1) first pillar of each sub-range (k_pfn_tcw2: one per set and TMEM lane quadrant)
 };
 
 // MBEV_OK when the stack fits the tensor-core kernel, MBEV_ERR_UNSUPPORTED when it must run on the FMA kernel.
@@ -776,7 +776,7 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capaci
   out->nb = static_cast<int>(nb);
   out->blocksum = cw.take<int>(out->nb);
   out->prefix = cw.take<int>(out->nb + 1);
-  out->bounds = cw.take<int>(4 * out->grid + 1);
+  out->bounds = cw.take<int>(8 * out->grid + 1);
   out->ws_bytes = cw.off;
   return MBEV_OK;
 }
@@ -792,7 +792,7 @@ inline int launch_prep(const MbevPfnParams *p, Plan &pl, const int32_t *num_poin
   MBEV_CHECK_LAUNCH();
   k_row_blocks<<<(pl.nb + 7) / 8, 256, 0, stream>>>(num_points, num_pillars_dev, pl.k.T, pl.nb, pl.blocksum);
   MBEV_CHECK_LAUNCH();
-  k_row_bounds<<<1, 1024, 0, stream>>>(pl.blocksum, pl.nb, num_pillars_dev, 4 * pl.grid, pl.prefix, pl.bounds);
+  k_row_bounds<<<1, 1024, 0, stream>>>(pl.blocksum, pl.nb, num_pillars_dev, 8 * pl.grid, pl.prefix, pl.bounds);
   MBEV_CHECK_LAUNCH();
   return MBEV_OK;
 }

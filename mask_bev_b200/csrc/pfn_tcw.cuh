@@ -154,9 +154,9 @@ k_pfn_tcw(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, 
     const int quad = warp & 3, h = warp >> 2;
     const int row = (quad << 5) | lane;
     const uint32_t tlane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
-    const int sub = 4 * blockIdx.x + quad;
+    const int sub = 8 * blockIdx.x + 2 * quad;  // the partition has 8 sub-ranges per CTA: a quadrant takes two
     int cursor = __ldg(bounds4 + sub);
-    const int pend = __ldg(bounds4 + sub + 1);
+    const int pend = __ldg(bounds4 + sub + 2);
     const uint32_t my_ev = bar_ev + 64u * h;
     uint32_t ev = 0, par_d0 = 0, par_d1 = 0, par_x0 = 0;
     float *xd = s_deco + row * kDecoPitch;
@@ -400,45 +400,6 @@ inline int tcw_split(const Kargs &k) {  // 0: not supported
     if (k.U[l] % 64) split = 2;
   }
   return split;
-}
-
-// FULL forward: warp-local kernel when it applies, else (and for every STATS launch) the block-level kernel.
-inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, const int32_t *num_points,
-                  const int32_t *coors, float *feats, int stat_layer, cudaStream_t stream) {
-  Kargs k = pl.k;
-  k.stat_layer = stat_layer;
-  {
-    static const int dbg = getenv("MBEV_TC_DBG") ? atoi(getenv("MBEV_TC_DBG")) : 0;
-    k.dbg = dbg;
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
-    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_done = true;
-  }
-  const int split = stat_layer < 0 ? tcw_split(k) : 0;
-  if (split) {
-    // k_pfn_tcw needs the weights, the [128][20] staging rows, scale/shift and the barriers — not the block
-    // kernel's transposition scratch and tables. Leaving a few KB of the SM's 228 KB unallocated lets small CTAs
-    // of another stream (the canvas zero-fill, K3a) run on the same SMs while this kernel computes.
-    uint32_t o = (k.w_bytes + 127u) & ~127u;
-    k.o_scr = o; o += kRows * kDecoPitch * 4 + 8 * 24 * 8;  // staging rows + the developer timestamp area
-    k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
-    k.o_tab = o; o += 16;
-    k.o_bar = o; o += 40 * 8 + 8;
-    k.smem_bytes = static_cast<int>(o);
-  }
-  if (split == 4) {
-    k_pfn_tcw<4><<<pl.grid, 17 * 32, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k);
-  } else if (split == 2) {
-    k_pfn_tcw<2><<<pl.grid, 9 * 32, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k);
-  } else {
-    k_pfn_tc<<<pl.grid, kThreads, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k);
-  }
-  MBEV_CHECK_LAUNCH();
-  return MBEV_OK;
 }
 
 }  // namespace tc
