@@ -211,6 +211,8 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
   const uint32_t bar_w = bar0 + 8 * kW2BarW;
   const uint32_t smem_base = smem_u32(smem_raw);
   const int L = k.L;
+  long long *s_ts = reinterpret_cast<long long *>(smem_raw + k.o_bar + 128);  // dbg: [8][24] timestamps (plan reserves them)
+#define MBEV_TS(slot) do { if ((k.dbg & 8) && blockIdx.x == 0 && lane == 0 && c >= 2 && c < 10) s_ts[(c - 2) * 24 + (slot)] = clock64(); } while (0)
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -309,8 +311,11 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
     int *live = s_live + 4 * set;
 
     for (int c = 0;; ++c) {
+      if (warp == 0) MBEV_TS(0);
       const Window w = pack_window(num_points, cursor, pend, k.T, lane);
+      if (warp == 0) MBEV_TS(1);
       if (h == 0) build_x0(k, w, rows_src, kept_idx, coors, xd, t_ah, t_al);
+      if (warp == 0) MBEV_TS(2);
       // ---- set rendezvous: every window's layer-0 input is in TMEM, nobody reads the previous chunk's D ------
       tc_fence_before();
       __syncwarp();
@@ -322,6 +327,7 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
       mbar_wait(bs + 8 * kW2X0, par_x0);
       par_x0 ^= 1u;
       if (*reinterpret_cast<volatile int *>(live + (c & 3)) == 0) break;
+      if (warp == 0) MBEV_TS(3);
 
       for (int l = 0; l < L; ++l) {
         const int U = k.U[l];
@@ -329,6 +335,7 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
         mbar_wait(bs + 8 * kW2D, par_d);
         par_d ^= 1u;
         tc_fence_after();
+        if (warp == 0) MBEV_TS(4 + 4 * l);
         const int Uh = U >> 1;
         const int nbat = Uh >> 4;
         const float *sc = s_ss + (2 * l) * MBEV_MAX_UNITS + h * Uh, *sh = s_ss + (2 * l + 1) * MBEV_MAX_UNITS + h * Uh;
@@ -362,10 +369,13 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bs + 8 * kW2EVX);
+          if (warp == 0) MBEV_TS(5 + 4 * l);
           seg_max16(w, lane, a0);  // runs while the x-part MMAs do
           if (nbat > 1) seg_max16(w, lane, a1);
+          if (warp == 0) MBEV_TS(6 + 4 * l);
           mbar_wait(bs + 8 * kW2XC, par_xc);  // the x-part MMAs have read A: its columns are free again
           par_xc ^= 1u;
+          if (warp == 0) MBEV_TS(7 + 4 * l);
           tc_fence_after();
           split_store16(t_ah + c0, t_al + c0, a0);  // max half: K index = U + unit index, same A columns
           if (nbat > 1) split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
@@ -375,12 +385,22 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
           if (lane == 0) mbar_arrive(bs + 8 * kW2EVM);
         }
       }
+      if (warp == 0) MBEV_TS(16);
       cursor += w.cnt;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == kW2EpiWarps) tmem_dealloc(tmem, kTmemCols);
+  if ((k.dbg & 8) && blockIdx.x == 0 && tid == 0) {
+    for (int cc = 0; cc < 8; ++cc) {
+      const long long *q = s_ts + cc * 24;
+      printf("chunk %d: pack %lld x0 %lld rdv %lld | L0: Dw %lld ld+st %lld segmax %lld XCw %lld | L1: mst %lld Dw... %lld ld+st %lld segmax %lld XCw %lld | L2: mst+Dw %lld epi %lld | total %lld\n", cc + 2,
+             q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4], q[6] - q[5], q[7] - q[6],
+             0LL, q[8] - q[7], q[9] - q[8], q[10] - q[9], q[11] - q[10], q[12] - q[11], q[16] - q[12], q[16] - q[0]);
+    }
+  }
+#undef MBEV_TS
 }
 
 // shared-memory plan of k_pfn_tcw2 (returns false when the stack does not fit)
@@ -393,7 +413,7 @@ inline bool tcw2_plan(Kargs &k) {
   k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
   k.o_tab = o; o += 4 * kW2Sets * 4;
   o = (o + 15u) & ~15u;
-  k.o_bar = o; o += kW2NumBars * 8 + 8;
+  k.o_bar = o; o += 128 + 8 * 24 * 8;  // barriers + TMEM slot, developer timestamps
   k.smem_bytes = static_cast<int>(o);
   return k.smem_bytes <= kSmemLimit;
 }
