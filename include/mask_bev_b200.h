@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 3
+#define MBEV_ABI_VERSION 4
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -183,9 +183,31 @@ MBEV_API int mbev_scatter_backward(const float *dcanvas, const int32_t *cell_tab
                           int nx, float *dfeats, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K2+K3 in one kernel (eval mode): PillarFeatureNet.forward and PointPillarsScatter.forward_batch
+ * (mask_bev_encoders.py:119-123) fused — the PFN walks the pillars in cell order and writer warps of the same
+ * persistent kernel stream the finished canvas region out (zeros or features, every byte once) while the next
+ * pillars compute, so the HBM-bound canvas write hides under the compute-bound PFN. Needs the tcgen05 path, T <= 32,
+ * ny*nx a multiple of 4 (>= 128) and a 16-byte aligned canvas: probe with mbev_pfn_scatter_supported (canvas may be
+ * NULL for a shape-only probe). `cell_table` must be the table of exactly these pillars (mbev_voxelize /
+ * mbev_build_cell_table); `feats` is still written (pillar_capacity, units[L-1]). Results are bit-identical to
+ * mbev_pfn_forward + mbev_scatter_forward.
+ * ---------------------------------------------------------------------------------------------- */
+MBEV_API int mbev_pfn_scatter_supported(const MbevPfnParams *params, int T, int batch, int ny, int nx,
+                                        const float *canvas);
+MBEV_API int mbev_pfn_scatter_default(void); /* 1 when mbev_encode_batch takes the fused kernel (MBEV_FUSED_CANVAS=1) */
+MBEV_API int mbev_pfn_scatter_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity, int batch,
+                                              int ny, int nx, size_t *bytes);
+MBEV_API int mbev_pfn_scatter_forward(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
+                                      const int32_t *coors, int64_t pillar_capacity, int T,
+                                      const MbevPfnParams *params, const int32_t *cell_table, int batch, int ny,
+                                      int nx, float *feats, float *canvas, void *workspace, size_t workspace_bytes,
+                                      void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused batch entry (additive): K1 -> K2(eval) -> K3, no host sync.
  * Equivalent to MaskBevEncoder.forward (mask_bev_encoders.py:77-91) without the trailing LayerNorm.
- * aux_stream: optional second stream (NULL = everything on `stream`). When given and the canvas allows the
+ * K2 and K3 run as the single fused kernel above when mbev_pfn_scatter_default() and mbev_pfn_scatter_supported() say so.
+ * aux_stream: optional second stream (NULL = everything on `stream`); only used when the fused kernel is not. When given and the canvas allows the
  * two-kernel scatter, the zero-fill of the empty sectors runs on aux_stream concurrently with K2 (HBM-bound
  * writes under a compute-bound kernel); the call forks and joins with events, so the caller only ever orders
  * against `stream`.

@@ -1,4 +1,6 @@
 // C-ABI glue: version probes, launch counter, and the fused batch entry K1 -> K2(eval) -> K3.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mbev {
@@ -40,6 +42,12 @@ int fused_ws(const MbevGeometry *geo, const MbevPfnParams *params, int batch, in
   if (st) return st;
   st = mbev_pfn_workspace_bytes(params, geo->max_points, pillar_capacity, 0, &pb);
   if (st) return st;
+  if (mbev_pfn_scatter_supported(params, geo->max_points, batch, geo->grid[1], geo->grid[0], nullptr)) {
+    size_t fb = 0;
+    st = mbev_pfn_scatter_workspace_bytes(params, geo->max_points, pillar_capacity, batch, geo->grid[1], geo->grid[0], &fb);
+    if (st) return st;
+    pb = std::max(pb, fb);
+  }
   w->vox_off = 0;
   w->vox_bytes = vb;
   w->pfn_off = align_up(vb);
@@ -75,6 +83,11 @@ extern "C" int mbev_encode_batch(const float *points, const int64_t *frame_offse
                      pillar_capacity, ws + w.vox_off, w.vox_bytes, stream);
   if (st) return st;
   const int c_out = params->units[params->num_layers - 1], ny = geo->grid[1], nx = geo->grid[0];
+  if (mbev_pfn_scatter_default() &&
+      mbev_pfn_scatter_supported(params, geo->max_points, batch, ny, nx, canvas))  // K2 + K3 as one kernel (opt-in)
+    return mbev_pfn_scatter_forward(points, geo->num_feats, kept_idx, num_points, coors, pillar_capacity,
+                                    geo->max_points, params, cell_table, batch, ny, nx, feats, canvas, ws + w.pfn_off,
+                                    w.pfn_bytes, stream);
   const bool split = aux_stream && aux_stream != stream && mbev_scatter_split_supported(ny, nx, canvas);
   cudaStream_t main_s = static_cast<cudaStream_t>(stream), aux_s = static_cast<cudaStream_t>(aux_stream);
   cudaEvent_t e_fork = nullptr, e_join = nullptr;

@@ -59,7 +59,7 @@ struct Kargs {
   int cluster, vcenter, dist, legacy, vcd;
   float vx, vy, vz, xo, yo, zo;
   int um;
-  uint32_t o_scr, o_ss, o_tab, o_bar;  // byte offsets in dynamic shared memory
+  uint32_t o_scr, o_ss, o_tab, o_bar, o_zero;  // byte offsets in dynamic shared memory
   int smem_bytes;
   int stat_layer;    // -1: full forward; s: accumulate the statistics of layer s and stop
   double *partials;  // (gridDim.x, 2, um)

@@ -23,6 +23,31 @@ namespace tc {
 constexpr int kW2Sets = 2;
 constexpr int kW2EpiWarps = 8 * kW2Sets;               // per set: 4 quadrants x 2 column halves
 constexpr int kW2Threads = (kW2EpiWarps + kW2Sets) * 32;
+// canvas form (K2 + K3 in one kernel): 1024 threads = 16 epilogue warps | 2 issuers + 14 canvas writers. The CTA
+// launches at 64 registers per thread; setmaxnreg then moves registers inside that allocation (it cannot take more
+// from the SM): epilogue warpgroups 96, the others 32 — 512 x 96 + 512 x 32 = 1024 x 64. One warp sustains only a few
+// bytes per clock of streaming stores (measured: 2 writer warps per SM -> 1.6 TB/s, 8 -> 3.4 TB/s), so every warp
+// the register file can hold next to the epilogue is a writer.
+constexpr int kCvWriterWarp0 = kW2EpiWarps + kW2Sets;
+constexpr int kCvWriters = 14;
+constexpr int kCvThreads = (kCvWriterWarp0 + kCvWriters) * 32;
+constexpr int kCvRegsEpi = 96, kCvRegsRest = 32;
+constexpr int kCvRun = 4;       // strips per writer claim: zeros go out as 2 KB bulk copies per plane
+constexpr int kCvZeroBytes = kCvRun * 128 * 4;  // shared-memory zero source of the bulk copies
+constexpr int kCvStrip = 128;  // cells per strip: one warp-wide float4 store covers a strip of one plane (512 B)
+
+// Canvas side of the fused kernel. Cells are numbered globally, gc = b * G + y * nx + x; a STRIP is 128 consecutive
+// global cells. Sub-range `s` (8 per CTA) owns the strips [sb[s], sb[s+1]) and the pillars ord[pb[s] .. pb[s+1]) that
+// live in them (ord lists the pillars in global cell order).
+struct CanvasArgs {
+  const int *table;   // (NC) cell -> pillar id, -1 empty
+  const int2 *ord;    // (P) (pillar id, num_points) in cell order
+  const int *sb;      // (8 * grid + 1) first strip of each sub-range
+  const int *pb;      // (8 * grid + 1) first ord index of each sub-range
+  const int *spre;    // (NS) occupied cells (= ord index) before each strip
+  float *canvas;      // (B, C_out, G)
+  int G, NC, Cout;
+};
 constexpr int kW2SetCols = 256;                         // TMEM columns per set: A_hi [0,64) A_lo [64,128) D [128,256)
 constexpr int kW2BarW = 0, kW2BarSet = 1, kW2BarsPerSet = 5, kW2NumBars = kW2BarSet + kW2Sets * kW2BarsPerSet;
 enum { kW2X0 = 0, kW2D = 1, kW2XC = 2, kW2EVX = 3, kW2EVM = 4 };
@@ -36,10 +61,21 @@ struct Window {
 
 // pack whole pillars cursor, cursor+1, ... into a 32-row window (lane r = row r); identical on every warp that
 // calls it with the same cursor
-__device__ __forceinline__ Window pack_window(const int *__restrict__ num_points, int cursor, int pend, int T, int lane) {
+// `ord` (optional): walk order, ord[j] = (pillar id, num_points) — the canvas kernel walks pillars in CELL order
+__device__ __forceinline__ Window pack_window(const int *__restrict__ num_points, const int2 *__restrict__ ord, int cursor,
+                                              int pend, int T, int lane) {
   Window w;
   const bool cand = cursor + lane < pend;
-  const int np = cand ? __ldg(num_points + cursor + lane) : 0;
+  int np = 0, pid = cursor + lane;
+  if (cand) {
+    if (ord) {
+      const int2 o = __ldg(ord + cursor + lane);
+      pid = o.x;
+      np = o.y;
+    } else {
+      np = __ldg(num_points + cursor + lane);
+    }
+  }
   const int need = cand ? np + (np < T ? 1 : 0) : 0;
   int incl = need;
 #pragma unroll
@@ -68,7 +104,7 @@ __device__ __forceinline__ Window pack_window(const int *__restrict__ num_points
   w.s1 = w.s0 + nd - 1;
   w.t = lane - w.s0;
   w.real = w.inwin && w.t < w.n;
-  w.pil = cursor + pi;
+  w.pil = ord ? __shfl_sync(0xffffffffu, pid, pi) : cursor + pi;
   int ml = w.inwin ? nd : 1;
 #pragma unroll
   for (int o = 16; o; o >>= 1) ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, o));
@@ -196,15 +232,127 @@ __device__ __forceinline__ void seg_max16(const Window &w, int lane, float (&a)[
   for (int j = 0; j < 16; ++j) a[j] = __shfl_sync(0xffffffffu, a[j], w.s1);
 }
 
-__global__ void __launch_bounds__(kW2Threads, 1)
+// ---- canvas writers ----------------------------------------------------------------------------------------------
+// The 14 writer warps of a CTA share its 8 sub-ranges: a writer claims the next RUN (4 strips = 512 cells) of a
+// sub-range (shared-memory ticket, preferring "its own" sub-range so that claims stay near every sub-range's compute
+// frontier), and
+//   1. zero-fills the run in all C_out planes with bulk-async copies (TMA engine, cp.async.bulk shared -> global, 2 KB
+//      per plane from a zero buffer in shared memory; one lane issues them, no registers or LSU slots involved) —
+//      no dependency on the PFN, this is ~97 % of the bytes;
+//   2. for every strip of the run that holds pillars: waits until both column halves of all of them are in `feats`
+//      (progress counters of the sub-range), then per pillar reads the 512-byte feature row coalesced (lane l =
+//      channels 4l..4l+3) and drops the values into their planes (4-byte stores into sectors zero-filled a moment
+//      ago: they merge in L2).
+// At most 14 runs per CTA are zero-filled ahead of their features, so the merge window is microseconds.
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void put_pillar(const CanvasArgs &cv, const float *feats, const int p, const int gcell,
+                                           const int lane) {
+  if (4 * lane >= cv.Cout) return;
+  const float4 v = __ldcg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(p) * cv.Cout) + lane);
+  const size_t G = static_cast<size_t>(cv.G);
+  const int b = gcell / cv.G;
+  float *o = cv.canvas + (static_cast<size_t>(b) * cv.Cout + 4 * lane) * G + (gcell - b * cv.G);
+  o[0] = v.x;
+  o[G] = v.y;
+  o[2 * G] = v.z;
+  o[3 * G] = v.w;
+}
+
+__device__ __forceinline__ void canvas_writer(const CanvasArgs &cv, const float *feats, const volatile int *s_prog,
+                                              int *s_next, const uint32_t zero_smem, const int wid, const int lane,
+                                              const int dbg) {
+  const size_t G = static_cast<size_t>(cv.G);
+  const int *sb = cv.sb + 8 * blockIdx.x, *pb = cv.pb + 8 * blockIdx.x;
+  for (;;) {
+    int sub = -1, s_first = 0, s_last = 0;
+    for (int a = 0; a < 8 && sub < 0; ++a) {  // next run of the preferred sub-range, else of the following ones
+      const int sidx = (wid + a) & 7;
+      const int s0 = __ldg(sb + sidx), s1 = __ldg(sb + sidx + 1);
+      if (*reinterpret_cast<volatile int *>(s_next + sidx) * kCvRun >= s1 - s0) continue;  // exhausted (cheap pre-check)
+      int idx = 0;
+      if (lane == 0) idx = atomicAdd(s_next + sidx, 1);
+      idx = __shfl_sync(0xffffffffu, idx, 0);
+      if (s0 + kCvRun * idx < s1) {
+        sub = sidx;
+        s_first = s0 + kCvRun * idx;
+        s_last = min(s_first + kCvRun, s1);
+      }
+    }
+    if (sub < 0) break;
+    // 1. zeros: [c0, c1) global cells, split at a frame boundary if the run straddles one
+    if (lane == 0) {
+      const int c0 = s_first * kCvStrip, c1 = min(s_last * kCvStrip, cv.NC);
+      const int b0 = c0 / cv.G;
+      const int cm = min(c1, (b0 + 1) * cv.G);  // end of the part inside frame b0
+      float *o0 = cv.canvas + static_cast<size_t>(b0) * cv.Cout * G + (c0 - b0 * cv.G);
+      float *o1 = cv.canvas + static_cast<size_t>(b0 + 1) * cv.Cout * G;
+      for (int ch = 0; ch < cv.Cout; ++ch) {
+        bulk_s2g(o0 + ch * G, zero_smem, static_cast<uint32_t>(cm - c0) * 4u);
+        if (c1 > cm) bulk_s2g(o1 + ch * G, zero_smem, static_cast<uint32_t>(c1 - cm) * 4u);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    // 2. features
+    bool waited = false;
+    for (int strip = s_first; strip < s_last; ++strip) {
+      const int gc = strip * kCvStrip + 4 * lane;
+      const int4 pid = (gc < cv.NC) ? __ldg(reinterpret_cast<const int4 *>(cv.table + gc)) : make_int4(-1, -1, -1, -1);
+      int cnt = __reduce_add_sync(0xffffffffu, (pid.x >= 0) + (pid.y >= 0) + (pid.z >= 0) + (pid.w >= 0));
+      if (dbg & 16) cnt = 0;
+      if (cnt == 0) continue;
+      const int need = __ldg(cv.spre + strip) + cnt - __ldg(pb + sub);
+      unsigned idle = 0;
+      while (min(s_prog[2 * sub], s_prog[2 * sub + 1]) < need) {
+        __nanosleep(100);
+        if (++idle > (1u << 24)) return;  // watchdog (seconds): never hang the device on a broken partition
+      }
+      __threadfence_block();  // acquire: the feature rows behind the progress counters
+      if (!waited) {          // the zeros of this run have landed before any feature is dropped on them
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncwarp();
+        waited = true;
+      }
+      const int g0 = strip * kCvStrip;
+      for (unsigned m = __ballot_sync(0xffffffffu, pid.x >= 0); m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        put_pillar(cv, feats, __shfl_sync(0xffffffffu, pid.x, src), g0 + 4 * src, lane);
+      }
+      for (unsigned m = __ballot_sync(0xffffffffu, pid.y >= 0); m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        put_pillar(cv, feats, __shfl_sync(0xffffffffu, pid.y, src), g0 + 4 * src + 1, lane);
+      }
+      for (unsigned m = __ballot_sync(0xffffffffu, pid.z >= 0); m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        put_pillar(cv, feats, __shfl_sync(0xffffffffu, pid.z, src), g0 + 4 * src + 2, lane);
+      }
+      for (unsigned m = __ballot_sync(0xffffffffu, pid.w >= 0); m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        put_pillar(cv, feats, __shfl_sync(0xffffffffu, pid.w, src), g0 + 4 * src + 3, lane);
+      }
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk writes done before the CTA exits
+}
+
+template <bool kCanvas>
+__global__ void __launch_bounds__(kCanvas ? kCvThreads : kW2Threads, 1)
 k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, const int *__restrict__ num_points,
            const int *__restrict__ coors, const int *__restrict__ bounds8, float *__restrict__ feats,
-           const __grid_constant__ Kargs k) {
+           const __grid_constant__ Kargs k, const __grid_constant__ CanvasArgs cv) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kNT = kCanvas ? kCvThreads : kW2Threads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float *s_deco = reinterpret_cast<float *>(smem_raw + k.o_scr);  // [2 sets][128][20] private staging rows
   float *s_ss = reinterpret_cast<float *>(smem_raw + k.o_ss);     // [L][2][128]
   int *s_live = reinterpret_cast<int *>(smem_raw + k.o_tab);      // [2 sets][4] live windows of chunk c (ring)
+  int *s_prog = s_live + 4 * kW2Sets;  // canvas: [8 sub-ranges][2 column halves] pillars whose features are in `feats`
+  int *s_next = s_prog + 16;           // canvas: [8 sub-ranges] next strip ticket
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + k.o_bar);
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + kW2NumBars);
   const uint32_t bar0 = smem_u32(s_bar);
@@ -227,10 +375,16 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 4 * kW2Sets) s_live[tid] = 0;
+  if (kCanvas && tid < 24) s_prog[tid] = 0;  // progress counters and strip tickets
+  if (kCanvas) {  // zero source of the writers' bulk copies (generic-proxy writes, read by the async proxy)
+    for (int i = tid; i < kCvZeroBytes / 16; i += kNT)
+      reinterpret_cast<float4 *>(smem_raw + k.o_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncwarp();
   if (warp == kW2EpiWarps) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   for (int l = 0; l < L; ++l) {
-    for (int i = tid; i < k.U[l]; i += kW2Threads) {
+    for (int i = tid; i < k.U[l]; i += kNT) {
       s_ss[(2 * l) * MBEV_MAX_UNITS + i] = __ldg(k.scale[l] + i);
       s_ss[(2 * l + 1) * MBEV_MAX_UNITS + i] = __ldg(k.shift[l] + i);
     }
@@ -239,8 +393,16 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
+  if (kCanvas) {  // register budget per role (see kCvRegs*)
+    if (warp < kW2EpiWarps) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kCvRegsEpi));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCvRegsRest));
+  }
 
-  if (warp >= kW2EpiWarps) {
+  if (kCanvas && warp >= kCvWriterWarp0) {
+    // =========================================== canvas writers ===============================================
+    if (!(k.dbg & 32))
+      canvas_writer(cv, feats, s_prog, s_next, smem_base + k.o_zero, warp - kCvWriterWarp0, lane, k.dbg);
+  } else if (warp >= kW2EpiWarps) {
     // =========================================== MMA issuer of set `set` =====================================
     const int set = warp - kW2EpiWarps;
     const bool leader = lane == 0;
@@ -304,15 +466,18 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
     const uint32_t t_ah = tl, t_al = tl + 64, t_d = tl + 128;
     const uint32_t bs = bar0 + 8 * (kW2BarSet + kW2BarsPerSet * set);
     const int sub = 8 * blockIdx.x + 4 * set + quad;
-    int cursor = __ldg(bounds8 + sub);
-    const int pend = __ldg(bounds8 + sub + 1);
+    const int *bnd = kCanvas ? cv.pb : bounds8;
+    const int2 *ord = kCanvas ? cv.ord : nullptr;
+    int cursor = __ldg(bnd + sub);
+    const int pend = (kCanvas && (k.dbg & 64)) ? cursor : __ldg(bnd + sub + 1);  // dbg 64: writers only
+    const int cursor0 = cursor;
     uint32_t par_d = 0, par_x0 = 0, par_xc = 0;
     float *xd = s_deco + (set * kRows + row) * kDecoPitch;
     int *live = s_live + 4 * set;
 
     for (int c = 0;; ++c) {
       if (warp == 0) MBEV_TS(0);
-      const Window w = pack_window(num_points, cursor, pend, k.T, lane);
+      const Window w = pack_window(num_points, ord, cursor, pend, k.T, lane);
       if (warp == 0) MBEV_TS(1);
       if (h == 0) build_x0(k, w, rows_src, kept_idx, coors, xd, t_ah, t_al);
       if (warp == 0) MBEV_TS(2);
@@ -387,6 +552,13 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
       }
       if (warp == 0) MBEV_TS(16);
       cursor += w.cnt;
+      if (kCanvas) {  // release: this warp's feature stores, then the progress counter its writer polls
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          *reinterpret_cast<volatile int *>(s_prog + 2 * (4 * set + quad) + h) = cursor - cursor0;
+        }
+      }
     }
   }
   tc_fence_before();
@@ -404,16 +576,21 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
 }
 
 // shared-memory plan of k_pfn_tcw2 (returns false when the stack does not fit)
-inline bool tcw2_plan(Kargs &k) {
+inline bool tcw2_plan(Kargs &k, bool canvas = false) {
   if (tcw_split(k) == 0) return false;
   for (int l = 0; l + 1 < k.L; ++l)
     if (k.U[l] > 64) return false;
   uint32_t o = (k.w_bytes + 127u) & ~127u;
   k.o_scr = o; o += kW2Sets * kRows * kDecoPitch * 4;
   k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
-  k.o_tab = o; o += 4 * kW2Sets * 4;
+  k.o_tab = o; o += 4 * kW2Sets * 4 + 24 * 4;  // live ring + the canvas kernel's progress counters and strip tickets
   o = (o + 15u) & ~15u;
   k.o_bar = o; o += 128 + 8 * 24 * 8;  // barriers + TMEM slot, developer timestamps
+  k.o_zero = 0;
+  if (canvas) {
+    o = (o + 127u) & ~127u;
+    k.o_zero = o; o += kCvZeroBytes;
+  }
   k.smem_bytes = static_cast<int>(o);
   return k.smem_bytes <= kSmemLimit;
 }
@@ -432,7 +609,7 @@ inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, co
     MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_done = true;
   }
   const bool allow_w = !(force && !strcmp(force, "tc"));
@@ -440,7 +617,8 @@ inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, co
   const int split = (stat_layer < 0 && allow_w) ? tcw_split(k) : 0;
   Kargs k2 = k;
   if (split && allow_w2 && tcw2_plan(k2)) {
-    k_pfn_tcw2<<<pl.grid, kW2Threads, k2.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k2);
+    k_pfn_tcw2<false><<<pl.grid, kW2Threads, k2.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats,
+                                                                      k2, CanvasArgs());
   } else if (split) {
     // k_pfn_tcw needs the weights, the [128][20] staging rows, scale/shift and the barriers — not the block
     // kernel's transposition scratch and tables

@@ -286,7 +286,8 @@ extern "C" int mbev_voxelize(const float *points, const int64_t *frame_offsets_h
   const int total = fr.off[batch];
   if (total > 0 && !points) return MBEV_ERR_BAD_ARG;
   const GeoK g = make_geok(*geo);
-  const int64_t need_cap = std::min<int64_t>(total, static_cast<int64_t>(batch) * g.V);
+  // a frame cannot hold more pillars than points, than V, or than cells
+  const int64_t need_cap = std::min<int64_t>(total, static_cast<int64_t>(batch) * std::min(g.V, g.cells));
   if (pillar_capacity < need_cap) return MBEV_ERR_BAD_ARG;
   const VoxWs w = carve(workspace, batch, total);
   if (workspace_bytes < w.bytes) return MBEV_ERR_WORKSPACE;

@@ -94,9 +94,15 @@ class MaskBevEncoder(nn.Module):
         pts = pts.contiguous()
         geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
         vb = F_.voxelize_batch(pts, sizes, geo)
-        feats = self._voxel_encoder.apply_rows(pts, vb.kept_idx, vb.num_points, vb.coors, vb.num_pillars_dev,
-                                               vb.capacity, geo.max_points)
-        canvas = scatter_with_table(feats, vb.cell_table, len(sizes), self._num_voxel_y, self._num_voxel_x)
+        fused = self._voxel_encoder.apply_rows_canvas(pts, vb.kept_idx, vb.num_points, vb.coors, vb.capacity,
+                                                      geo.max_points, vb.cell_table, len(sizes), self._num_voxel_y,
+                                                      self._num_voxel_x)
+        if fused is not None:  # inference: K2 + K3 in one kernel
+            feats, canvas = fused
+        else:
+            feats = self._voxel_encoder.apply_rows(pts, vb.kept_idx, vb.num_points, vb.coors, vb.num_pillars_dev,
+                                                   vb.capacity, geo.max_points)
+            canvas = scatter_with_table(feats, vb.cell_table, len(sizes), self._num_voxel_y, self._num_voxel_x)
         if return_aux:
             return canvas, EncodeAux(vb.coors, vb.num_points, vb.kept_idx, vb.pillar_base, vb.cell_table, feats, sizes)
         return canvas

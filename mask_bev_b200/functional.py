@@ -208,6 +208,46 @@ def pfn_forward_eval(rows, kept_idx, num_points, coors, num_pillars_dev, capacit
     return feats
 
 
+def pfn_scatter_default() -> bool:
+    """Does the library route the fused batch entry through the single K2+K3 kernel (MBEV_FUSED_CANVAS=1)?"""
+    return bool(_lib.load().mbev_pfn_scatter_default())
+
+
+def pfn_scatter_supported(cfg: PfnConfig, T: int, batch: int, ny: int, nx: int) -> bool:
+    """Can K2 and K3 run as the single fused kernel (mbev_pfn_scatter_forward) for this stack / canvas shape?"""
+    lib = _lib.load()
+    L = len(cfg.units)
+    params = _pfn_struct(cfg, [None] * L, None, None)
+    return bool(lib.mbev_pfn_scatter_supported(ctypes.byref(params), T, batch, ny, nx, ctypes.c_void_p(None)))
+
+
+def pfn_scatter_forward_eval(rows, kept_idx, num_points, coors, capacity, T, cfg: PfnConfig, weights, scales, shifts,
+                             cell_table, batch: int, ny: int, nx: int, canvas_out: Optional[torch.Tensor] = None):
+    """Eval-mode PFN forward + scatter in one kernel: returns (feats (capacity, C_out), canvas (B, C_out, ny, nx))."""
+    lib = _lib.load()
+    _need_cuda(rows, "features")
+    dev = rows.device
+    weights = [_f32c(w) for w in weights]
+    scales = [_f32c(s) for s in scales]
+    shifts = [_f32c(s) for s in shifts]
+    params = _pfn_struct(cfg, weights, scales, shifts)
+    nbytes = ctypes.c_size_t()
+    check(lib.mbev_pfn_scatter_workspace_bytes(ctypes.byref(params), T, capacity, batch, ny, nx, ctypes.byref(nbytes)),
+          "pfn_scatter_workspace_bytes")
+    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
+    feats = torch.empty((capacity, cfg.units[-1]), dtype=torch.float32, device=dev)
+    canvas = canvas_out if canvas_out is not None else torch.empty((batch, cfg.units[-1], ny, nx), dtype=torch.float32,
+                                                                   device=dev)
+    if canvas.shape != (batch, cfg.units[-1], ny, nx) or canvas.dtype != torch.float32 or not canvas.is_contiguous():
+        raise _lib.MbevError("canvas_out must be a contiguous float32 (B, C_out, ny, nx) tensor")
+    with torch.cuda.device(dev):
+        check(lib.mbev_pfn_scatter_forward(ptr(rows), cfg.in_channels, ptr(kept_idx), ptr(num_points), ptr(coors),
+                                           capacity, T, ctypes.byref(params), ptr(cell_table), batch, ny, nx,
+                                           ptr(feats), ptr(canvas), ptr(ws), ws.numel(), _stream()),
+              "pfn_scatter_forward")
+    return feats, canvas
+
+
 def pfn_forward_train(rows, kept_idx, num_points, coors, num_pillars_dev, capacity, T, cfg: PfnConfig,
                       weights, gammas, betas):
     """Returns (feats, scale_shift (L,2,MAX_UNITS), batch_stats (L,2,MAX_UNITS) = mean / biased var)."""

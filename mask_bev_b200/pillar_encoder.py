@@ -177,6 +177,25 @@ class PillarFeatureNet(nn.Module):
             return _PfnFunction.forward(_NullCtx(), self, rows, kept_idx, num_points, coors, npil_dev, capacity, T,
                                         *params)
 
+    def apply_rows_canvas(self, rows, kept_idx, num_points, coors, capacity: int, T: int, cell_table, batch: int,
+                          ny: int, nx: int, canvas_out=None, force: bool = False):
+        """Eval-mode, no-grad path: PFN + scatter as ONE kernel (opt-in with MBEV_FUSED_CANVAS=1, or `force`). Returns
+        (feats, canvas), or None when the call needs autograd / train-mode statistics, the stack does not fit the
+        fused kernel, or the fused kernel is not selected."""
+        params = self._param_list()
+        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in params)):
+            return None
+        if not force and not F_.pfn_scatter_default():
+            return None
+        cfg = self._config()
+        if capacity <= 0 or not F_.pfn_scatter_supported(cfg, T, batch, ny, nx):
+            return None
+        with torch.no_grad():
+            scales, shifts, _, _ = self._folded()
+            return F_.pfn_scatter_forward_eval(rows, kept_idx, num_points, coors, capacity, T, cfg,
+                                               [l.linear.weight for l in self.pfn_layers], scales, shifts,
+                                               cell_table, batch, ny, nx, canvas_out=canvas_out)
+
     # -- upstream forward -----------------------------------------------------------------------------
     def forward(self, features: torch.Tensor, num_points: torch.Tensor, coors: torch.Tensor, *args, **kwargs):
         """features (P, T, C) float32 zero-padded, num_points (P,), coors (P, 4) int (b, z, y, x) -> (P, C_out).

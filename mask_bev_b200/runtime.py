@@ -99,6 +99,19 @@ class FusedEncoderRunner:
                                         ctypes.byref(self.params), ptr(self.feats), ptr(self.ws), self.ws.numel(),
                                         self._stream()), "pfn_forward")
 
+    def run_pfn_scatter(self):
+        """K2 + K3 as the single fused kernel (after run_voxelize)."""
+        nb = ctypes.c_size_t()
+        check(self.lib.mbev_pfn_scatter_workspace_bytes(ctypes.byref(self.params), self.geo.max_points, self.cap,
+                                                        self.B, self.ny, self.nx, ctypes.byref(nb)), "ws")
+        if getattr(self, "_ws_fused", None) is None or self._ws_fused.numel() < nb.value:
+            self._ws_fused = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=self.device)
+        check(self.lib.mbev_pfn_scatter_forward(ptr(self.points_dev), self.C, ptr(self.kept_idx), ptr(self.num_points),
+                                                ptr(self.coors), self.cap, self.geo.max_points,
+                                                ctypes.byref(self.params), ptr(self.cell_table), self.B, self.ny,
+                                                self.nx, ptr(self.feats), ptr(self.canvas), ptr(self._ws_fused),
+                                                self._ws_fused.numel(), self._stream()), "pfn_scatter_forward")
+
     def run_fill_empty(self):
         check(self.lib.mbev_scatter_fill_empty(ptr(self.cell_table), self.B, self.c_out, self.ny, self.nx,
                                                ptr(self.canvas), self._stream()), "scatter_fill_empty")
