@@ -41,6 +41,52 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class NvmlSampler:
+    """SM clock / throttle reasons through NVML every ~5 ms during the timed region (a step is ~2 ms, so nvidia-smi's
+    200 ms period sees one or two samples of a default run); falls back to ClockSampler when NVML is unavailable."""
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index: int):
+        self.index, self.ok, self.samples, self.stop_flag = index, False, [], False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.fallback = ClockSampler(index)
+
+    def start(self):
+        if not self.ok:
+            return self.fallback.start()
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        if not self.ok:
+            return self.fallback.stop()
+        self.stop_flag = True
+        self.thread.join(timeout=1)
+        sm = [s[0] for s in self.samples]
+        reasons = sorted(n for n, b in self.BITS.items() if any(s[1] & b for s in self.samples))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": self.max, "reasons": reasons, "samples": len(sm),
+                "power_w_max": max((s[2] for s in self.samples), default=None), "source": "nvml"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -246,7 +292,7 @@ def run_ours(args):
         runner.run_device()
     barrier()
     l0 = _lib.launch_count()
-    sampler = ClockSampler(local)
+    sampler = NvmlSampler(local)
     if rank == 0:
         sampler.start()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -258,22 +304,29 @@ def run_ours(args):
     ms = s.elapsed_time(e)
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    # ---- end to end through the host entry (`e2e`) ----
-    for _ in range(max(1, args.warmup // 2)):
-        runner.run_host(host)
-    barrier()
-    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s2.record()
-    for _ in range(args.steps):
-        runner.run_host(host)
-        counts_host.copy_(runner.pillar_base, non_blocking=True)
-    e2.record()
-    barrier()
-    ms2 = s2.elapsed_time(e2)
-    t = torch.tensor([ms, ms2], dtype=torch.float64, device=dev)
+    # ---- end to end through the host entry (`e2e`): pinned host points in, per-frame pillar counts out, every
+    # step; pipelined = the H2D copy of step i+1 overlaps the kernels of step i (two device point buffers) ----
+    host2 = host.clone().pin_memory()  # alternate two host batches so that no step can reuse a stale device copy
+
+    def e2e_loop(fn):
+        for i in range(max(1, args.warmup // 2)):
+            fn(host2 if i & 1 else host)
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for i in range(args.steps):
+            fn(host2 if i & 1 else host)
+            counts_host.copy_(runner.pillar_base, non_blocking=True)
+        e2.record()
+        barrier()
+        return s2.elapsed_time(e2)
+
+    ms2s = e2e_loop(runner.run_host)
+    ms2 = e2e_loop(runner.run_host_pipelined)
+    t = torch.tensor([ms, ms2, ms2s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms2 = float(t[0]), float(t[1])
+    ms, ms2, ms2s = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -291,6 +344,9 @@ def run_ours(args):
     t_vox = ev_time(runner.run_voxelize, iters, sync)
     t_pfn = ev_time(runner.run_pfn, iters, sync)
     t_sc = ev_time(runner.run_scatter, iters, sync)
+    fused_ok = bool(runner.lib.mbev_pfn_scatter_supported(ctypes.byref(runner.params), T, B, runner.ny, runner.nx,
+                                                          ctypes.c_void_p(runner.canvas.data_ptr())))
+    t_fused = ev_time(runner.run_pfn_scatter, iters, sync) if fused_ok else None
     split_ok = bool(runner.lib.mbev_scatter_split_supported(runner.ny, runner.nx, ctypes.c_void_p(runner.canvas.data_ptr())))
     t_sc2 = ev_time(runner.run_scatter_split, iters, sync) if split_ok else None
     t_fill = ev_time(runner.run_fill_empty, iters, sync) if split_ok else None
@@ -315,8 +371,15 @@ def run_ours(args):
                                                        "note": "two-kernel form of K3 used by the fused path; timed back to "
                                                                "back on one stream here, K3a overlaps K2 in the step",
                                                        "K3a_fill_empty_ms": t_fill, "K3b_scatter_occupied_ms": t_occ}
+    if t_fused is not None:
+        kernels["K2+K3_fused_kernel"] = {"ms": t_fused, "alg_bytes": by_pfn + by_sc - 2 * P * Co * 4,
+                                         "gbs": (by_pfn + by_sc - 2 * P * Co * 4) / t_fused / 1e6,
+                                         "frac_hbm": (by_pfn + by_sc - 2 * P * Co * 4) / t_fused / 1e6 / peak,
+                                         "default": bool(runner.lib.mbev_pfn_scatter_default()),
+                                         "note": "single kernel (PFN in cell order + canvas writer warps); opt-in with "
+                                                 "MBEV_FUSED_CANVAS=1"}
     dom = max(("K1_voxelize", "K2_pfn", "K3_scatter"), key=lambda k: kernels[k]["ms"])
-    roof = {"kernel": "K3_scatter (k_scatter)", "bound": "hbm", "achieved": kernels["K3_scatter"]["gbs"], "peak": peak,
+    roof = {"kernel": "K3_scatter (k_scatter_warp)", "bound": "hbm", "achieved": kernels["K3_scatter"]["gbs"], "peak": peak,
             "unit": "GB/s", "frac": kernels["K3_scatter"]["frac_hbm"], "traffic": None, "peak_source": peak_src,
             "launch_ms": t_sc, "dominant_by_time": dom,
             "share_of_step": t_sc / (t_vox + t_pfn + t_sc)}
@@ -347,8 +410,11 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps2, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
                     "d2h_bytes_per_step": int(counts_host.numel() * 4),
-                    "what": "mbev_encode_batch_host: pinned host points -> H2D -> K1,K2,K3 -> canvas in HBM (where the "
-                            "reference's consumer reads it) + D2H of per-frame pillar counts"},
+                    "serial_value": world * B * args.steps / (ms2s * 1e-3),
+                    "what": "mbev_encode_batch_host_async, every step: pinned host points -> H2D (copy stream, two "
+                            "device buffers: overlaps the previous step's kernels) -> K1,K2,K3 -> canvas in HBM "
+                            "(where the reference's consumer reads it) + D2H of per-frame pillar counts; serial_value "
+                            "= same through mbev_encode_batch_host (copy and kernels on one stream)"},
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "pillars_per_step": P, "kept_points_per_step": nk, "points_per_step": N}
     print(json.dumps(line), flush=True)
@@ -359,8 +425,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti_b16")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -228,6 +228,21 @@ MBEV_API int mbev_encode_batch_host(const float *points_host, float *points_dev,
                            int32_t *pillar_base, int64_t pillar_capacity, float *feats, float *canvas,
                            void *workspace, size_t workspace_bytes, void *stream, void *aux_stream);
 
+/* Pipelined form of the host entry for a stream of batches: the copy of `points_host` runs on `copy_stream`
+ * (first waiting for `ev_consumed`: the previous batch that read this `points_dev` buffer is done with it), then
+ * `stream` waits for `ev_copied` and runs K1..K3, then records `ev_consumed`. With two `points_dev` buffers and two
+ * event pairs used alternately, the H2D copy of batch i+1 overlaps the kernels of batch i; everything else (tables,
+ * canvas, workspace) is ordered by `stream` as usual. Events come from mbev_event_create (cudaEventDisableTiming). */
+MBEV_API int mbev_event_create(void **event);
+MBEV_API int mbev_event_destroy(void *event);
+MBEV_API int mbev_encode_batch_host_async(const float *points_host, float *points_dev,
+                                          const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
+                                          const MbevPfnParams *params, int32_t *cell_table, int32_t *coors,
+                                          int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
+                                          int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
+                                          size_t workspace_bytes, void *stream, void *aux_stream, void *copy_stream,
+                                          void *ev_copied, void *ev_consumed);
+
 /* Launch counter: number of library kernels enqueued by this process since load (for bench.py's
  * `gpu_launches`). Thread-safe. */
 MBEV_API int64_t mbev_launch_count(void);

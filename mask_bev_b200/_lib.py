@@ -74,6 +74,10 @@ SIGNATURES = {
                                   c_size_t, _v, _v]),
     "mbev_encode_batch_host": (c_int, [_v, _v, POINTER(c_int64), c_int, _G, _P, _v, _v, _v, _v, _v, c_int64, _v,
                                        _v, _v, c_size_t, _v, _v]),
+    "mbev_event_create": (c_int, [POINTER(c_void_p)]),
+    "mbev_event_destroy": (c_int, [_v]),
+    "mbev_encode_batch_host_async": (c_int, [_v, _v, POINTER(c_int64), c_int, _G, _P, _v, _v, _v, _v, _v, c_int64, _v,
+                                             _v, _v, c_size_t, _v, _v, _v, _v, _v]),
     "mbev_launch_count": (c_int64, []),
 }
 

@@ -131,3 +131,46 @@ extern "C" int mbev_encode_batch_host(const float *points_host, float *points_de
   return mbev_encode_batch(points_dev, frame_offsets_host, batch, geo, params, cell_table, coors, num_points,
                            kept_idx, pillar_base, pillar_capacity, feats, canvas, workspace, workspace_bytes, stream, aux_stream);
 }
+
+// ---- pipelined host entry: the H2D copy of batch i+1 overlaps the kernels of batch i ---------------------------
+extern "C" int mbev_event_create(void **event) {
+  if (!event) return MBEV_ERR_BAD_ARG;
+  cudaEvent_t e = nullptr;
+  MBEV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *event = e;
+  return MBEV_OK;
+}
+
+extern "C" int mbev_event_destroy(void *event) {
+  if (!event) return MBEV_OK;
+  MBEV_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+  return MBEV_OK;
+}
+
+extern "C" int mbev_encode_batch_host_async(const float *points_host, float *points_dev,
+                                            const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
+                                            const MbevPfnParams *params, int32_t *cell_table, int32_t *coors,
+                                            int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
+                                            int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
+                                            size_t workspace_bytes, void *stream, void *aux_stream, void *copy_stream,
+                                            void *ev_copied, void *ev_consumed) {
+  if (!geo || !frame_offsets_host || batch < 1 || batch > MBEV_MAX_BATCH) return MBEV_ERR_BAD_ARG;
+  if (!copy_stream || !ev_copied || !ev_consumed || copy_stream == stream) return MBEV_ERR_BAD_ARG;
+  cudaStream_t cs = static_cast<cudaStream_t>(copy_stream), ms = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e_copied = static_cast<cudaEvent_t>(ev_copied), e_consumed = static_cast<cudaEvent_t>(ev_consumed);
+  const int64_t total = frame_offsets_host[batch];
+  // the previous batch that read points_dev must be done with it (a never-recorded event counts as complete)
+  MBEV_CUDA(cudaStreamWaitEvent(cs, e_consumed, 0));
+  if (total > 0) {
+    if (!points_host || !points_dev) return MBEV_ERR_BAD_ARG;
+    MBEV_CUDA(cudaMemcpyAsync(points_dev, points_host, sizeof(float) * static_cast<size_t>(total) * geo->num_feats,
+                              cudaMemcpyHostToDevice, cs));
+  }
+  MBEV_CUDA(cudaEventRecord(e_copied, cs));
+  MBEV_CUDA(cudaStreamWaitEvent(ms, e_copied, 0));
+  const int st = mbev_encode_batch(points_dev, frame_offsets_host, batch, geo, params, cell_table, coors, num_points,
+                                   kept_idx, pillar_base, pillar_capacity, feats, canvas, workspace, workspace_bytes,
+                                   stream, aux_stream);
+  MBEV_CUDA(cudaEventRecord(e_consumed, ms));  // also on error, so that the copy stream never waits forever
+  return st;
+}

@@ -178,69 +178,114 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
 // pillars, k_row_bounds prefix-sums the blocks and gives sub-range b (8 per CTA) the blocks whose prefix falls in
 // [R b / G, R (b+1) / G). Static and deterministic (train-mode statistics stay run-to-run identical).
 constexpr int kBlkPillars = 32;
+constexpr int kRbBlocks = 64;  // blocks of 32 pillars per partition CTA (2048 pillars)
 
-__global__ void k_row_blocks(const int *__restrict__ num_points, const int *__restrict__ num_pillars, const int T,
-                             const int nb, int *__restrict__ blocksum) {
-  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= nb) return;
-  const int lane = threadIdx.x & 31, P = *num_pillars;
-  int s = 0;
+// per block of 32 pillars: compact rows; per CTA (64 blocks): their total
+__global__ void __launch_bounds__(256)
+k_row_blocks(const int *__restrict__ num_points, const int *__restrict__ num_pillars, const int T, const int nb,
+             int *__restrict__ blocksum, int *__restrict__ ctot) {
+  __shared__ int s_w[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, P = *num_pillars;
   static_assert(kBlkPillars == 32, "one pillar per lane");
-  {
-    const int p = j * kBlkPillars + lane;
-    if (p < P) {
-      const int n = __ldg(num_points + p);
-      s += n + (n < T ? 1 : 0);
-    }
-  }
+  int wsum = 0;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) blocksum[j] = s;
+  for (int i = 0; i < kRbBlocks / 8; ++i) {
+    const int j = blockIdx.x * kRbBlocks + warp * (kRbBlocks / 8) + i;
+    const int p = j * kBlkPillars + lane;
+    int s = 0;
+    if (j < nb && p < P) {
+      const int n = __ldg(num_points + p);
+      s = n + (n < T ? 1 : 0);
+    }
+    s = __reduce_add_sync(0xffffffffu, s);
+    if (lane == 0 && j < nb) blocksum[j] = s;
+    wsum += s;
+  }
+  if (lane == 0) s_w[warp] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    ctot[blockIdx.x] = t;
+  }
 }
 
-// single CTA of 1024 threads; prefix[] has nb + 1 entries (global scratch)
-__global__ void k_row_bounds(const int *__restrict__ blocksum, const int nb, const int *__restrict__ num_pillars,
-                             const int G, int *__restrict__ prefix, int *__restrict__ bounds) {
-  __shared__ int s_part[1024];
-  const int t = threadIdx.x;
-  const int per = (nb + 1023) / 1024;
-  const int j0 = min(nb, t * per), j1 = min(nb, j0 + per);
-  int s = 0;
-  for (int j = j0; j < j1; ++j) s += blocksum[j];
-  s_part[t] = s;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-    const int v = t >= o ? s_part[t - o] : 0;
-    __syncthreads();
-    s_part[t] += v;
-    __syncthreads();
+// Two-level prefix (every CTA re-reduces the <= ~1 k CTA totals, then scans its own 64 blocks) and the bounds that
+// fall inside this CTA: bound b = first block j whose exclusive row prefix reaches ceil(R b / G). The former
+// single-CTA version of this kernel cost a fixed ~60 us per forward call.
+__global__ void __launch_bounds__(256)
+k_row_bounds(const int *__restrict__ blocksum, const int *__restrict__ ctot, const int nbA, const int nb,
+             const int *__restrict__ num_pillars, const int *__restrict__ num_points, const int T, const int G,
+             int *__restrict__ bounds) {
+  __shared__ int s_red[2][8];
+  __shared__ int s_pre[kRbBlocks + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, bid = blockIdx.x;
+  int base = 0, tot = 0;
+  for (int j = tid; j < nbA; j += 256) {
+    const int v = __ldg(ctot + j);
+    tot += v;
+    if (j < bid) base += v;
   }
-  int run = s_part[t] - s;  // exclusive prefix of this thread's first block
-  for (int j = j0; j < j1; ++j) {
-    prefix[j] = run;
-    run += blocksum[j];
+  base = __reduce_add_sync(0xffffffffu, base);
+  tot = __reduce_add_sync(0xffffffffu, tot);
+  if (lane == 0) {
+    s_red[0][warp] = base;
+    s_red[1][warp] = tot;
   }
-  const int R = s_part[1023];
-  if (t == 0) prefix[nb] = R;
-  __threadfence_block();
-  __syncthreads();
-  const int P = *num_pillars;
-  for (int b = t; b <= G; b += 1024) {
-    int res;
-    if (b == 0) {
-      res = 0;
-    } else if (b == G) {
-      res = P;
-    } else {
-      const long long target = (static_cast<long long>(R) * b + G - 1) / G;
-      int lo = 0, hi = nb;  // first j with prefix[j] >= target
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (prefix[mid] >= target) hi = mid; else lo = mid + 1;
-      }
-      res = static_cast<int>(min(static_cast<long long>(lo) * kBlkPillars, static_cast<long long>(P)));
+  const int j0 = bid * kRbBlocks;
+  const int nloc = min(kRbBlocks, nb - j0);
+  if (warp == 0) {
+    const int a = (2 * lane < nloc) ? __ldg(blocksum + j0 + 2 * lane) : 0;
+    const int c = (2 * lane + 1 < nloc) ? __ldg(blocksum + j0 + 2 * lane + 1) : 0;
+    int inc = a + c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    bounds[b] = res;
+    s_pre[2 * lane] = inc - a - c;
+    s_pre[2 * lane + 1] = inc - c;
+    if (lane == 31) s_pre[kRbBlocks] = inc;
+  }
+  __syncthreads();
+  base = 0;
+  tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    base += s_red[0][w];
+    tot += s_red[1][w];
+  }
+  const long long R = tot;
+  const int P = *num_pillars;
+  const long long lo_pre = base, hi_pre = static_cast<long long>(base) + s_pre[nloc];
+  for (int b = tid; b <= G; b += 256) {
+    if (b == G) {
+      if (bid == nbA - 1) bounds[G] = P;
+      continue;
+    }
+    const long long target = (R * b + G - 1) / G;
+    if (target <= 0) {
+      if (bid == 0) bounds[b] = 0;
+      continue;
+    }
+    if (!(lo_pre < target && target <= hi_pre)) continue;
+    int lo = 1, hi = nloc;  // smallest local j in [1, nloc] with base + s_pre[j] >= target
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (base + s_pre[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    // the crossing lies inside block j0 + lo - 1: walk its pillars so that the bound is pillar-exact (with one
+    // frame the 1184 sub-ranges hold ~24 pillars each, less than a block)
+    long long acc = static_cast<long long>(base) + s_pre[lo - 1];
+    int p = (j0 + lo - 1) * kBlkPillars;
+    const int pe = min(p + kBlkPillars, P);
+    while (p < pe && acc < target) {
+      const int n = __ldg(num_points + p);
+      acc += n + (n < T ? 1 : 0);
+      ++p;
+    }
+    bounds[b] = p;
   }
 }
 
@@ -703,8 +748,9 @@ struct Plan {
   size_t ws_bytes;
   int grid;
   int nb;         // blocks of kBlkPillars pillars covering the capacity
+  int nbA;        // partition CTAs (kRbBlocks blocks each)
   int *blocksum;  // (nb)
-  int *prefix;    // (nb + 1)
+  int *ctot;      // (nbA)
   int *bounds;    // (8 * grid + 1) first pillar of each sub-range (k_pfn_tcw2: one per set and TMEM lane quadrant)
 };
 
@@ -775,7 +821,8 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capaci
   if (nb > (1 << 24)) return MBEV_ERR_UNSUPPORTED;
   out->nb = static_cast<int>(nb);
   out->blocksum = cw.take<int>(out->nb);
-  out->prefix = cw.take<int>(out->nb + 1);
+  out->nbA = (out->nb + kRbBlocks - 1) / kRbBlocks;
+  out->ctot = cw.take<int>(out->nbA);
   out->bounds = cw.take<int>(8 * out->grid + 1);
   out->ws_bytes = cw.off;
   return MBEV_OK;
@@ -790,9 +837,10 @@ inline int launch_prep(const MbevPfnParams *p, Plan &pl, const int32_t *num_poin
   }
   k_prep_weights_tc<<<dim3(16, pl.k.L), 256, 0, stream>>>(pl.prep);
   MBEV_CHECK_LAUNCH();
-  k_row_blocks<<<(pl.nb + 7) / 8, 256, 0, stream>>>(num_points, num_pillars_dev, pl.k.T, pl.nb, pl.blocksum);
+  k_row_blocks<<<pl.nbA, 256, 0, stream>>>(num_points, num_pillars_dev, pl.k.T, pl.nb, pl.blocksum, pl.ctot);
   MBEV_CHECK_LAUNCH();
-  k_row_bounds<<<1, 1024, 0, stream>>>(pl.blocksum, pl.nb, num_pillars_dev, 8 * pl.grid, pl.prefix, pl.bounds);
+  k_row_bounds<<<pl.nbA, 256, 0, stream>>>(pl.blocksum, pl.ctot, pl.nbA, pl.nb, num_pillars_dev, num_points, pl.k.T,
+                                           8 * pl.grid, pl.bounds);
   MBEV_CHECK_LAUNCH();
   return MBEV_OK;
 }

@@ -86,12 +86,16 @@ k_scatter(const float *__restrict__ feats, const int *__restrict__ table, const 
 // on the table load — so this version removes them.
 constexpr int kS2Cells = 512;
 
+// `csplit` > 1 (small batches): a task is (run, channel chunk) so that one frame still fills the machine.
 __global__ void __launch_bounds__(kThreads)
 k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
-               const int tiles_per_frame, const int num_tiles, float *__restrict__ canvas) {
+               const int tiles_per_frame, const int num_tiles, const int csplit, float *__restrict__ canvas) {
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (kThreads / 32);
-  for (int tile = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); tile < num_tiles; tile += nw) {
+  const int cper = (C + csplit - 1) / csplit;
+  for (int task = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); task < num_tiles * csplit; task += nw) {
+    const int tile = task / csplit;
+    const int ch0 = (task - tile * csplit) * cper, ch1 = min(C, ch0 + cper);
     const int b = tile / tiles_per_frame;
     const int g0 = (tile - b * tiles_per_frame) * kS2Cells + 4 * lane;
     int4 pid[4];
@@ -106,7 +110,7 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
     float *out = canvas + (static_cast<size_t>(b) * C) * G + g0;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!__any_sync(0xffffffffu, any)) {  // a run without pillars: pure zero stream
-      for (int ch = 0; ch < C; ++ch) {
+      for (int ch = ch0; ch < ch1; ++ch) {
         float *o = out + static_cast<size_t>(ch) * G;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -114,7 +118,7 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
       }
       continue;
     }
-    for (int ch = 0; ch < C; ++ch) {
+    for (int ch = ch0; ch < ch1; ++ch) {
       float *o = out + static_cast<size_t>(ch) * G;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -274,8 +278,13 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
   if (variant == 1 && (G & 3) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 15) == 0) {
     const int tiles_per_frame = (G + kS2Cells - 1) / kS2Cells;
     const int num_tiles = tiles_per_frame * batch;
-    const int blocks = std::min((num_tiles + kThreads / 32 - 1) / (kThreads / 32), kNumSMs * s2_ctas);
-    k_scatter_warp<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame, num_tiles, canvas);
+    const int want_warps = kNumSMs * s2_ctas * (kThreads / 32);
+    int csplit = 1;  // split the channels of a run over several warps until every resident warp has a task
+    while (csplit < 16 && num_tiles * csplit < want_warps && c_out / (2 * csplit) >= 4) csplit *= 2;
+    const int tasks = num_tiles * csplit;
+    const int blocks = std::min((tasks + kThreads / 32 - 1) / (kThreads / 32), kNumSMs * s2_ctas);
+    k_scatter_warp<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame, num_tiles, csplit,
+                                                    canvas);
   } else if ((G & 3) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 15) == 0 && smem <= 200 * 1024) {
     const int tiles_per_frame = (G + kCells - 1) / kCells;
     const int num_tiles = tiles_per_frame * batch;

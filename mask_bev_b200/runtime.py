@@ -85,6 +85,39 @@ class FusedEncoderRunner:
               "encode_batch_host")
         return self.canvas
 
+    def _pipe_init(self):
+        self._pipe_points = [self.points_dev, torch.empty_like(self.points_dev)]
+        self._pipe_copy = torch.cuda.Stream(device=self.device)
+        self._pipe_events = []
+        for _ in range(4):  # (copied, consumed) x 2 buffers
+            e = ctypes.c_void_p()
+            check(self.lib.mbev_event_create(ctypes.byref(e)), "event_create")
+            self._pipe_events.append(e)
+        self._pipe_i = 0
+
+    def run_host_pipelined(self, points_host: torch.Tensor) -> torch.Tensor:
+        """Like run_host for a stream of batches: two device point buffers used alternately, the H2D copy on its
+        own stream, so that the copy of batch i+1 overlaps K1..K3 of batch i (mbev_encode_batch_host_async)."""
+        if getattr(self, "_pipe_points", None) is None:
+            self._pipe_init()
+        k = self._pipe_i & 1
+        self._pipe_i += 1
+        check(self.lib.mbev_encode_batch_host_async(ptr(points_host), ptr(self._pipe_points[k]), self.off, self.B,
+                                                    ctypes.byref(self.geo), ctypes.byref(self.params),
+                                                    ptr(self.cell_table), ptr(self.coors), ptr(self.num_points),
+                                                    ptr(self.kept_idx), ptr(self.pillar_base), self.cap,
+                                                    ptr(self.feats), ptr(self.canvas), ptr(self.ws), self.ws.numel(),
+                                                    self._stream(), self._aux(),
+                                                    ctypes.c_void_p(self._pipe_copy.cuda_stream),
+                                                    self._pipe_events[2 * k], self._pipe_events[2 * k + 1]),
+              "encode_batch_host_async")
+        return self.canvas
+
+    def close(self):
+        for e in getattr(self, "_pipe_events", []):
+            self.lib.mbev_event_destroy(e)
+        self._pipe_events = []
+
     # stage-by-stage entry points (per-kernel timing in bench.py)
     def run_voxelize(self):
         nb = ctypes.c_size_t()

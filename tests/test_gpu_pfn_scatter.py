@@ -285,3 +285,30 @@ def test_runner_two_streams_matches_single_stream_and_oracle():
     with torch.no_grad():
         ref = orc.forward(frames).numpy()
     assert_close(outs[0].cpu().numpy(), ref, what="runner canvas")
+
+
+def test_runner_pipelined_host_entry_matches_device_entry():
+    """mbev_encode_batch_host_async: alternating host batches through two device buffers and a copy stream give the
+    same canvases as the device-resident entry, in order."""
+    from mask_bev_b200.runtime import FusedEncoderRunner
+    kw = ref_test_kwargs(feat_channels=(128, 128, 128), T=32)
+    enc, _ = encoder_pair(kw, seed=17)
+    enc = enc.to(DEV).eval()
+    fa, fb = _frames(30000, 4, seeds=(41, 42)), _frames(30000, 4, seeds=(43, 44))
+    ha = torch.from_numpy(np.concatenate(fa, 0)).pin_memory()
+    hb = torch.from_numpy(np.concatenate(fb, 0)).pin_memory()
+    r = FusedEncoderRunner(enc, [len(f) for f in fa], torch.device(DEV))
+    refs = [r.run_device(h.to(DEV)).clone() for h in (ha, hb)]
+    torch.cuda.synchronize()
+    for i in range(6):
+        out = r.run_host_pipelined(hb if i & 1 else ha).clone()  # clone is ordered on the compute stream
+        torch.cuda.synchronize()
+        assert torch.equal(out, refs[i & 1]), f"pipelined step {i} differs"
+    outs = []
+    for i in range(6):  # back to back, no host synchronisation in between
+        r.run_host_pipelined(hb if i & 1 else ha)
+        outs.append(r.canvas.clone())
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert torch.equal(o, refs[i & 1]), f"back-to-back pipelined step {i} differs"
+    r.close()
