@@ -89,6 +89,11 @@ __device__ __forceinline__ void st_global_v4_stream(float *p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+// same store without the compiler-level memory clobber: loads of later iterations may be scheduled above it
+// (use only where the stored range cannot alias anything the kernel reads)
+__device__ __forceinline__ void st_global_v4_stream_nc(float *p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
 #endif
 
 }  // namespace mbev

@@ -89,7 +89,8 @@ constexpr int kS2Cells = 512;
 // `csplit` > 1 (small batches): a task is (run, channel chunk) so that one frame still fills the machine.
 __global__ void __launch_bounds__(kThreads)
 k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
-               const int tiles_per_frame, const int num_tiles, const int csplit, float *__restrict__ canvas) {
+               const int tiles_per_frame, const int num_tiles, const int csplit, const int sparse_mode,
+               float *__restrict__ canvas) {
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (kThreads / 32);
   const int cper = (C + csplit - 1) / csplit;
@@ -103,8 +104,8 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int g = g0 + 128 * k;
-      pid[k] = (g < G) ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g))
-                       : make_int4(-1, -1, -1, -1);
+      pid[k] = (g < G && feats) ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g))
+                                : make_int4(-1, -1, -1, -1);
       any |= (pid[k].x & pid[k].y & pid[k].z & pid[k].w) >= 0;
     }
     float *out = canvas + (static_cast<size_t>(b) * C) * G + g0;
@@ -118,18 +119,188 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
       }
       continue;
     }
+    // Sparse runs (the LiDAR case: ~17 pillars in 512 cells, no lane owns more than kSlots of them): per plane the
+    // warp streams 4 unconditional zero stores and each lane then drops its few feature values as 4-byte stores
+    // into its OWN 16 bytes of the line it wrote a few instructions earlier (same thread, same address: ordered;
+    // the line is still in L2, so DRAM sees one full-line write). Feature rows are read 4 channels at a time and
+    // one channel quad ahead. ~8 instructions per plane instead of ~40 for the composing loop below.
+    constexpr int kSlots = 4;
+    int sp[kSlots], so[kSlots], mycnt = 0;  // pillar id / cell offset inside the run of this lane's occupied cells
+#pragma unroll
+    for (int j = 0; j < kSlots; ++j) sp[j] = so[j] = 0;
+    if (sparse_mode == 1 || sparse_mode == 2)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int pk[4] = {pid[k].x, pid[k].y, pid[k].z, pid[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (pk[j] >= 0) {
+#pragma unroll
+          for (int q = 0; q < kSlots; ++q)
+            if (mycnt == q) {
+              sp[q] = pk[j];
+              so[q] = 128 * k + j;
+            }
+          ++mycnt;
+        }
+      }
+    }
+    const int maxcnt = __reduce_max_sync(0xffffffffu, mycnt);
+    if ((sparse_mode == 1 || sparse_mode == 2) && maxcnt <= kSlots && ((ch1 - ch0) & 3) == 0 && (ch0 & 3) == 0) {
+      float4 nxt[kSlots];
+#pragma unroll
+      for (int q = 0; q < kSlots; ++q)
+        nxt[q] = (q < mycnt) ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(sp[q]) * C + ch0)) : z;
+      for (int c4 = ch0; c4 < ch1; c4 += 4) {
+        float4 cur[kSlots];
+#pragma unroll
+        for (int q = 0; q < kSlots; ++q) {
+          cur[q] = nxt[q];
+          if (q < maxcnt && q < mycnt && c4 + 4 < ch1)
+            nxt[q] = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(sp[q]) * C + c4 + 4));
+        }
+        float *o = out + static_cast<size_t>(c4) * G;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (g0 + 128 * k < G) {
+              if (sparse_mode == 2) *reinterpret_cast<float4 *>(o + static_cast<size_t>(i) * G + 128 * k) = z;
+              else st_global_v4_stream(o + static_cast<size_t>(i) * G + 128 * k, z);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kSlots; ++q) {
+          if (q < maxcnt && q < mycnt) {
+            float *d = o + so[q];
+            d[0] = cur[q].x;
+            d[static_cast<size_t>(G)] = cur[q].y;
+            d[2 * static_cast<size_t>(G)] = cur[q].z;
+            d[3 * static_cast<size_t>(G)] = cur[q].w;
+          }
+        }
+      }
+      continue;
+    }
+    if (sparse_mode == 3 && ((ch1 - ch0) & 3) == 0 && (ch0 & 3) == 0) {
+      // compose 4 planes at a time: one 16-byte feature load per occupied cell and channel quad
+      for (int c4 = ch0; c4 < ch1; c4 += 4) {
+        float *o = out + static_cast<size_t>(c4) * G;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float4 v0 = z, v1 = z, v2 = z, v3 = z;
+          if (any) {
+            if (pid[k].x >= 0) v0 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid[k].x) * C + c4));
+            if (pid[k].y >= 0) v1 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid[k].y) * C + c4));
+            if (pid[k].z >= 0) v2 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid[k].z) * C + c4));
+            if (pid[k].w >= 0) v3 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid[k].w) * C + c4));
+          }
+          if (g0 + 128 * k < G) {
+            st_global_v4_stream(o + 128 * k, make_float4(v0.x, v1.x, v2.x, v3.x));
+            st_global_v4_stream(o + static_cast<size_t>(G) + 128 * k, make_float4(v0.y, v1.y, v2.y, v3.y));
+            st_global_v4_stream(o + 2 * static_cast<size_t>(G) + 128 * k, make_float4(v0.z, v1.z, v2.z, v3.z));
+            st_global_v4_stream(o + 3 * static_cast<size_t>(G) + 128 * k, make_float4(v0.w, v1.w, v2.w, v3.w));
+          }
+        }
+      }
+      continue;
+    }
+    // compose every 16-byte store, one plane at a time; the feature values of plane ch+1 are requested before the
+    // stores of plane ch are issued, so the store stream does not stall behind its own loads
+    auto load_plane = [&](int ch, float4 (&v)[4]) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] = z;
+        if (any) {
+          if (pid[k].x >= 0) v[k].x = __ldg(feats + static_cast<size_t>(pid[k].x) * C + ch);
+          if (pid[k].y >= 0) v[k].y = __ldg(feats + static_cast<size_t>(pid[k].y) * C + ch);
+          if (pid[k].z >= 0) v[k].z = __ldg(feats + static_cast<size_t>(pid[k].z) * C + ch);
+          if (pid[k].w >= 0) v[k].w = __ldg(feats + static_cast<size_t>(pid[k].w) * C + ch);
+        }
+      }
+    };
+    float4 nxt[4];
+    load_plane(ch0, nxt);
+    for (int ch = ch0; ch < ch1; ++ch) {
+      float4 cur[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+      if (ch + 1 < ch1) load_plane(ch + 1, nxt);
+      float *o = out + static_cast<size_t>(ch) * G;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (g0 + 128 * k < G) st_global_v4_stream_nc(o + 128 * k, cur[k]);
+    }
+  }
+}
+
+// One-pass scatter with the zeros and the features on separate instruction streams (the default when planes are
+// 32-byte aligned). k_scatter_warp composes every 16-byte store from four predicated loads — ~10 instructions per
+// store, 45 % issue utilisation, and the store stream stalls behind the feature loads; a plain memset of the same
+// canvas runs at 7.4 TB/s, k_scatter_warp at 5.6. Here a warp owns a run of 512 cells as before, but
+//   zero pass   : per plane 4 x 512-byte stores, lanes whose 32-byte sector holds a pillar are predicated off
+//                 (4 loop-invariant predicates) — ~2 instructions per store, no loads in the loop;
+//   sector pass : per occupied sector (8 cells, lanes 2j / 2j+1 of one k) the warp turns into "lane = channel quad":
+//                 the <= 8 pillar rows are read coalesced (512 B each), transposed in registers and written as whole
+//                 sectors, 32 planes per store instruction.
+// Every byte is still written exactly once and every sector whole (its two halves by adjacent instructions).
+__global__ void __launch_bounds__(kThreads, 4)
+k_scatter_holes(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
+                const int tiles_per_frame, const int num_tiles, const int csplit, float *__restrict__ canvas) {
+  const int lane = threadIdx.x & 31;
+  const int nw = gridDim.x * (kThreads / 32);
+  const int cper = C / csplit;  // multiple of 4
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int task = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); task < num_tiles * csplit; task += nw) {
+    const int tile = task / csplit;
+    const int ch0 = (task - tile * csplit) * cper, ch1 = ch0 + cper;
+    const int b = tile / tiles_per_frame;
+    const int g0 = (tile - b * tiles_per_frame) * kS2Cells + 4 * lane;
+    int4 pid[4];
+    bool hole[4];  // my sector (this lane's 16 bytes + its pair lane's) holds a pillar: the sector pass writes it
+    unsigned smask[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = g0 + 128 * k;
+      pid[k] = (g < G) ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g))
+                       : make_int4(-1, -1, -1, -1);
+      const bool occ = (pid[k].x & pid[k].y & pid[k].z & pid[k].w) >= 0;
+      const unsigned m = __ballot_sync(0xffffffffu, occ);
+      const unsigned sect = (m | (m >> 1)) & 0x55555555u;  // bit 2j: sector j (lanes 2j, 2j+1) is occupied
+      smask[k] = sect;
+      hole[k] = ((sect >> (lane & ~1)) & 1u) != 0 || g >= G;
+    }
+    float *out = canvas + (static_cast<size_t>(b) * C) * G + g0;
     for (int ch = ch0; ch < ch1; ++ch) {
       float *o = out + static_cast<size_t>(ch) * G;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float4 v = z;
-        if (any) {
-          if (pid[k].x >= 0) v.x = __ldg(feats + static_cast<size_t>(pid[k].x) * C + ch);
-          if (pid[k].y >= 0) v.y = __ldg(feats + static_cast<size_t>(pid[k].y) * C + ch);
-          if (pid[k].z >= 0) v.z = __ldg(feats + static_cast<size_t>(pid[k].z) * C + ch);
-          if (pid[k].w >= 0) v.w = __ldg(feats + static_cast<size_t>(pid[k].w) * C + ch);
+      for (int k = 0; k < 4; ++k)
+        if (!hole[k]) st_global_v4_stream(o + 128 * k, z);
+    }
+    // sector pass: lane = channel quad 4*lane .. 4*lane+3 (when inside this task's channel chunk)
+    const int cq = 4 * lane;
+    const bool cact = cq >= ch0 && cq < ch1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      for (unsigned m = smask[k]; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;  // even lane; the sector is cells 4*src .. 4*src+7 of this k
+        float *so = canvas + (static_cast<size_t>(b) * C + cq) * G + (g0 - 4 * lane) + 128 * k + 4 * src;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int p0 = __shfl_sync(0xffffffffu, pid[k].x, src + half), p1 = __shfl_sync(0xffffffffu, pid[k].y, src + half);
+          const int p2 = __shfl_sync(0xffffffffu, pid[k].z, src + half), p3 = __shfl_sync(0xffffffffu, pid[k].w, src + half);
+          if (!cact) continue;
+          float4 v0 = z, v1 = z, v2 = z, v3 = z;
+          if (p0 >= 0) v0 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(p0) * C + cq));
+          if (p1 >= 0) v1 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(p1) * C + cq));
+          if (p2 >= 0) v2 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(p2) * C + cq));
+          if (p3 >= 0) v3 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(p3) * C + cq));
+          float *ho = so + 4 * half;
+          st_global_v4_stream(ho, make_float4(v0.x, v1.x, v2.x, v3.x));
+          st_global_v4_stream(ho + static_cast<size_t>(G), make_float4(v0.y, v1.y, v2.y, v3.y));
+          st_global_v4_stream(ho + 2 * static_cast<size_t>(G), make_float4(v0.z, v1.z, v2.z, v3.z));
+          st_global_v4_stream(ho + 3 * static_cast<size_t>(G), make_float4(v0.w, v1.w, v2.w, v3.w));
         }
-        if (g0 + 128 * k < G) st_global_v4_stream(o + 128 * k, v);
       }
     }
   }
@@ -273,18 +444,30 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int G = static_cast<int>(G64);
   const size_t smem = sizeof(float) * kCells * (static_cast<size_t>(c_out) + 1);
-  static const int variant = getenv("MBEV_SCATTER") ? atoi(getenv("MBEV_SCATTER")) : 1;  // 0: tile kernel with barriers
+  // 2: zeros / features on separate instruction streams; 1: composing warp-per-run; 0: tile kernel with barriers
+  // (2 measured 2.3 ms against 0.97 ms for 1 on kitti_b16: single 32-byte sectors written apart from their line cost
+  // DRAM read-modify-writes; kept selectable as a documented negative result.) 3: developer probe, zeros only.
+  static const int variant = getenv("MBEV_SCATTER") ? atoi(getenv("MBEV_SCATTER")) : 1;
+  // developer knob: 0 = compose every store (default), 1 = zero stream (.cs) + feature drops, 2 = same with plain stores
+  static const int sparse_mode = getenv("MBEV_SCATTER_SPARSE") ? atoi(getenv("MBEV_SCATTER_SPARSE")) : 0;
   static const int s2_ctas = getenv("MBEV_SCATTER_CTAS") ? atoi(getenv("MBEV_SCATTER_CTAS")) : 6;
-  if (variant == 1 && (G & 3) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 15) == 0) {
+  if (variant >= 1 && (G & 3) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 15) == 0) {
     const int tiles_per_frame = (G + kS2Cells - 1) / kS2Cells;
     const int num_tiles = tiles_per_frame * batch;
     const int want_warps = kNumSMs * s2_ctas * (kThreads / 32);
     int csplit = 1;  // split the channels of a run over several warps until every resident warp has a task
-    while (csplit < 16 && num_tiles * csplit < want_warps && c_out / (2 * csplit) >= 4) csplit *= 2;
+    while (csplit < 16 && num_tiles * csplit < want_warps && c_out % (8 * csplit) == 0) csplit *= 2;
     const int tasks = num_tiles * csplit;
     const int blocks = std::min((tasks + kThreads / 32 - 1) / (kThreads / 32), kNumSMs * s2_ctas);
-    k_scatter_warp<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame, num_tiles, csplit,
-                                                    canvas);
+    // the hole kernel needs whole 32-byte sectors per lane pair (planes 32-byte aligned) and one channel quad per lane
+    const bool holes = variant == 2 && (G & 7) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 31) == 0 &&
+                       (c_out & 3) == 0 && c_out <= 128;
+    if (holes)
+      k_scatter_holes<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame, num_tiles, csplit,
+                                                       canvas);
+    else
+      k_scatter_warp<<<blocks, kThreads, 0, stream>>>(variant == 3 ? nullptr : feats, cell_table, c_out, G,
+                                                      tiles_per_frame, num_tiles, csplit, sparse_mode, canvas);
   } else if ((G & 3) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 15) == 0 && smem <= 200 * 1024) {
     const int tiles_per_frame = (G + kCells - 1) / kCells;
     const int num_tiles = tiles_per_frame * batch;
