@@ -172,6 +172,14 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
 
+// Same split on the integer / FMA pipes only (cvt.rna.tf32 issues at a fraction of the ALU rate and sits on the
+// epilogue's critical chain): hi = round-half-up to 10 mantissa bits by integer add + mask, lo = x - hi (exact);
+// the tensor core ignores the low 13 mantissa bits of lo itself, which costs <= 2^-21 |x| instead of 2^-22 |x|.
+__device__ __forceinline__ void split_tf32_alu(float x, uint32_t &hi, uint32_t &lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(__fsub_rn(x, __uint_as_float(hi)));
+}
+
 // ---- row-balanced static partition ------------------------------------------------------------------------
 // Pillars are numbered in order of first appearance, so the heavy pillars of a frame come first: an equal-count
 // split leaves the CTAs 3x apart in rows. k_row_blocks sums the compact rows (n + [n < T]) of blocks of 32

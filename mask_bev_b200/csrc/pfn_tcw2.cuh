@@ -184,10 +184,10 @@ __device__ __forceinline__ void build_x0(const Kargs &k, const Window &w, const 
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
     const float4 v = *reinterpret_cast<const float4 *>(xd + 4 * j4);
-    split_tf32(v.x, hi[4 * j4 + 0], lo[4 * j4 + 0]);
-    split_tf32(v.y, hi[4 * j4 + 1], lo[4 * j4 + 1]);
-    split_tf32(v.z, hi[4 * j4 + 2], lo[4 * j4 + 2]);
-    split_tf32(v.w, hi[4 * j4 + 3], lo[4 * j4 + 3]);
+    split_tf32_alu(v.x, hi[4 * j4 + 0], lo[4 * j4 + 0]);
+    split_tf32_alu(v.y, hi[4 * j4 + 1], lo[4 * j4 + 1]);
+    split_tf32_alu(v.z, hi[4 * j4 + 2], lo[4 * j4 + 2]);
+    split_tf32_alu(v.w, hi[4 * j4 + 3], lo[4 * j4 + 3]);
   }
   tmem_st16(t_hi, hi);
   tmem_st16(t_lo, lo);
@@ -213,7 +213,7 @@ __device__ __forceinline__ void load_bn_relu(uint32_t taddr, const float *sc, co
 __device__ __forceinline__ void split_store16(uint32_t t_hi, uint32_t t_lo, const float (&a)[16]) {
   uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) split_tf32(a[j], hi[j], lo[j]);
+  for (int j = 0; j < 16; ++j) split_tf32_alu(a[j], hi[j], lo[j]);
   tmem_st16(t_hi, hi);
   tmem_st16(t_lo, lo);
 }
