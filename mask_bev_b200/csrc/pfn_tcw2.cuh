@@ -219,6 +219,8 @@ __device__ __forceinline__ void split_store16(uint32_t t_hi, uint32_t t_lo, cons
 }
 
 // per-pillar max over the lanes of the window: segmented inclusive max-scan, then read the pillar's last lane
+// (kBroadcast = false: only the pillar's LAST lane holds the result — enough for the last layer's store)
+template <bool kBroadcast = true>
 __device__ __forceinline__ void seg_max16(const Window &w, int lane, float (&a)[16]) {
   for (int d = 1; d < w.maxlen; d <<= 1) {
     const bool take = lane - d >= w.s0;
@@ -228,8 +230,10 @@ __device__ __forceinline__ void seg_max16(const Window &w, int lane, float (&a)[
       a[j] = take ? fmaxf(a[j], o) : a[j];
     }
   }
+  if (kBroadcast) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) a[j] = __shfl_sync(0xffffffffu, a[j], w.s1);
+    for (int j = 0; j < 16; ++j) a[j] = __shfl_sync(0xffffffffu, a[j], w.s1);
+  }
 }
 
 // ---- canvas writers ----------------------------------------------------------------------------------------------
@@ -510,8 +514,8 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
             const int col0 = h * Uh + 16 * b;
             float a[16];
             load_bn_relu(t_d + static_cast<uint32_t>(col0), sc + 16 * b, sh + 16 * b, a);
-            seg_max16(w, lane, a);
-            if (w.inwin && w.t == 0) {  // first lane of each pillar writes its 16 columns (64 contiguous bytes)
+            seg_max16<false>(w, lane, a);
+            if (w.inwin && lane == w.s1) {  // the last lane of each pillar holds its max: 16 columns, 64 contiguous bytes
               float4 *out = reinterpret_cast<float4 *>(feats + static_cast<size_t>(w.pil) * U + col0);
               out[0] = make_float4(a[0], a[1], a[2], a[3]);
               out[1] = make_float4(a[4], a[5], a[6], a[7]);
