@@ -111,6 +111,7 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
     float *out = canvas + (static_cast<size_t>(b) * C) * G + g0;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!__any_sync(0xffffffffu, any)) {  // a run without pillars: pure zero stream
+      if (sparse_mode == 4) continue;  // (probe) occupied lines only
       for (int ch = ch0; ch < ch1; ++ch) {
         float *o = out + static_cast<size_t>(ch) * G;
 #pragma unroll
@@ -219,6 +220,13 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
         }
       }
     };
+    bool wr[4];  // (probe, sparse_mode 4 / 5) write only the 128-byte lines with / without a pillar
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned m = __ballot_sync(0xffffffffu, (pid[k].x & pid[k].y & pid[k].z & pid[k].w) >= 0);
+      const bool lineocc = (m & (0xffu << (lane & ~7))) != 0;
+      wr[k] = (g0 + 128 * k < G) && (sparse_mode == 4 ? lineocc : sparse_mode == 5 ? !lineocc : true);
+    }
     float4 nxt[4];
     load_plane(ch0, nxt);
     for (int ch = ch0; ch < ch1; ++ch) {
@@ -229,7 +237,7 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
       float *o = out + static_cast<size_t>(ch) * G;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (g0 + 128 * k < G) st_global_v4_stream_nc(o + 128 * k, cur[k]);
+        if (wr[k]) st_global_v4_stream_nc(o + 128 * k, cur[k]);
     }
   }
 }
