@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 4
+#define MBEV_ABI_VERSION 5
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -181,6 +181,25 @@ MBEV_API int mbev_scatter_occupied(const float *feats, const int32_t *coors, con
                           float *canvas, void *stream);
 MBEV_API int mbev_scatter_backward(const float *dcanvas, const int32_t *cell_table, int batch, int c_out, int ny,
                           int nx, float *dfeats, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3+LN  scatter fused with the LayerNorm that follows it (forward, inference) — SURVEY.md §8 row f1.
+ * Replaces: `self._layer_norm(self.middle_encode(...))` with nn.LayerNorm([C, ny, nx], eps=1e-3)
+ *           (mask_bev_encoders.py:75, 91-92): per frame, normalisation over all C*ny*nx elements, element-wise affine.
+ * The statistics come from the pillar features alone (all other cells are exact zeros; fp64, fixed order), then one
+ * streaming pass writes ((x - mean_b) * rstd_b) * weight + bias: weight and bias are read once per BATCH, the canvas
+ * is written once.
+ *   pillar_base (batch+1) device int32 from mbev_voxelize (pillars of frame b are [pillar_base[b], pillar_base[b+1]))
+ *   ln_weight, ln_bias (C, ny, nx) float32;  out (batch, C, ny, nx) float32;  stats_out (batch, 2) = mean, rstd
+ * Needs ny*nx % 4 == 0 and 16-byte aligned out / weight / bias (probe: mbev_scatter_layernorm_supported).
+ * ---------------------------------------------------------------------------------------------- */
+MBEV_API int mbev_scatter_layernorm_supported(int batch, int c_out, int ny, int nx, const float *out,
+                                              const float *ln_weight, const float *ln_bias);
+MBEV_API int mbev_scatter_layernorm_workspace_bytes(int batch, size_t *bytes);
+MBEV_API int mbev_scatter_layernorm_forward(const float *feats, const int32_t *cell_table, const int32_t *pillar_base,
+                                            int batch, int c_out, int ny, int nx, const float *ln_weight,
+                                            const float *ln_bias, float eps, float *out, float *stats_out,
+                                            void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2+K3 in one kernel (eval mode): PillarFeatureNet.forward and PointPillarsScatter.forward_batch

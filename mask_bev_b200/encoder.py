@@ -109,10 +109,33 @@ class MaskBevEncoder(nn.Module):
 
     def forward(self, point_clouds):
         """list of (N_i, C) float32 CUDA tensors -> (B, C_out, ny, nx)   (mask_bev_encoders.py:77-93)"""
+        if self.apply_layer_norm and not torch.is_grad_enabled():
+            fused = self._forward_fused_layer_norm(point_clouds)
+            if fused is not None:
+                return fused
         pseudo_img = self.encode_batch(point_clouds)
         if self.apply_layer_norm:
             pseudo_img = self._layer_norm(pseudo_img)
         return pseudo_img
+
+    def _forward_fused_layer_norm(self, point_clouds):
+        """Inference: K1 -> K2 -> (K3 + LayerNorm) — the canvas is written once, already normalised."""
+        ln = self._layer_norm
+        if len(point_clouds) == 0 or not ln.elementwise_affine or ln.weight is None or ln.bias is None:
+            return None
+        sizes = [int(pc.shape[0]) for pc in point_clouds]
+        pts = (point_clouds[0] if len(point_clouds) == 1 else torch.cat(point_clouds, dim=0)).contiguous()
+        geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
+        vb = F_.voxelize_batch(pts, sizes, geo)
+        with torch.no_grad():
+            feats = self._voxel_encoder.apply_rows(pts, vb.kept_idx, vb.num_points, vb.coors, vb.num_pillars_dev,
+                                                   vb.capacity, geo.max_points)
+            res = F_.scatter_layernorm_forward(feats, vb.cell_table, vb.pillar_base, len(sizes), self._num_voxel_y,
+                                               self._num_voxel_x, ln.weight, ln.bias, ln.eps)
+        if res is None:  # shape / alignment outside the fused kernel: K3, then torch's LayerNorm
+            canvas = scatter_with_table(feats, vb.cell_table, len(sizes), self._num_voxel_y, self._num_voxel_x)
+            return ln(canvas)
+        return res[0]
 
     # -- module-level methods with the reference's semantics ---------------------------------------------
     def voxelize(self, point_clouds):

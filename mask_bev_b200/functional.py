@@ -328,6 +328,33 @@ def scatter_forward(feats: torch.Tensor, cell_table: torch.Tensor, batch: int, n
     return canvas
 
 
+def scatter_layernorm_forward(feats: torch.Tensor, cell_table: torch.Tensor, pillar_base: torch.Tensor, batch: int,
+                              ny: int, nx: int, weight: torch.Tensor, bias: torch.Tensor, eps: float,
+                              out: Optional[torch.Tensor] = None):
+    """K3 + LayerNorm([C, ny, nx]) in one pass (forward only). Returns (out (B, C, ny, nx), stats (B, 2) = mean,
+    rstd), or None when the shapes / alignment do not fit the fused kernel (the caller then runs K3 + torch LN)."""
+    lib = _lib.load()
+    _need_cuda(feats, "voxel_features")
+    dev = feats.device
+    C = feats.shape[1]
+    feats = _f32c(feats)
+    weight, bias = _f32c(weight), _f32c(bias)
+    if tuple(weight.shape) != (C, ny, nx) or tuple(bias.shape) != (C, ny, nx):
+        raise _lib.MbevError(f"LayerNorm weight/bias must be ({C}, {ny}, {nx})")
+    out = out if out is not None else torch.empty((batch, C, ny, nx), dtype=torch.float32, device=dev)
+    if not lib.mbev_scatter_layernorm_supported(batch, C, ny, nx, ptr(out), ptr(weight), ptr(bias)):
+        return None
+    stats = torch.empty((batch, 2), dtype=torch.float32, device=dev)
+    nbytes = ctypes.c_size_t()
+    check(lib.mbev_scatter_layernorm_workspace_bytes(batch, ctypes.byref(nbytes)), "scatter_layernorm_workspace_bytes")
+    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.mbev_scatter_layernorm_forward(ptr(feats), ptr(cell_table), ptr(pillar_base), batch, C, ny, nx,
+                                                 ptr(weight), ptr(bias), float(eps), ptr(out), ptr(stats), ptr(ws),
+                                                 ws.numel(), _stream()), "scatter_layernorm_forward")
+    return out, stats
+
+
 def scatter_backward(dcanvas: torch.Tensor, cell_table: torch.Tensor, num_rows: int) -> torch.Tensor:
     lib = _lib.load()
     B, C, ny, nx = dcanvas.shape
