@@ -381,6 +381,27 @@ def run_ours(args):
                                          "default": bool(runner.lib.mbev_pfn_scatter_default()),
                                          "note": "single kernel (PFN in cell order + canvas writer warps); opt-in with "
                                                  "MBEV_FUSED_CANVAS=1"}
+    # SURVEY §8 f1 ("next" row, not part of the headline metric): the LayerNorm that follows the scatter in
+    # MaskBevEncoder.forward, fused into the scatter, next to torch's own LayerNorm on the finished canvas
+    layernorm = None
+    if not args.no_layernorm:
+        from mask_bev_b200 import functional as F_
+        ln = enc._layer_norm
+        out_ln = torch.empty_like(runner.canvas)
+
+        def fused_ln():
+            return F_.scatter_layernorm_forward(runner.feats, runner.cell_table, runner.pillar_base, B, runner.ny,
+                                                runner.nx, ln.weight, ln.bias, ln.eps, out=out_ln)
+        if fused_ln() is not None:
+            t_ln = ev_time(fused_ln, iters, sync)
+            with torch.no_grad():
+                t_torch = ev_time(lambda: ln(runner.canvas), 2, sync)
+            by_ln = B * G * Co * 4 + 2 * G * Co * 4 + P * Co * 4 + B * G * 4
+            layernorm = {"K3+LN_fused_ms": t_ln, "alg_bytes": by_ln, "gbs": by_ln / t_ln / 1e6,
+                         "frac_hbm": by_ln / t_ln / 1e6 / peak, "K3_then_torch_layernorm_ms": t_sc + t_torch,
+                         "torch_layernorm_ms": t_torch,
+                         "note": "mbev_scatter_layernorm_forward vs K3 followed by nn.LayerNorm([C,ny,nx]) (mask_bev_encoders.py:75,92)"}
+        del out_ln
     dom = max(("K1_voxelize", "K2_pfn", "K3_scatter"), key=lambda k: kernels[k]["ms"])
     roof = {"kernel": "K3_scatter (k_scatter_warp)", "bound": "hbm", "achieved": kernels["K3_scatter"]["gbs"], "peak": peak,
             "unit": "GB/s", "frac": kernels["K3_scatter"]["frac_hbm"], "traffic": None, "peak_source": peak_src,
@@ -418,7 +439,7 @@ def run_ours(args):
                             "device buffers: overlaps the previous step's kernels) -> K1,K2,K3 -> canvas in HBM "
                             "(where the reference's consumer reads it) + D2H of per-frame pillar counts; serial_value "
                             "= same through mbev_encode_batch_host (copy and kernels on one stream)"},
-            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": roof, "kernels": kernels, "layernorm_f1": layernorm, "cpu_baseline": cpu,
             "pillars_per_step": P, "kept_points_per_step": nk, "points_per_step": N}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -433,6 +454,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti_b16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-layernorm", action="store_true", help="skip the K3+LayerNorm (SURVEY f1) timing")
     ap.add_argument("--overlap", action="store_true", help="two streams: K3a zero-fill under K2, then K3b (default: one stream, one-pass K3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
