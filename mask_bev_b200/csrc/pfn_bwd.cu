@@ -245,23 +245,31 @@ k_build_x(const float *__restrict__ Y, const int U, const float *__restrict__ sc
 // ---------------------------------------------------------------------------------------------------
 // backward pieces
 // ---------------------------------------------------------------------------------------------------
-// Block = U threads (one per unit), loops over a contiguous range of pillars. For each (pillar, unit):
+// Block = (U, NL) threads: threadIdx.x = unit, threadIdx.y = pillar lane. The block owns a contiguous range of
+// pillars; lane y walks pillars pa + y, pa + y + NL, ... (NL independent load chains per unit instead of one — the
+// single-lane form of this kernel was latency-bound at 7.6 ms per layer on kitti_b16). For each (pillar, unit):
 //   dm = dfeats (last layer) or sum over the pillar's rows of dXnext[r][U + u]   (gradient of the broadcast max)
 //   route dm to the FIRST row attaining the max (torch.max semantics; real rows precede the virtual row),
 //   add the per-row gradient dXnext[r][u], apply the ReLU mask -> dz; accumulate S1 = sum dz, S2 = sum dz*xhat.
-__global__ void
+// The lanes' sums are combined in lane order through shared memory: fixed order, run-to-run identical.
+constexpr int kDzThreads = 1024;
+
+__global__ void __launch_bounds__(kDzThreads)
 k_dz(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ shift,
      const float *__restrict__ mean, const float *__restrict__ var, const float eps, const float *__restrict__ Mx,
      const float *__restrict__ dfeats, const float *__restrict__ dXnext, const int ldx,
-     const int *__restrict__ row_off, const int *__restrict__ num_pillars, const int pillars_per_block,
-     float *__restrict__ DZ, double *__restrict__ partials) {
-  const int u = threadIdx.x;
+     const int *__restrict__ row_off, const int *__restrict__ num_pillars, float *__restrict__ DZ,
+     double *__restrict__ partials) {
+  extern __shared__ double s_sum[];  // [NL][2][U]
+  const int u = threadIdx.x, yl = threadIdx.y, NL = blockDim.y;
   const int P = *num_pillars;
-  const int pa = blockIdx.x * pillars_per_block, pb = min(P, pa + pillars_per_block);
+  // the split follows the ACTUAL pillar count (device side), not the capacity: every block has work
+  const int pillars_per_block = (P + gridDim.x - 1) / gridDim.x;
+  const int pa = min(P, blockIdx.x * pillars_per_block), pb = min(P, pa + pillars_per_block);
   const float sc = scale[u], sh = shift[u];
   const float mu = mean[u], rstd = rsqrtf(var[u] + eps);
   double s1 = 0.0, s2 = 0.0;
-  for (int p = pa; p < pb; ++p) {
+  for (int p = pa + yl; p < pb; p += NL) {
     const int r0 = row_off[p], r1 = row_off[p + 1];
     float dm;
     if (dXnext == nullptr) {
@@ -287,8 +295,18 @@ k_dz(const float *__restrict__ Y, const int U, const float *__restrict__ scale, 
       s2 += static_cast<double>(dz) * static_cast<double>((y - mu) * rstd);
     }
   }
-  partials[(static_cast<size_t>(blockIdx.x) * 2 + 0) * U + u] = s1;
-  partials[(static_cast<size_t>(blockIdx.x) * 2 + 1) * U + u] = s2;
+  s_sum[(yl * 2 + 0) * U + u] = s1;
+  s_sum[(yl * 2 + 1) * U + u] = s2;
+  __syncthreads();
+  if (yl == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int j = 0; j < NL; ++j) {
+      t1 += s_sum[(j * 2 + 0) * U + u];
+      t2 += s_sum[(j * 2 + 1) * U + u];
+    }
+    partials[(static_cast<size_t>(blockIdx.x) * 2 + 0) * U + u] = t1;
+    partials[(static_cast<size_t>(blockIdx.x) * 2 + 1) * U + u] = t2;
+  }
 }
 
 __global__ void k_bn_finalize(const double *__restrict__ partials, const int nblocks, const int U,
@@ -330,7 +348,7 @@ struct BwdWs {
 };
 
 constexpr int kDzBlocks = 1024;
-constexpr int kSplitK = 64;
+constexpr int kSplitK = 296;  // dW split-K: 2 x 2 output tiles x 296 row slices = 8 CTAs per SM
 
 BwdWs carve_bwd(void *ws, const MbevPfnParams *p, int64_t cap, int64_t rows_cap) {
   Carver c(ws);
@@ -460,10 +478,10 @@ extern "C" int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_i
   // ---- backward, top layer first ------------------------------------------------------------------------
   for (int l = L - 1; l >= 0; --l) {
     const int U = params->units[l], K = params->in_dim[l];
-    const int ppb = static_cast<int>((pillar_capacity + kDzBlocks - 1) / kDzBlocks);
-    k_dz<<<kDzBlocks, U, 0, stream>>>(w.Y[l], U, SC(l), SH(l), MEAN(l), VAR(l), eps, w.Mx[l], dfeats,
-                                      (l == L - 1) ? nullptr : w.DX, (l == L - 1) ? 0 : params->in_dim[l + 1],
-                                      w.row_off, num_pillars_dev, ppb, w.DZ, w.partials);
+    const int nl = std::max(1, kDzThreads / U);
+    k_dz<<<kDzBlocks, dim3(U, nl), sizeof(double) * 2 * U * nl, stream>>>(
+        w.Y[l], U, SC(l), SH(l), MEAN(l), VAR(l), eps, w.Mx[l], dfeats, (l == L - 1) ? nullptr : w.DX,
+        (l == L - 1) ? 0 : params->in_dim[l + 1], w.row_off, num_pillars_dev, w.DZ, w.partials);
     MBEV_CHECK_LAUNCH();
     k_bn_finalize<<<(U + 127) / 128, 128, 0, stream>>>(w.partials, kDzBlocks, U, num_pillars_dev, T, train, dgamma[l],
                                                        dbeta[l], w.c12);
