@@ -381,6 +381,17 @@ def run_ours(args):
                                          "default": bool(runner.lib.mbev_pfn_scatter_default()),
                                          "note": "single kernel (PFN in cell order + canvas writer warps); opt-in with "
                                                  "MBEV_FUSED_CANVAS=1"}
+    # BASELINE config 4 flavour (not the headline, which is fp32): same path with a bfloat16 canvas
+    bf16 = None
+    if (G & 3) == 0:
+        t_sc16 = ev_time(runner.run_scatter_bf16, iters, sync)
+        t_step16 = ev_time(runner.run_device_bf16, iters, sync)
+        by_sc16 = P * Co * 4 + P * 16 + B * G * Co * 2
+        bf16 = {"K3_scatter_bf16_ms": t_sc16, "alg_bytes": by_sc16, "gbs": by_sc16 / t_sc16 / 1e6,
+                "frac_hbm": by_sc16 / t_sc16 / 1e6 / peak, "ms_per_step": t_step16,
+                "frames_per_s": B / (t_step16 * 1e-3),
+                "note": "fp32 PFN (3xTF32), canvas rounded to bf16 on the way out (mbev_scatter_forward_bf16); one GPU"}
+        runner.canvas_bf16 = None
     # SURVEY §8 f1 ("next" row, not part of the headline metric): the LayerNorm that follows the scatter in
     # MaskBevEncoder.forward, fused into the scatter, next to torch's own LayerNorm on the finished canvas
     layernorm = None
@@ -439,7 +450,7 @@ def run_ours(args):
                             "device buffers: overlaps the previous step's kernels) -> K1,K2,K3 -> canvas in HBM "
                             "(where the reference's consumer reads it) + D2H of per-frame pillar counts; serial_value "
                             "= same through mbev_encode_batch_host (copy and kernels on one stream)"},
-            "roofline": roof, "kernels": kernels, "layernorm_f1": layernorm, "cpu_baseline": cpu,
+            "roofline": roof, "kernels": kernels, "layernorm_f1": layernorm, "bf16_canvas": bf16, "cpu_baseline": cpu,
             "pillars_per_step": P, "kept_points_per_step": nk, "points_per_step": N}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -169,6 +169,11 @@ MBEV_API int mbev_build_cell_table(const int32_t *coors, const int32_t *num_pill
                           int batch, int ny, int nx, int32_t *cell_table, void *stream);
 MBEV_API int mbev_scatter_forward(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny, int nx,
                          float *canvas, void *stream);
+/* Same scatter with a bfloat16 canvas (BASELINE.json config 4; north star tolerance 1e-2 in bf16): every value is
+ * the fp32 feature rounded to nearest-even bf16, so the result equals the fp32 canvas cast to bf16 bit for bit.
+ * canvas_bf16: (batch, C_out, ny, nx) bfloat16; needs ny*nx % 4 == 0 and an 8-byte aligned canvas. Forward only. */
+MBEV_API int mbev_scatter_forward_bf16(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny,
+                                       int nx, void *canvas_bf16, void *stream);
 /* Two-kernel form of the same scatter (G = ny*nx a multiple of 8 and a 32-byte aligned canvas; probe with
  * mbev_scatter_split_supported): fill_empty zeroes every 32-byte sector (8 cells of one channel plane) that holds
  * no pillar and needs only the cell table, so it can run on a second stream while K2 computes; occupied writes

@@ -60,6 +60,7 @@ SIGNATURES = {
                                   POINTER(_PTRS), POINTER(_PTRS), POINTER(_PTRS), _v, c_size_t, _v]),
     "mbev_build_cell_table": (c_int, [_v, _v, c_int64, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_forward": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, _v]),
+    "mbev_scatter_forward_bf16": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_split_supported": (c_int, [c_int, c_int, _v]),
     "mbev_scatter_fill_empty": (c_int, [_v, c_int, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_occupied": (c_int, [_v, _v, _v, c_int64, _v, c_int, c_int, c_int, c_int, _v, _v]),

@@ -242,6 +242,76 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
   }
 }
 
+// bf16 canvas (BASELINE config 4 / north star "1e-2 in bf16"): the same one-pass walk, every value rounded to
+// nearest-even bf16 on the way out, 8 bytes per lane and store — the canvas bytes, i.e. K3's roofline, halve.
+__device__ __forceinline__ void st_global_v2_stream_nc(void *p, uint32_t a, uint32_t b) {
+  asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_scatter_warp_bf16(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
+                    const int tiles_per_frame, const int num_tiles, const int csplit, uint16_t *__restrict__ canvas) {
+  const int lane = threadIdx.x & 31;
+  const int nw = gridDim.x * (kThreads / 32);
+  const int cper = (C + csplit - 1) / csplit;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int task = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); task < num_tiles * csplit; task += nw) {
+    const int tile = task / csplit;
+    const int ch0 = (task - tile * csplit) * cper, ch1 = min(C, ch0 + cper);
+    const int b = tile / tiles_per_frame;
+    const int g0 = (tile - b * tiles_per_frame) * kS2Cells + 4 * lane;
+    int4 pid[4];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = g0 + 128 * k;
+      pid[k] = (g < G) ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g))
+                       : make_int4(-1, -1, -1, -1);
+      any |= (pid[k].x & pid[k].y & pid[k].z & pid[k].w) >= 0;
+    }
+    uint16_t *out = canvas + (static_cast<size_t>(b) * C) * G + g0;
+    if (!__any_sync(0xffffffffu, any)) {
+      for (int ch = ch0; ch < ch1; ++ch) {
+        uint16_t *o = out + static_cast<size_t>(ch) * G;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (g0 + 128 * k < G) st_global_v2_stream_nc(o + 128 * k, 0u, 0u);
+      }
+      continue;
+    }
+    auto load_plane = [&](int ch, float4 (&v)[4]) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] = z;
+        if (any) {
+          if (pid[k].x >= 0) v[k].x = __ldg(feats + static_cast<size_t>(pid[k].x) * C + ch);
+          if (pid[k].y >= 0) v[k].y = __ldg(feats + static_cast<size_t>(pid[k].y) * C + ch);
+          if (pid[k].z >= 0) v[k].z = __ldg(feats + static_cast<size_t>(pid[k].z) * C + ch);
+          if (pid[k].w >= 0) v[k].w = __ldg(feats + static_cast<size_t>(pid[k].w) * C + ch);
+        }
+      }
+    };
+    float4 nxt[4];
+    load_plane(ch0, nxt);
+    for (int ch = ch0; ch < ch1; ++ch) {
+      float4 cur[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+      if (ch + 1 < ch1) load_plane(ch + 1, nxt);
+      uint16_t *o = out + static_cast<size_t>(ch) * G;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (g0 + 128 * k < G)
+          st_global_v2_stream_nc(o + 128 * k, pack_bf16x2(cur[k].x, cur[k].y), pack_bf16x2(cur[k].z, cur[k].w));
+    }
+  }
+}
+
 // One-pass scatter with the zeros and the features on separate instruction streams (the default when planes are
 // 32-byte aligned). k_scatter_warp composes every 16-byte store from four predicated loads — ~10 instructions per
 // store, 45 % issue utilisation, and the store stream stalls behind the feature loads; a plain memset of the same
@@ -493,6 +563,26 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
     const int blocks = static_cast<int>(std::min<long long>((total + kThreads - 1) / kThreads, kNumSMs * 16));
     k_scatter_scalar<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, total, canvas);
   }
+  MBEV_CHECK_LAUNCH();
+  return MBEV_OK;
+}
+
+extern "C" int mbev_scatter_forward_bf16(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny,
+                                         int nx, void *canvas_bf16, void *stream_) {
+  if (!cell_table || !canvas_bf16 || batch < 1 || c_out < 1 || ny < 1 || nx < 1) return MBEV_ERR_BAD_ARG;
+  const int64_t G64 = static_cast<int64_t>(ny) * nx;
+  if (G64 * batch > 0x7fffffffLL) return MBEV_ERR_UNSUPPORTED;
+  if ((G64 & 3) || (reinterpret_cast<uintptr_t>(canvas_bf16) & 7)) return MBEV_ERR_UNSUPPORTED;
+  const int G = static_cast<int>(G64);
+  const int tiles_per_frame = (G + kS2Cells - 1) / kS2Cells;
+  const int num_tiles = tiles_per_frame * batch;
+  const int want_warps = kNumSMs * 6 * (kThreads / 32);
+  int csplit = 1;
+  while (csplit < 16 && num_tiles * csplit < want_warps && c_out % (8 * csplit) == 0) csplit *= 2;
+  const int tasks = num_tiles * csplit;
+  const int blocks = std::min((tasks + kThreads / 32 - 1) / (kThreads / 32), kNumSMs * 6);
+  k_scatter_warp_bf16<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      feats, cell_table, c_out, G, tiles_per_frame, num_tiles, csplit, static_cast<uint16_t *>(canvas_bf16));
   MBEV_CHECK_LAUNCH();
   return MBEV_OK;
 }

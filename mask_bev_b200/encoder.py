@@ -85,24 +85,35 @@ class MaskBevEncoder(nn.Module):
             raise MbevError(f"voxel grid {gs.tolist()} disagrees with the canvas {out_shape} (SURVEY.md a1)")
 
     # -- fused path -------------------------------------------------------------------------------------
-    def encode_batch(self, point_clouds: List[torch.Tensor], return_aux: bool = False):
-        """K1 -> K2 -> K3 for the whole batch: (B, C_out, ny, nx) canvas, before the LayerNorm."""
+    def encode_batch(self, point_clouds: List[torch.Tensor], return_aux: bool = False,
+                     canvas_dtype: torch.dtype = torch.float32):
+        """K1 -> K2 -> K3 for the whole batch: (B, C_out, ny, nx) canvas, before the LayerNorm.
+        canvas_dtype=torch.bfloat16 (inference only): the PFN still computes in fp32, the canvas is written in bf16."""
         if len(point_clouds) == 0:
             raise MbevError("empty batch")
+        if canvas_dtype != torch.float32:
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self._voxel_encoder.parameters()):
+                raise MbevError("a bfloat16 canvas is forward-only: call under torch.no_grad()")
         sizes = [int(pc.shape[0]) for pc in point_clouds]
         pts = point_clouds[0] if len(point_clouds) == 1 else torch.cat(point_clouds, dim=0)
         pts = pts.contiguous()
         geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
         vb = F_.voxelize_batch(pts, sizes, geo)
-        fused = self._voxel_encoder.apply_rows_canvas(pts, vb.kept_idx, vb.num_points, vb.coors, vb.capacity,
-                                                      geo.max_points, vb.cell_table, len(sizes), self._num_voxel_y,
-                                                      self._num_voxel_x)
+        fused = None
+        if canvas_dtype == torch.float32:
+            fused = self._voxel_encoder.apply_rows_canvas(pts, vb.kept_idx, vb.num_points, vb.coors, vb.capacity,
+                                                          geo.max_points, vb.cell_table, len(sizes),
+                                                          self._num_voxel_y, self._num_voxel_x)
         if fused is not None:  # inference: K2 + K3 in one kernel
             feats, canvas = fused
         else:
             feats = self._voxel_encoder.apply_rows(pts, vb.kept_idx, vb.num_points, vb.coors, vb.num_pillars_dev,
                                                    vb.capacity, geo.max_points)
-            canvas = scatter_with_table(feats, vb.cell_table, len(sizes), self._num_voxel_y, self._num_voxel_x)
+            if canvas_dtype == torch.float32:
+                canvas = scatter_with_table(feats, vb.cell_table, len(sizes), self._num_voxel_y, self._num_voxel_x)
+            else:
+                canvas = F_.scatter_forward(feats.detach(), vb.cell_table, len(sizes), self._num_voxel_y,
+                                            self._num_voxel_x, dtype=canvas_dtype)
         if return_aux:
             return canvas, EncodeAux(vb.coors, vb.num_points, vb.kept_idx, vb.pillar_base, vb.cell_table, feats, sizes)
         return canvas

@@ -317,14 +317,23 @@ def build_cell_table(coors: torch.Tensor, num_pillars_dev: torch.Tensor, capacit
 
 
 def scatter_forward(feats: torch.Tensor, cell_table: torch.Tensor, batch: int, ny: int, nx: int,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    out: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """K3. dtype=torch.bfloat16 writes a bf16 canvas (= the fp32 canvas rounded to nearest-even; forward only)."""
     lib = _lib.load()
     _need_cuda(feats, "voxel_features")
     C = feats.shape[1]
-    canvas = out if out is not None else torch.empty((batch, C, ny, nx), dtype=torch.float32, device=feats.device)
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise _lib.MbevError(f"canvas dtype {dtype} is not supported (float32 or bfloat16)")
+    canvas = out if out is not None else torch.empty((batch, C, ny, nx), dtype=dtype, device=feats.device)
+    if canvas.dtype != dtype or tuple(canvas.shape) != (batch, C, ny, nx) or not canvas.is_contiguous():
+        raise _lib.MbevError("out must be a contiguous (B, C, ny, nx) tensor of the requested dtype")
     with torch.cuda.device(feats.device):
-        check(lib.mbev_scatter_forward(ptr(feats), ptr(cell_table), batch, C, ny, nx, ptr(canvas), _stream()),
-              "scatter_forward")
+        if dtype == torch.bfloat16:
+            check(lib.mbev_scatter_forward_bf16(ptr(feats), ptr(cell_table), batch, C, ny, nx, ptr(canvas), _stream()),
+                  "scatter_forward_bf16")
+        else:
+            check(lib.mbev_scatter_forward(ptr(feats), ptr(cell_table), batch, C, ny, nx, ptr(canvas), _stream()),
+                  "scatter_forward")
     return canvas
 
 

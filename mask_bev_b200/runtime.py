@@ -162,6 +162,20 @@ class FusedEncoderRunner:
                                              ptr(self.cell_table), self.B, self.c_out, self.ny, self.nx,
                                              ptr(self.canvas), self._stream()), "scatter_occupied")
 
+    def run_scatter_bf16(self):
+        """K3 into a bfloat16 canvas (allocated on first use)."""
+        if getattr(self, "canvas_bf16", None) is None:
+            self.canvas_bf16 = torch.empty((self.B, self.c_out, self.ny, self.nx), dtype=torch.bfloat16, device=self.device)
+        check(self.lib.mbev_scatter_forward_bf16(ptr(self.feats), ptr(self.cell_table), self.B, self.c_out, self.ny,
+                                                 self.nx, ptr(self.canvas_bf16), self._stream()), "scatter_forward_bf16")
+
+    def run_device_bf16(self):
+        """K1 -> K2 -> K3(bf16 canvas) on the resident points: three C-ABI calls, one stream, no host sync."""
+        self.run_voxelize()
+        self.run_pfn()
+        self.run_scatter_bf16()
+        return self.canvas_bf16
+
     def run_scatter(self):
         check(self.lib.mbev_scatter_forward(ptr(self.feats), ptr(self.cell_table), self.B, self.c_out, self.ny,
                                             self.nx, ptr(self.canvas), self._stream()), "scatter_forward")

@@ -312,3 +312,24 @@ def test_runner_pipelined_host_entry_matches_device_entry():
     for i, o in enumerate(outs):
         assert torch.equal(o, refs[i & 1]), f"back-to-back pipelined step {i} differs"
     r.close()
+
+
+@pytest.mark.parametrize("rng,vs,C", [((-40, 40), 0.16, 4), ((-75.2, 75.2), 0.32, 5)])
+def test_bf16_canvas_is_the_rounded_fp32_canvas(rng, vs, C):
+    """mbev_scatter_forward_bf16 (BASELINE config 4 / north star 1e-2 in bf16): bit-equal to the fp32 canvas cast to
+    bfloat16 (round to nearest even), hence within 2^-9 relative of it; forward only."""
+    kw = ref_test_kwargs(feat_channels=(128, 128, 128), T=32, C=C, x_range=rng, y_range=rng, vs=vs)
+    enc, orc = encoder_pair(kw, seed=9)
+    enc = enc.to(DEV).eval()
+    orc.pfn.eval()
+    frames = _frames(30000, C, seeds=(5, 6, 7))
+    pcs = [torch.from_numpy(f).to(DEV) for f in frames]
+    with torch.no_grad():
+        c32 = enc.encode_batch(pcs)
+        c16 = enc.encode_batch(pcs, canvas_dtype=torch.bfloat16)
+        ref = orc.forward(frames).numpy()
+    assert c16.dtype == torch.bfloat16 and c16.shape == c32.shape
+    assert torch.equal(c16, c32.to(torch.bfloat16))
+    assert rel_err(c16.float().cpu().numpy(), ref) <= 1e-2
+    with pytest.raises(Exception):
+        enc.encode_batch(pcs, canvas_dtype=torch.bfloat16)  # grad enabled: forward-only path refuses
