@@ -272,9 +272,13 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL writes its version banner to stdout when the first communicator is built; rank 0 must print ONE
+        # JSON line, so everything before that line goes to stderr (fd 1 -> fd 2 until the final print)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     cfg, kwargs, frames = build_workload(args.workload, rank)
     B = len(frames)
@@ -452,8 +456,13 @@ def run_ours(args):
                             "= same through mbev_encode_batch_host (copy and kernels on one stream)"},
             "roofline": roof, "kernels": kernels, "layernorm_f1": layernorm, "bf16_canvas": bf16, "cpu_baseline": cpu,
             "pillars_per_step": P, "kept_points_per_step": nk, "points_per_step": N}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)  # teardown chatter, if any, stays off stdout as well
         dist.destroy_process_group()
 
 

@@ -95,8 +95,10 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
   const int nw = gridDim.x * (kThreads / 32);
   const int cper = (C + csplit - 1) / csplit;
   for (int task = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); task < num_tiles * csplit; task += nw) {
-    const int tile = task / csplit;
-    const int ch0 = (task - tile * csplit) * cper, ch1 = min(C, ch0 + cper);
+    // last frame first: K2 has just written the features in pillar (= frame) order, so the rows of the last frames
+    // are the ones still in L2
+    const int tile = num_tiles - 1 - task / csplit;
+    const int ch0 = (task % csplit) * cper, ch1 = min(C, ch0 + cper);
     const int b = tile / tiles_per_frame;
     const int g0 = (tile - b * tiles_per_frame) * kS2Cells + 4 * lane;
     int4 pid[4];
