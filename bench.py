@@ -280,7 +280,7 @@ def run_ours(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
-    cfg, kwargs, frames = build_workload(args.workload, rank)
+    cfg, kwargs, frames = build_workload(args.workload, rank, batch=args.batch)
     B = len(frames)
     enc, pfn_cpu = make_encoder(kwargs, dev)
     runner = FusedEncoderRunner(enc, [len(f) for f in frames], dev, overlap=args.overlap)
@@ -473,6 +473,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti_b16")
+    ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (default: the workload's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layernorm", action="store_true", help="skip the K3+LayerNorm (SURVEY f1) timing")
     ap.add_argument("--overlap", action="store_true", help="two streams: K3a zero-fill under K2, then K3b (default: one stream, one-pass K3)")

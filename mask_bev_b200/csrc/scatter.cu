@@ -244,6 +244,83 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
   }
 }
 
+// Warp-local staging form of the one-pass scatter (MBEV_SCATTER=4). k_scatter_warp composes every 16-byte store
+// from four predicated loads and spends ~40 instructions per plane on a run that holds ~17 pillars (60 % issue
+// utilisation; zeros alone stream at 7.0 TB/s with the same access pattern). Here the warp keeps one plane of its
+// run (512 floats) in shared memory, all zeros: per plane, lane i drops the value of pillar i at its cell (one load
+// + one shared store per PILLAR, not per cell), the warp reads its 4 x 16 bytes back and streams them out, and lane
+// i zeroes its cell again. The (cell, pillar) list of the run is built once with ballots. No block barrier.
+__global__ void __launch_bounds__(kThreads)
+k_scatter_stage(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
+                const int tiles_per_frame, const int num_tiles, const int csplit, float *__restrict__ canvas) {
+  __shared__ __align__(16) float s_plane[kThreads / 32][kS2Cells];
+  __shared__ int s_pid[kThreads / 32][kS2Cells];
+  __shared__ unsigned short s_off[kThreads / 32][kS2Cells];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = gridDim.x * (kThreads / 32);
+  const int cper = (C + csplit - 1) / csplit;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float *plane = s_plane[warp];
+  for (int i = lane; i < kS2Cells; i += 32) plane[i] = 0.f;
+  __syncwarp();
+  for (int task = blockIdx.x * (kThreads / 32) + warp; task < num_tiles * csplit; task += nw) {
+    const int tile = num_tiles - 1 - task / csplit;  // last frame first (its feature rows are the freshest in L2)
+    const int ch0 = (task % csplit) * cper, ch1 = min(C, ch0 + cper);
+    const int b = tile / tiles_per_frame;
+    const int g0 = (tile - b * tiles_per_frame) * kS2Cells + 4 * lane;
+    int np = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = g0 + 128 * k;
+      const int4 p4 = (g < G) ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g))
+                              : make_int4(-1, -1, -1, -1);
+      const int pk[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned m = __ballot_sync(0xffffffffu, pk[j] >= 0);
+        if (pk[j] >= 0) {
+          const int pos = np + __popc(m & ((1u << lane) - 1u));
+          s_pid[warp][pos] = pk[j];
+          s_off[warp][pos] = static_cast<unsigned short>(128 * k + 4 * lane + j);
+        }
+        np += __popc(m);
+      }
+    }
+    __syncwarp();
+    float *out = canvas + (static_cast<size_t>(b) * C) * G + g0;
+    if (np == 0) {  // a run without pillars: pure zero stream
+      for (int ch = ch0; ch < ch1; ++ch) {
+        float *o = out + static_cast<size_t>(ch) * G;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (g0 + 128 * k < G) st_global_v4_stream(o + 128 * k, z);
+      }
+      continue;
+    }
+    // the first 32 pillars of the run live in registers (the usual case: ~17 per run), the rest in the list
+    const bool mine = lane < np;
+    const float *row0 = feats + static_cast<size_t>(mine ? s_pid[warp][lane] : 0) * C;
+    const int off0 = mine ? s_off[warp][lane] : 0;
+    float nxt = mine ? __ldg(row0 + ch0) : 0.f;
+    for (int ch = ch0; ch < ch1; ++ch) {
+      if (mine) plane[off0] = nxt;
+      for (int i = 32 + lane; i < np; i += 32) plane[s_off[warp][i]] = __ldg(feats + static_cast<size_t>(s_pid[warp][i]) * C + ch);
+      if (mine && ch + 1 < ch1) nxt = __ldg(row0 + ch + 1);
+      __syncwarp();
+      float *o = out + static_cast<size_t>(ch) * G;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 v = *reinterpret_cast<const float4 *>(plane + 128 * k + 4 * lane);
+        if (g0 + 128 * k < G) st_global_v4_stream_nc(o + 128 * k, v);
+      }
+      __syncwarp();
+      if (mine) plane[off0] = 0.f;
+      for (int i = 32 + lane; i < np; i += 32) plane[s_off[warp][i]] = 0.f;
+    }
+    __syncwarp();
+  }
+}
+
 // bf16 canvas (BASELINE config 4 / north star "1e-2 in bf16"): the same one-pass walk, every value rounded to
 // nearest-even bf16 on the way out, 8 bytes per lane and store — the canvas bytes, i.e. K3's roofline, halve.
 __device__ __forceinline__ void st_global_v2_stream_nc(void *p, uint32_t a, uint32_t b) {
@@ -542,7 +619,10 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
     // the hole kernel needs whole 32-byte sectors per lane pair (planes 32-byte aligned) and one channel quad per lane
     const bool holes = variant == 2 && (G & 7) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 31) == 0 &&
                        (c_out & 3) == 0 && c_out <= 128;
-    if (holes)
+    if (variant == 4)  // 40 KB of shared memory per CTA: 5 CTAs per SM
+      k_scatter_stage<<<std::min(blocks, kNumSMs * 5), kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame,
+                                                                             num_tiles, csplit, canvas);
+    else if (holes)
       k_scatter_holes<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame, num_tiles, csplit,
                                                        canvas);
     else
