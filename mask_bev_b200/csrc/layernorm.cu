@@ -20,7 +20,7 @@ namespace mbev {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kRun = 512;      // cells per warp task
+constexpr int kRun = 256;      // cells per warp task of k_scatter_ln
 constexpr int kStatBlocks = 64;  // partial sums per frame
 
 // partial (sum, sumsq) of the feature rows of frame b, slice j of kStatBlocks: one warp per pillar row at a time
@@ -80,12 +80,17 @@ __global__ void k_ln_finalize(const double2 *__restrict__ partial, const int bat
   stats[b] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + eps)));
 }
 
-// A warp owns (run of 512 cells, channel chunk, ONE frame) and composes x exactly as k_scatter_warp does (pillar
+// A warp owns (run of 256 cells, channel chunk, ONE frame) and composes x exactly as k_scatter_warp does (pillar
 // ids in registers, feature values requested one plane ahead), multiplies by the run's weight / adds its bias and
-// streams the result out. Tasks are ordered run-major / frame-minor, so the ~2 400 resident warps work on ~150 runs
-// for all frames at once: the weight / bias lines of a run are fetched from HBM once and hit L2 for the other
-// frames (footprint ~75 MB of the 126 MB L2).
-__global__ void __launch_bounds__(kThreads, 2)
+// streams the result out. Weight and bias of plane ch+1 are requested one plane ahead as well: they come from L2
+// (or HBM for the first frame that touches them) and were the kernel's main stall when loaded at the point of use
+// (ncu: long-scoreboard 11 per issue on the FMA lines, 16 warps per SM at 128 registers; hence the 256-cell run:
+// half the registers per warp, 24 warps per SM). Tasks are ordered run-major / frame-minor, so the resident warps
+// work on the same runs for all frames at once: the weight / bias lines of a run are fetched from HBM once and hit
+// L2 for the other frames (ncu: 886 MB of DRAM reads = weight + bias + features + table, each once).
+constexpr int kLnK = 2;  // 128-cell groups per run
+
+__global__ void __launch_bounds__(kThreads, 3)
 k_scatter_ln(const float *__restrict__ feats, const int *__restrict__ table, const float2 *__restrict__ stats,
              const float *__restrict__ lnw, const float *__restrict__ lnb, const int batch, const int C, const int G,
              const int runs, const int csplit, float *__restrict__ out) {
@@ -102,19 +107,23 @@ k_scatter_ln(const float *__restrict__ feats, const int *__restrict__ table, con
     const int g0 = run * kRun + 4 * lane;
     const float2 st = __ldg(stats + b);
     const float mean = st.x, rstd = st.y;
-    int4 pid[4];
-    bool inb[4], any = false;
+    int4 pid[kLnK];
+    bool inb[kLnK], any = false;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kLnK; ++k) {
       inb[k] = g0 + 128 * k < G;
       pid[k] = inb[k] ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g0 + 128 * k))
                       : make_int4(-1, -1, -1, -1);
       any |= (pid[k].x & pid[k].y & pid[k].z & pid[k].w) >= 0;
     }
-    auto load_plane = [&](int ch, float4 (&v)[4]) {
+    auto load_plane = [&](int ch, float4 (&v)[kLnK], float4 (&w)[kLnK], float4 (&bi)[kLnK]) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        v[k] = z;
+      for (int k = 0; k < kLnK; ++k) {
+        v[k] = w[k] = bi[k] = z;
+        if (inb[k]) {
+          w[k] = __ldg(reinterpret_cast<const float4 *>(lnw + static_cast<size_t>(ch) * G + g0 + 128 * k));
+          bi[k] = __ldg(reinterpret_cast<const float4 *>(lnb + static_cast<size_t>(ch) * G + g0 + 128 * k));
+        }
         if (any) {
           if (pid[k].x >= 0) v[k].x = __ldg(feats + static_cast<size_t>(pid[k].x) * C + ch);
           if (pid[k].y >= 0) v[k].y = __ldg(feats + static_cast<size_t>(pid[k].y) * C + ch);
@@ -123,25 +132,26 @@ k_scatter_ln(const float *__restrict__ feats, const int *__restrict__ table, con
         }
       }
     };
-    float4 nxt[4];
-    load_plane(ch0, nxt);
+    float4 xn[kLnK], wn[kLnK], bn[kLnK];
+    load_plane(ch0, xn, wn, bn);
     float *o = out + (static_cast<size_t>(b) * C) * G + g0;
     for (int ch = ch0; ch < ch1; ++ch) {
-      float4 x[4];
+      float4 x[kLnK], w[kLnK], bi[kLnK];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) x[k] = nxt[k];
-      if (ch + 1 < ch1) load_plane(ch + 1, nxt);
-      const float *wp = lnw + static_cast<size_t>(ch) * G + g0, *bp = lnb + static_cast<size_t>(ch) * G + g0;
+      for (int k = 0; k < kLnK; ++k) {
+        x[k] = xn[k];
+        w[k] = wn[k];
+        bi[k] = bn[k];
+      }
+      if (ch + 1 < ch1) load_plane(ch + 1, xn, wn, bn);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kLnK; ++k) {
         if (!inb[k]) continue;
-        const float4 w = __ldg(reinterpret_cast<const float4 *>(wp + 128 * k));
-        const float4 bi = __ldg(reinterpret_cast<const float4 *>(bp + 128 * k));
         float4 y;  // ((x - mean) * rstd) * w + b, the operation order of torch's LayerNorm kernel
-        y.x = __fmaf_rn(__fmul_rn(__fsub_rn(x[k].x, mean), rstd), w.x, bi.x);
-        y.y = __fmaf_rn(__fmul_rn(__fsub_rn(x[k].y, mean), rstd), w.y, bi.y);
-        y.z = __fmaf_rn(__fmul_rn(__fsub_rn(x[k].z, mean), rstd), w.z, bi.z);
-        y.w = __fmaf_rn(__fmul_rn(__fsub_rn(x[k].w, mean), rstd), w.w, bi.w);
+        y.x = __fmaf_rn(__fmul_rn(__fsub_rn(x[k].x, mean), rstd), w[k].x, bi[k].x);
+        y.y = __fmaf_rn(__fmul_rn(__fsub_rn(x[k].y, mean), rstd), w[k].y, bi[k].y);
+        y.z = __fmaf_rn(__fmul_rn(__fsub_rn(x[k].z, mean), rstd), w[k].z, bi[k].z);
+        y.w = __fmaf_rn(__fmul_rn(__fsub_rn(x[k].w, mean), rstd), w[k].w, bi[k].w);
         st_global_v4_stream_nc(o + static_cast<size_t>(ch) * G + 128 * k, y);
       }
     }
@@ -200,13 +210,13 @@ extern "C" int mbev_scatter_layernorm_forward(const float *feats, const int32_t 
                                                         static_cast<double>(eps), stats);
   MBEV_CHECK_LAUNCH();
   const int runs = (G + kRun - 1) / kRun;
-  const int want_warps = kNumSMs * 2 * (kThreads / 32) * 4;  // several tasks per resident warp (tail balance)
+  const int want_warps = kNumSMs * 3 * (kThreads / 32) * 4;  // several tasks per resident warp (tail balance)
   int csplit = 1;
   while (csplit < 32 && static_cast<int64_t>(runs) * batch * csplit < want_warps && c_out / (2 * csplit) >= 1) csplit *= 2;
   const int64_t tasks64 = static_cast<int64_t>(runs) * batch * csplit;
   if (tasks64 > 0x7fffffffLL) return MBEV_ERR_UNSUPPORTED;
   const int tasks = static_cast<int>(tasks64);
-  const int blocks = std::min((tasks + kThreads / 32 - 1) / (kThreads / 32), kNumSMs * 2);
+  const int blocks = std::min((tasks + kThreads / 32 - 1) / (kThreads / 32), kNumSMs * 3);
   k_scatter_ln<<<blocks, kThreads, 0, stream>>>(feats, cell_table, stats, ln_weight, ln_bias, batch, c_out, G, runs,
                                                 csplit, out);
   MBEV_CHECK_LAUNCH();
