@@ -216,7 +216,7 @@ extern "C" int mbev_scatter_layernorm_forward(const float *feats, const int32_t 
   const int64_t tasks64 = static_cast<int64_t>(runs) * batch * csplit;
   if (tasks64 > 0x7fffffffLL) return MBEV_ERR_UNSUPPORTED;
   const int tasks = static_cast<int>(tasks64);
-  const int blocks = std::min((tasks + kThreads / 32 - 1) / (kThreads / 32), kNumSMs * 3);
+  const int blocks = (tasks + kThreads / 32 - 1) / (kThreads / 32);  // no grid-stride: the CTA scheduler balances
   k_scatter_ln<<<blocks, kThreads, 0, stream>>>(feats, cell_table, stats, ln_weight, ln_bias, batch, c_out, G, runs,
                                                 csplit, out);
   MBEV_CHECK_LAUNCH();

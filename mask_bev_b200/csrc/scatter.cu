@@ -244,6 +244,68 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
   }
 }
 
+// Lean form of k_scatter_warp with the run length as a template parameter (KK x 128 cells): only the zero-stream
+// fast path and the composing loop with load-ahead. MBEV_SCATTER=5 runs KK = 2 (half the registers per warp, more
+// resident warps, 1 KB instead of 2 KB contiguous per plane and warp), MBEV_SCATTER=6 runs KK = 4.
+template <int KK, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_scatter_run(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
+              const int tiles_per_frame, const int num_tiles, const int csplit, float *__restrict__ canvas) {
+  const int lane = threadIdx.x & 31;
+  const int nw = gridDim.x * (kThreads / 32);
+  const int cper = (C + csplit - 1) / csplit;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int task = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); task < num_tiles * csplit; task += nw) {
+    const int tile = num_tiles - 1 - task / csplit;
+    const int ch0 = (task % csplit) * cper, ch1 = min(C, ch0 + cper);
+    const int b = tile / tiles_per_frame;
+    const int g0 = (tile - b * tiles_per_frame) * (128 * KK) + 4 * lane;
+    int4 pid[KK];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      const int g = g0 + 128 * k;
+      pid[k] = (g < G) ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g))
+                       : make_int4(-1, -1, -1, -1);
+      any |= (pid[k].x & pid[k].y & pid[k].z & pid[k].w) >= 0;
+    }
+    float *out = canvas + (static_cast<size_t>(b) * C) * G + g0;
+    if (!__any_sync(0xffffffffu, any)) {
+      for (int ch = ch0; ch < ch1; ++ch) {
+        float *o = out + static_cast<size_t>(ch) * G;
+#pragma unroll
+        for (int k = 0; k < KK; ++k)
+          if (g0 + 128 * k < G) st_global_v4_stream(o + 128 * k, z);
+      }
+      continue;
+    }
+    auto load_plane = [&](int ch, float4 (&v)[KK]) {
+#pragma unroll
+      for (int k = 0; k < KK; ++k) {
+        v[k] = z;
+        if (any) {
+          if (pid[k].x >= 0) v[k].x = __ldg(feats + static_cast<size_t>(pid[k].x) * C + ch);
+          if (pid[k].y >= 0) v[k].y = __ldg(feats + static_cast<size_t>(pid[k].y) * C + ch);
+          if (pid[k].z >= 0) v[k].z = __ldg(feats + static_cast<size_t>(pid[k].z) * C + ch);
+          if (pid[k].w >= 0) v[k].w = __ldg(feats + static_cast<size_t>(pid[k].w) * C + ch);
+        }
+      }
+    };
+    float4 nxt[KK];
+    load_plane(ch0, nxt);
+    for (int ch = ch0; ch < ch1; ++ch) {
+      float4 cur[KK];
+#pragma unroll
+      for (int k = 0; k < KK; ++k) cur[k] = nxt[k];
+      if (ch + 1 < ch1) load_plane(ch + 1, nxt);
+      float *o = out + static_cast<size_t>(ch) * G;
+#pragma unroll
+      for (int k = 0; k < KK; ++k)
+        if (g0 + 128 * k < G) st_global_v4_stream_nc(o + 128 * k, cur[k]);
+    }
+  }
+}
+
 // Warp-local staging form of the one-pass scatter (MBEV_SCATTER=4). k_scatter_warp composes every 16-byte store
 // from four predicated loads and spends ~40 instructions per plane on a run that holds ~17 pillars (60 % issue
 // utilisation; zeros alone stream at 7.0 TB/s with the same access pattern). Here the warp keeps one plane of its
@@ -601,12 +663,14 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int G = static_cast<int>(G64);
   const size_t smem = sizeof(float) * kCells * (static_cast<size_t>(c_out) + 1);
-  // 2: zeros / features on separate instruction streams; 1: composing warp-per-run; 0: tile kernel with barriers
+  // 5 (default): k_scatter_run<2>, non-persistent; 6/7/8: other run lengths / occupancies; 1: k_scatter_warp
+  // (persistent, 512-cell runs; also hosts the developer probes); 2: k_scatter_holes; 4: k_scatter_stage; 0: tile kernel
   // (2 measured 2.3 ms against 0.97 ms for 1 on kitti_b16: single 32-byte sectors written apart from their line cost
   // DRAM read-modify-writes; kept selectable as a documented negative result.) 3: developer probe, zeros only.
-  static const int variant = getenv("MBEV_SCATTER") ? atoi(getenv("MBEV_SCATTER")) : 1;
+  static const int variant = getenv("MBEV_SCATTER") ? atoi(getenv("MBEV_SCATTER")) : 5;
   // developer knob: 0 = compose every store (default), 1 = zero stream (.cs) + feature drops, 2 = same with plain stores
   static const int sparse_mode = getenv("MBEV_SCATTER_SPARSE") ? atoi(getenv("MBEV_SCATTER_SPARSE")) : 0;
+  static const int s2_ctas_env = getenv("MBEV_SCATTER_CTAS") ? atoi(getenv("MBEV_SCATTER_CTAS")) : 0;
   static const int s2_ctas = getenv("MBEV_SCATTER_CTAS") ? atoi(getenv("MBEV_SCATTER_CTAS")) : 6;
   if (variant >= 1 && (G & 3) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 15) == 0) {
     const int tiles_per_frame = (G + kS2Cells - 1) / kS2Cells;
@@ -619,7 +683,22 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
     // the hole kernel needs whole 32-byte sectors per lane pair (planes 32-byte aligned) and one channel quad per lane
     const bool holes = variant == 2 && (G & 7) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 31) == 0 &&
                        (c_out & 3) == 0 && c_out <= 128;
-    if (variant == 4)  // 40 KB of shared memory per CTA: 5 CTAs per SM
+    if (variant >= 5 && variant <= 8) {
+      // default (5): 256-cell runs, one CTA per 8 tasks and NO grid-stride loop — the hardware CTA scheduler balances
+      // the unequal runs better than a persistent grid did (0.94 -> 0.87 ms on kitti_b16)
+      const int kk = variant == 5 ? 2 : variant == 6 ? 4 : variant == 7 ? 2 : 1;
+      const int tpf = (G + 128 * kk - 1) / (128 * kk);
+      const int nt = tpf * batch;
+      int cs = 1;  // small batches: split the channels of a run over several warps
+      while (cs < 16 && nt * cs < want_warps && c_out % (8 * cs) == 0) cs *= 2;
+      const int64_t tasks5 = static_cast<int64_t>(nt) * cs;
+      const int full = static_cast<int>((tasks5 + kThreads / 32 - 1) / (kThreads / 32));
+      const int blk = s2_ctas_env > 0 ? std::min(full, kNumSMs * s2_ctas_env) : full;
+      if (variant == 5) k_scatter_run<2, 1><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
+      else if (variant == 6) k_scatter_run<4, 1><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
+      else if (variant == 7) k_scatter_run<2, 4><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
+      else k_scatter_run<1, 5><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
+    } else if (variant == 4)  // 40 KB of shared memory per CTA: 5 CTAs per SM
       k_scatter_stage<<<std::min(blocks, kNumSMs * 5), kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame,
                                                                              num_tiles, csplit, canvas);
     else if (holes)
@@ -662,7 +741,7 @@ extern "C" int mbev_scatter_forward_bf16(const float *feats, const int32_t *cell
   int csplit = 1;
   while (csplit < 16 && num_tiles * csplit < want_warps && c_out % (8 * csplit) == 0) csplit *= 2;
   const int tasks = num_tiles * csplit;
-  const int blocks = std::min((tasks + kThreads / 32 - 1) / (kThreads / 32), kNumSMs * 6);
+  const int blocks = (tasks + kThreads / 32 - 1) / (kThreads / 32);  // no grid-stride: the CTA scheduler balances
   k_scatter_warp_bf16<<<blocks, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
       feats, cell_table, c_out, G, tiles_per_frame, num_tiles, csplit, static_cast<uint16_t *>(canvas_bf16));
   MBEV_CHECK_LAUNCH();
