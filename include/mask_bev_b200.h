@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 5
+#define MBEV_ABI_VERSION 6
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -266,6 +266,21 @@ MBEV_API int mbev_encode_batch_host_async(const float *points_host, float *point
                                           int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
                                           size_t workspace_bytes, void *stream, void *aux_stream, void *copy_stream,
                                           void *ev_copied, void *ev_consumed);
+
+/* Two-stage pipeline for a stream of batches. Stage 1 runs on `prep_stream`: wait `ev_consumed` (the previous batch
+ * that used THIS buffer set is done), copy `points_host` to `points_dev` if points_host != NULL (else the points are
+ * already resident), K1; record `ev_ready`. Stage 2 runs on `stream`: wait `ev_ready`, K2, K3, record `ev_consumed`.
+ * The caller alternates TWO buffer sets (points_dev when copying, cell_table, coors, num_points, kept_idx,
+ * pillar_base, vox_workspace, and the event pair): K1 — latency / L2 bound — and the H2D copy of batch i+1 then
+ * overlap K2 / K3 of batch i. feats, canvas and `workspace` (mbev_pfn_workspace_bytes) stay single: stage 2 is
+ * ordered by `stream`. vox_workspace: mbev_voxelize_workspace_bytes. */
+MBEV_API int mbev_encode_batch_pipelined(const float *points_host, float *points_dev,
+                                         const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
+                                         const MbevPfnParams *params, int32_t *cell_table, int32_t *coors,
+                                         int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
+                                         int64_t pillar_capacity, float *feats, float *canvas, void *vox_workspace,
+                                         size_t vox_workspace_bytes, void *workspace, size_t workspace_bytes,
+                                         void *stream, void *prep_stream, void *ev_ready, void *ev_consumed);
 
 /* Launch counter: number of library kernels enqueued by this process since load (for bench.py's
  * `gpu_launches`). Thread-safe. */

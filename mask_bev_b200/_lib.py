@@ -13,7 +13,7 @@ MAX_BATCH = 128
 MAX_LAYERS = 4
 MAX_UNITS = 128
 MAX_POINT_DIM = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 GEMM_AUTO, GEMM_FMA, GEMM_TCGEN05 = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -83,6 +83,8 @@ SIGNATURES = {
     "mbev_event_destroy": (c_int, [_v]),
     "mbev_encode_batch_host_async": (c_int, [_v, _v, POINTER(c_int64), c_int, _G, _P, _v, _v, _v, _v, _v, c_int64, _v,
                                              _v, _v, c_size_t, _v, _v, _v, _v, _v]),
+    "mbev_encode_batch_pipelined": (c_int, [_v, _v, POINTER(c_int64), c_int, _G, _P, _v, _v, _v, _v, _v, c_int64, _v, _v,
+                                            _v, c_size_t, _v, c_size_t, _v, _v, _v, _v]),
     "mbev_launch_count": (c_int64, []),
 }
 

@@ -174,3 +174,44 @@ extern "C" int mbev_encode_batch_host_async(const float *points_host, float *poi
   MBEV_CUDA(cudaEventRecord(e_consumed, ms));  // also on error, so that the copy stream never waits forever
   return st;
 }
+
+// ---- two-stage pipeline for a stream of batches: [H2D +] K1 of batch i+1 on a prep stream under K2 / K3 of batch i ----
+extern "C" int mbev_encode_batch_pipelined(const float *points_host, float *points_dev,
+                                           const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
+                                           const MbevPfnParams *params, int32_t *cell_table, int32_t *coors,
+                                           int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
+                                           int64_t pillar_capacity, float *feats, float *canvas, void *vox_workspace,
+                                           size_t vox_workspace_bytes, void *workspace, size_t workspace_bytes,
+                                           void *stream, void *prep_stream, void *ev_ready, void *ev_consumed) {
+  if (!geo || !params || !frame_offsets_host || batch < 1 || batch > MBEV_MAX_BATCH) return MBEV_ERR_BAD_ARG;
+  if (!prep_stream || !ev_ready || !ev_consumed || prep_stream == stream || !feats || !canvas || !workspace)
+    return MBEV_ERR_BAD_ARG;
+  if (geo->grid[2] != 1) return MBEV_ERR_UNSUPPORTED;
+  cudaStream_t ps = static_cast<cudaStream_t>(prep_stream), ms = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e_ready = static_cast<cudaEvent_t>(ev_ready), e_consumed = static_cast<cudaEvent_t>(ev_consumed);
+  const int64_t total = frame_offsets_host[batch];
+  size_t pb = 0;
+  int st = mbev_pfn_workspace_bytes(params, geo->max_points, pillar_capacity, 0, &pb);
+  if (st) return st;
+  if (workspace_bytes < pb) return MBEV_ERR_WORKSPACE;
+  // stage 1 (prep stream): the previous batch that used THIS buffer set must be done with it
+  MBEV_CUDA(cudaStreamWaitEvent(ps, e_consumed, 0));
+  if (points_host && total > 0) {
+    if (!points_dev) return MBEV_ERR_BAD_ARG;
+    MBEV_CUDA(cudaMemcpyAsync(points_dev, points_host, sizeof(float) * static_cast<size_t>(total) * geo->num_feats,
+                              cudaMemcpyHostToDevice, ps));
+  }
+  st = mbev_voxelize(points_dev, frame_offsets_host, batch, geo, cell_table, coors, num_points, kept_idx, pillar_base,
+                     pillar_capacity, vox_workspace, vox_workspace_bytes, prep_stream);
+  MBEV_CUDA(cudaEventRecord(e_ready, ps));
+  // stage 2 (main stream)
+  MBEV_CUDA(cudaStreamWaitEvent(ms, e_ready, 0));
+  if (!st)
+    st = mbev_pfn_forward(points_dev, geo->num_feats, kept_idx, num_points, coors, pillar_base + batch, pillar_capacity,
+                          geo->max_points, params, feats, workspace, workspace_bytes, stream);
+  if (!st)
+    st = mbev_scatter_forward(feats, cell_table, batch, params->units[params->num_layers - 1], geo->grid[1],
+                              geo->grid[0], canvas, stream);
+  MBEV_CUDA(cudaEventRecord(e_consumed, ms));  // also on error, so that the prep stream never waits forever
+  return st;
+}

@@ -113,7 +113,59 @@ class FusedEncoderRunner:
               "encode_batch_host_async")
         return self.canvas
 
+    def _pipe2_init(self):
+        dev, T = self.device, self.geo.max_points
+        cells = self.ny * self.nx
+        nb = ctypes.c_size_t()
+        check(self.lib.mbev_voxelize_workspace_bytes(ctypes.byref(self.geo), self.B, self.total, ctypes.byref(nb)), "ws")
+        self._p2_sets = []
+        for k in range(2):
+            ev = []
+            for _ in range(2):
+                e = ctypes.c_void_p()
+                check(self.lib.mbev_event_create(ctypes.byref(e)), "event_create")
+                ev.append(e)
+            self._p2_sets.append(dict(
+                points=torch.empty_like(self.points_dev),
+                cell_table=self.cell_table if k == 0 else torch.empty_like(self.cell_table),
+                coors=self.coors if k == 0 else torch.empty_like(self.coors),
+                num_points=self.num_points if k == 0 else torch.empty_like(self.num_points),
+                kept_idx=self.kept_idx if k == 0 else torch.empty_like(self.kept_idx),
+                pillar_base=self.pillar_base if k == 0 else torch.zeros_like(self.pillar_base),
+                vox_ws=torch.empty(max(nb.value, 16), dtype=torch.uint8, device=dev), ev=ev))
+        self._p2_prep = torch.cuda.Stream(device=dev)
+        self._p2_i = 0
+        self._p2_last = self._p2_sets[0]
+
+    def run_pipelined(self, points_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Stream-of-batches form (mbev_encode_batch_pipelined): the H2D copy (when `points_host` is given; otherwise
+        the runner's resident points) and K1 of this batch run on a prep stream into one of two buffer sets and
+        overlap K2 / K3 of the previous batch. `last_pillar_base` is the pillar_base of the batch just enqueued."""
+        if getattr(self, "_p2_sets", None) is None:
+            self._pipe2_init()
+        s = self._p2_sets[self._p2_i & 1]
+        self._p2_i += 1
+        pts_dev = s["points"] if points_host is not None else self.points_dev
+        check(self.lib.mbev_encode_batch_pipelined(ptr(points_host), ptr(pts_dev), self.off, self.B,
+                                                   ctypes.byref(self.geo), ctypes.byref(self.params),
+                                                   ptr(s["cell_table"]), ptr(s["coors"]), ptr(s["num_points"]),
+                                                   ptr(s["kept_idx"]), ptr(s["pillar_base"]), self.cap,
+                                                   ptr(self.feats), ptr(self.canvas), ptr(s["vox_ws"]),
+                                                   s["vox_ws"].numel(), ptr(self.ws), self.ws.numel(), self._stream(),
+                                                   ctypes.c_void_p(self._p2_prep.cuda_stream), s["ev"][0], s["ev"][1]),
+              "encode_batch_pipelined")
+        self._p2_last = s
+        return self.canvas
+
+    @property
+    def last_pillar_base(self) -> torch.Tensor:
+        return self._p2_last["pillar_base"] if getattr(self, "_p2_sets", None) is not None else self.pillar_base
+
     def close(self):
+        for st in getattr(self, "_p2_sets", None) or []:
+            for e in st["ev"]:
+                self.lib.mbev_event_destroy(e)
+        self._p2_sets = None
         for e in getattr(self, "_pipe_events", []):
             self.lib.mbev_event_destroy(e)
         self._pipe_events = []

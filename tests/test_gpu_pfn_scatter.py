@@ -333,3 +333,36 @@ def test_bf16_canvas_is_the_rounded_fp32_canvas(rng, vs, C):
     assert rel_err(c16.float().cpu().numpy(), ref) <= 1e-2
     with pytest.raises(Exception):
         enc.encode_batch(pcs, canvas_dtype=torch.bfloat16)  # grad enabled: forward-only path refuses
+
+
+def test_runner_two_stage_pipeline_matches_device_entry():
+    """mbev_encode_batch_pipelined: K1 (and the H2D copy) of batch i+1 on a prep stream under K2 / K3 of batch i, two
+    buffer sets; canvases and pillar counts equal the single-stream entry, in order, with and without host input."""
+    from mask_bev_b200.runtime import FusedEncoderRunner
+    kw = ref_test_kwargs(feat_channels=(128, 128, 128), T=32)
+    enc, _ = encoder_pair(kw, seed=19)
+    enc = enc.to(DEV).eval()
+    fa, fb = _frames(30000, 4, seeds=(51, 52)), _frames(30000, 4, seeds=(53, 54))
+    ha = torch.from_numpy(np.concatenate(fa, 0)).pin_memory()
+    hb = torch.from_numpy(np.concatenate(fb, 0)).pin_memory()
+    r = FusedEncoderRunner(enc, [len(f) for f in fa], torch.device(DEV))
+    refs, bases = [], []
+    for h in (ha, hb):
+        refs.append(r.run_device(h.to(DEV)).clone())
+        bases.append(r.pillar_base.clone())
+    torch.cuda.synchronize()
+    outs, got_bases = [], []
+    for i in range(7):  # back to back, no host synchronisation in between
+        r.run_pipelined(hb if i & 1 else ha)
+        outs.append(r.canvas.clone())
+        got_bases.append(r.last_pillar_base.clone())
+    torch.cuda.synchronize()
+    for i, (o, b) in enumerate(zip(outs, got_bases)):
+        assert torch.equal(o, refs[i & 1]), f"pipelined step {i} differs"
+        assert torch.equal(b, bases[i & 1])
+    r.points_dev.copy_(ha.to(DEV))  # device-resident form: no copy, K1 still on the prep stream
+    for i in range(3):
+        r.run_pipelined()
+        torch.cuda.synchronize()
+        assert torch.equal(r.canvas, refs[0])
+    r.close()
