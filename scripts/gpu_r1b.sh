@@ -10,7 +10,7 @@ for w in semkitti_b1 waymo_b32 dense_1024; do
   timeout 300 python bench.py --no-cpu-baseline --workload $w > gpurun_out/${T}_bench_$w.json 2> gpurun_out/${T}_bench_$w.err
 done
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_bench.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-layernorm > gpurun_out/${T}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_scatter_run -s 3 -c 1 -o gpurun_out/${T}_scatter python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pfn_tcw2 -s 3 -c 1 -o gpurun_out/${T}_pfn python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_rank|k_assign|k_emit|k_scan|k_head|k_flag" -s 12 -c 5 -o gpurun_out/${T}_vox python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
