@@ -16,6 +16,8 @@
 //   per layer  l = L-1..0 :  k_dz (arg-max routing + ReLU mask + BN sums) ; k_bn_finalize (dgamma, dbeta) ;
 //                            k_dy ; dW_l = dY^T X_l (split-K, fixed-order reduce) ; dX = dY W_l
 // Every reduction has a fixed order => run-to-run identical gradients. fp32 FMA throughout (1e-5 parity).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mbev {
@@ -200,6 +202,95 @@ k_gemm(const __grid_constant__ GemmK g) {
   }
 }
 
+// Row-streaming form for the two GEMMs whose M is the compact row count (forward recompute Y = X W^T, dX = dY W):
+// 128 x BN tile, BK 16, 256 threads, 8 x (BN/16) outputs per thread (16 FMAs per shared-memory load instead of 8),
+// the next k-block's global loads are in flight while the current one is multiplied. A must be row-major
+// (sAk == 1). Every output element still accumulates k = 0, 1, 2, ... in order with one fmaf per term, so the
+// result is bit-identical to k_gemm and to the forward kernel the statistics came from.
+template <int BN>
+__global__ void __launch_bounds__(256)
+k_gemm_rows(const __grid_constant__ GemmK g) {
+  constexpr int BM = 128, BK = 16, TN = BN / 16;
+  __shared__ float sA[BK][BM + 4];
+  __shared__ float sB[BK][BN + 4];
+  const int M = g.m_dev ? *g.m_dev : g.M;
+  const int K = g.K, N = g.N;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.y * BN;
+  for (int mt = blockIdx.x; mt * BM < M; mt += gridDim.x) {
+    const int m0 = mt * BM;
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    float ra[8], rb[BN / 16];
+    auto gload = [&](int kb) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {  // A tile 128 x 16: 16 consecutive k of one row per 16 threads
+        const int idx = tid + it * 256;
+        const int kk = idx & 15, mm = idx >> 4;
+        const int m = m0 + mm, k = kb + kk;
+        ra[it] = (m < M && k < K) ? __ldg(g.A + static_cast<long long>(m) * g.sAm + k) : 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < BN / 16; ++it) {  // B tile 16 x BN, fastest thread index along the unit stride
+        const int idx = tid + it * 256;
+        int nn, kk;
+        if (g.sBn == 1) { nn = idx % BN; kk = idx / BN; } else { kk = idx & 15; nn = idx >> 4; }
+        const int n = n0 + nn, k = kb + kk;
+        rb[it] = (n < N && k < K) ? __ldg(g.B + static_cast<long long>(k) * g.sBk + static_cast<long long>(n) * g.sBn) : 0.f;
+      }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = tid + it * 256;
+        sA[idx & 15][idx >> 4] = ra[it];
+      }
+#pragma unroll
+      for (int it = 0; it < BN / 16; ++it) {
+        const int idx = tid + it * 256;
+        if (g.sBn == 1) sB[idx / BN][idx % BN] = rb[it]; else sB[idx & 15][idx >> 4] = rb[it];
+      }
+    };
+    gload(0);
+    for (int kb = 0; kb < K; kb += BK) {
+      __syncthreads();  // the previous block's readers are done with the tiles
+      sstore();
+      __syncthreads();
+      if (kb + BK < K) gload(kb + BK);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4 *>(&sA[kk][ty * 8]);
+        const float4 a1 = *reinterpret_cast<const float4 *>(&sA[kk][ty * 8 + 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float bv[TN];  // columns tx*4 .. tx*4+3 of every 64-column half: consecutive lanes read consecutive 16 bytes
+#pragma unroll
+        for (int j4 = 0; j4 < TN; j4 += 4) {
+          const float4 b = *reinterpret_cast<const float4 *>(&sB[kk][tx * 4 + 16 * j4]);
+          bv[j4] = b.x; bv[j4 + 1] = b.y; bv[j4 + 2] = b.z; bv[j4 + 3] = b.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + ty * 8 + i;
+      if (m >= M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int n = n0 + tx * 4 + 16 * (j & ~3) + (j & 3);
+        if (n < N) g.C[static_cast<long long>(m) * g.ldc + n] = acc[i][j];
+      }
+    }
+  }
+}
+
 // fixed-order reduction of split-K partials into dst (count elements)
 __global__ void k_reduce_splits(const float *__restrict__ part, const int nsplit, const long long stride,
                                 const int count, float *__restrict__ dst) {
@@ -377,6 +468,17 @@ BwdWs carve_bwd(void *ws, const MbevPfnParams *p, int64_t cap, int64_t rows_cap)
 }
 
 int launch_gemm(const GemmK &g, int m_tiles_cap, int n, int splits, cudaStream_t stream) {
+  static const bool old_gemm = getenv("MBEV_BWD_GEMM64") != nullptr;  // developer knob: the 64 x 64 kernel everywhere
+  if (!old_gemm && splits == 1 && g.sAk == 1 && g.m_dev != nullptr && (g.sBn == 1 || g.sBk == 1)) {
+    const int tiles = std::max(1, std::min((m_tiles_cap + 1) / 2, kNumSMs * 4));
+    if (n > 64) {
+      k_gemm_rows<128><<<dim3(tiles, (n + 127) / 128), 256, 0, stream>>>(g);
+    } else {
+      k_gemm_rows<64><<<dim3(tiles, (n + 63) / 64), 256, 0, stream>>>(g);
+    }
+    MBEV_CHECK_LAUNCH();
+    return MBEV_OK;
+  }
   dim3 grid(std::max(1, std::min(m_tiles_cap, kNumSMs * 8)), (n + 63) / 64, splits);
   k_gemm<<<grid, 256, 0, stream>>>(g);
   MBEV_CHECK_LAUNCH();
