@@ -87,16 +87,14 @@ k_scatter(const float *__restrict__ feats, const int *__restrict__ table, const 
 constexpr int kS2Cells = 512;
 
 // `csplit` > 1 (small batches): a task is (run, channel chunk) so that one frame still fills the machine.
+// Persistent form (grid-stride over tasks): kept selectable (MBEV_SCATTER=1) next to k_scatter_run, which replaced it.
 __global__ void __launch_bounds__(kThreads)
 k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
-               const int tiles_per_frame, const int num_tiles, const int csplit, const int sparse_mode,
-               float *__restrict__ canvas) {
+               const int tiles_per_frame, const int num_tiles, const int csplit, float *__restrict__ canvas) {
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * (kThreads / 32);
   const int cper = (C + csplit - 1) / csplit;
   for (int task = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); task < num_tiles * csplit; task += nw) {
-    // last frame first: K2 has just written the features in pillar (= frame) order, so the rows of the last frames
-    // are the ones still in L2
     const int tile = num_tiles - 1 - task / csplit;
     const int ch0 = (task % csplit) * cper, ch1 = min(C, ch0 + cper);
     const int b = tile / tiles_per_frame;
@@ -106,105 +104,18 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int g = g0 + 128 * k;
-      pid[k] = (g < G && feats) ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g))
-                                : make_int4(-1, -1, -1, -1);
+      pid[k] = (g < G) ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g))
+                       : make_int4(-1, -1, -1, -1);
       any |= (pid[k].x & pid[k].y & pid[k].z & pid[k].w) >= 0;
     }
     float *out = canvas + (static_cast<size_t>(b) * C) * G + g0;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!__any_sync(0xffffffffu, any)) {  // a run without pillars: pure zero stream
-      if (sparse_mode == 4) continue;  // (probe) occupied lines only
       for (int ch = ch0; ch < ch1; ++ch) {
         float *o = out + static_cast<size_t>(ch) * G;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (g0 + 128 * k < G) st_global_v4_stream(o + 128 * k, z);
-      }
-      continue;
-    }
-    // Sparse runs (the LiDAR case: ~17 pillars in 512 cells, no lane owns more than kSlots of them): per plane the
-    // warp streams 4 unconditional zero stores and each lane then drops its few feature values as 4-byte stores
-    // into its OWN 16 bytes of the line it wrote a few instructions earlier (same thread, same address: ordered;
-    // the line is still in L2, so DRAM sees one full-line write). Feature rows are read 4 channels at a time and
-    // one channel quad ahead. ~8 instructions per plane instead of ~40 for the composing loop below.
-    constexpr int kSlots = 4;
-    int sp[kSlots], so[kSlots], mycnt = 0;  // pillar id / cell offset inside the run of this lane's occupied cells
-#pragma unroll
-    for (int j = 0; j < kSlots; ++j) sp[j] = so[j] = 0;
-    if (sparse_mode == 1 || sparse_mode == 2)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int pk[4] = {pid[k].x, pid[k].y, pid[k].z, pid[k].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (pk[j] >= 0) {
-#pragma unroll
-          for (int q = 0; q < kSlots; ++q)
-            if (mycnt == q) {
-              sp[q] = pk[j];
-              so[q] = 128 * k + j;
-            }
-          ++mycnt;
-        }
-      }
-    }
-    const int maxcnt = __reduce_max_sync(0xffffffffu, mycnt);
-    if ((sparse_mode == 1 || sparse_mode == 2) && maxcnt <= kSlots && ((ch1 - ch0) & 3) == 0 && (ch0 & 3) == 0) {
-      float4 nxt[kSlots];
-#pragma unroll
-      for (int q = 0; q < kSlots; ++q)
-        nxt[q] = (q < mycnt) ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(sp[q]) * C + ch0)) : z;
-      for (int c4 = ch0; c4 < ch1; c4 += 4) {
-        float4 cur[kSlots];
-#pragma unroll
-        for (int q = 0; q < kSlots; ++q) {
-          cur[q] = nxt[q];
-          if (q < maxcnt && q < mycnt && c4 + 4 < ch1)
-            nxt[q] = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(sp[q]) * C + c4 + 4));
-        }
-        float *o = out + static_cast<size_t>(c4) * G;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (g0 + 128 * k < G) {
-              if (sparse_mode == 2) *reinterpret_cast<float4 *>(o + static_cast<size_t>(i) * G + 128 * k) = z;
-              else st_global_v4_stream(o + static_cast<size_t>(i) * G + 128 * k, z);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < kSlots; ++q) {
-          if (q < maxcnt && q < mycnt) {
-            float *d = o + so[q];
-            d[0] = cur[q].x;
-            d[static_cast<size_t>(G)] = cur[q].y;
-            d[2 * static_cast<size_t>(G)] = cur[q].z;
-            d[3 * static_cast<size_t>(G)] = cur[q].w;
-          }
-        }
-      }
-      continue;
-    }
-    if (sparse_mode == 3 && ((ch1 - ch0) & 3) == 0 && (ch0 & 3) == 0) {
-      // compose 4 planes at a time: one 16-byte feature load per occupied cell and channel quad
-      for (int c4 = ch0; c4 < ch1; c4 += 4) {
-        float *o = out + static_cast<size_t>(c4) * G;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float4 v0 = z, v1 = z, v2 = z, v3 = z;
-          if (any) {
-            if (pid[k].x >= 0) v0 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid[k].x) * C + c4));
-            if (pid[k].y >= 0) v1 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid[k].y) * C + c4));
-            if (pid[k].z >= 0) v2 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid[k].z) * C + c4));
-            if (pid[k].w >= 0) v3 = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid[k].w) * C + c4));
-          }
-          if (g0 + 128 * k < G) {
-            st_global_v4_stream(o + 128 * k, make_float4(v0.x, v1.x, v2.x, v3.x));
-            st_global_v4_stream(o + static_cast<size_t>(G) + 128 * k, make_float4(v0.y, v1.y, v2.y, v3.y));
-            st_global_v4_stream(o + 2 * static_cast<size_t>(G) + 128 * k, make_float4(v0.z, v1.z, v2.z, v3.z));
-            st_global_v4_stream(o + 3 * static_cast<size_t>(G) + 128 * k, make_float4(v0.w, v1.w, v2.w, v3.w));
-          }
-        }
       }
       continue;
     }
@@ -222,13 +133,6 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
         }
       }
     };
-    bool wr[4];  // (probe, sparse_mode 4 / 5) write only the 128-byte lines with / without a pillar
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned m = __ballot_sync(0xffffffffu, (pid[k].x & pid[k].y & pid[k].z & pid[k].w) >= 0);
-      const bool lineocc = (m & (0xffu << (lane & ~7))) != 0;
-      wr[k] = (g0 + 128 * k < G) && (sparse_mode == 4 ? lineocc : sparse_mode == 5 ? !lineocc : true);
-    }
     float4 nxt[4];
     load_plane(ch0, nxt);
     for (int ch = ch0; ch < ch1; ++ch) {
@@ -239,7 +143,7 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
       float *o = out + static_cast<size_t>(ch) * G;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (wr[k]) st_global_v4_stream_nc(o + 128 * k, cur[k]);
+        if (g0 + 128 * k < G) st_global_v4_stream_nc(o + 128 * k, cur[k]);
     }
   }
 }
@@ -247,8 +151,8 @@ k_scatter_warp(const float *__restrict__ feats, const int *__restrict__ table, c
 // Lean form of k_scatter_warp with the run length as a template parameter (KK x 128 cells): only the zero-stream
 // fast path and the composing loop with load-ahead. MBEV_SCATTER=5 runs KK = 2 (half the registers per warp, more
 // resident warps, 1 KB instead of 2 KB contiguous per plane and warp), MBEV_SCATTER=6 runs KK = 4.
-template <int KK, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
+template <int KK>
+__global__ void __launch_bounds__(kThreads)
 k_scatter_run(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
               const int tiles_per_frame, const int num_tiles, const int csplit, float *__restrict__ canvas) {
   const int lane = threadIdx.x & 31;
@@ -663,13 +567,11 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int G = static_cast<int>(G64);
   const size_t smem = sizeof(float) * kCells * (static_cast<size_t>(c_out) + 1);
-  // 5 (default): k_scatter_run<2>, non-persistent; 6/7/8: other run lengths / occupancies; 1: k_scatter_warp
-  // (persistent, 512-cell runs; also hosts the developer probes); 2: k_scatter_holes; 4: k_scatter_stage; 0: tile kernel
+  // 5 (default): k_scatter_run<2>, non-persistent; 6: the same with 512-cell runs; 1: k_scatter_warp (persistent,
+  // 512-cell runs); 2: k_scatter_holes; 4: k_scatter_stage; 0: tile kernel with block barriers
   // (2 measured 2.3 ms against 0.97 ms for 1 on kitti_b16: single 32-byte sectors written apart from their line cost
-  // DRAM read-modify-writes; kept selectable as a documented negative result.) 3: developer probe, zeros only.
+  // DRAM read-modify-writes; kept selectable as a documented negative result.)
   static const int variant = getenv("MBEV_SCATTER") ? atoi(getenv("MBEV_SCATTER")) : 5;
-  // developer knob: 0 = compose every store (default), 1 = zero stream (.cs) + feature drops, 2 = same with plain stores
-  static const int sparse_mode = getenv("MBEV_SCATTER_SPARSE") ? atoi(getenv("MBEV_SCATTER_SPARSE")) : 0;
   static const int s2_ctas_env = getenv("MBEV_SCATTER_CTAS") ? atoi(getenv("MBEV_SCATTER_CTAS")) : 0;
   static const int s2_ctas = getenv("MBEV_SCATTER_CTAS") ? atoi(getenv("MBEV_SCATTER_CTAS")) : 6;
   if (variant >= 1 && (G & 3) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 15) == 0) {
@@ -683,10 +585,10 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
     // the hole kernel needs whole 32-byte sectors per lane pair (planes 32-byte aligned) and one channel quad per lane
     const bool holes = variant == 2 && (G & 7) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 31) == 0 &&
                        (c_out & 3) == 0 && c_out <= 128;
-    if (variant >= 5 && variant <= 8) {
+    if (variant == 5 || variant == 6) {
       // default (5): 256-cell runs, one CTA per 8 tasks and NO grid-stride loop — the hardware CTA scheduler balances
-      // the unequal runs better than a persistent grid did (0.94 -> 0.87 ms on kitti_b16)
-      const int kk = variant == 5 ? 2 : variant == 6 ? 4 : variant == 7 ? 2 : 1;
+      // the unequal runs better than a persistent grid did (0.94 -> 0.87 ms on kitti_b16); 6: 512-cell runs
+      const int kk = variant == 5 ? 2 : 4;
       const int tpf = (G + 128 * kk - 1) / (128 * kk);
       const int nt = tpf * batch;
       int cs = 1;  // small batches: split the channels of a run over several warps
@@ -694,10 +596,8 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
       const int64_t tasks5 = static_cast<int64_t>(nt) * cs;
       const int full = static_cast<int>((tasks5 + kThreads / 32 - 1) / (kThreads / 32));
       const int blk = s2_ctas_env > 0 ? std::min(full, kNumSMs * s2_ctas_env) : full;
-      if (variant == 5) k_scatter_run<2, 1><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
-      else if (variant == 6) k_scatter_run<4, 1><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
-      else if (variant == 7) k_scatter_run<2, 4><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
-      else k_scatter_run<1, 5><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
+      if (variant == 5) k_scatter_run<2><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
+      else k_scatter_run<4><<<blk, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tpf, nt, cs, canvas);
     } else if (variant == 4)  // 40 KB of shared memory per CTA: 5 CTAs per SM
       k_scatter_stage<<<std::min(blocks, kNumSMs * 5), kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame,
                                                                              num_tiles, csplit, canvas);
@@ -705,8 +605,8 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
       k_scatter_holes<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame, num_tiles, csplit,
                                                        canvas);
     else
-      k_scatter_warp<<<blocks, kThreads, 0, stream>>>(variant == 3 ? nullptr : feats, cell_table, c_out, G,
-                                                      tiles_per_frame, num_tiles, csplit, sparse_mode, canvas);
+      k_scatter_warp<<<blocks, kThreads, 0, stream>>>(feats, cell_table, c_out, G, tiles_per_frame, num_tiles, csplit,
+                                                      canvas);
   } else if ((G & 3) == 0 && (reinterpret_cast<uintptr_t>(canvas) & 15) == 0 && smem <= 200 * 1024) {
     const int tiles_per_frame = (G + kCells - 1) / kCells;
     const int num_tiles = tiles_per_frame * batch;

@@ -58,6 +58,41 @@ def test_argument_validation_without_gpu():
         _lib.check(-3, "x")
 
 
+def test_capability_probes_without_gpu():
+    """Shape / alignment probes of the fused entries are pure host code: they answer without a device."""
+    from mask_bev_b200 import _lib
+    from mask_bev_b200 import functional as F_
+    import mask_bev_b200 as M
+    from mask_bev_b200.synthetic import encoder_kwargs
+    lib = _lib.load()
+    null = ctypes.c_void_p(None)
+    # K3 + LayerNorm: ny*nx must be a multiple of 4, batch within MBEV_MAX_BATCH
+    assert lib.mbev_scatter_layernorm_supported(16, 128, 800, 800, null, null, null) == 1
+    assert lib.mbev_scatter_layernorm_supported(2, 64, 25, 25, null, null, null) == 0
+    assert lib.mbev_scatter_layernorm_supported(0, 64, 500, 500, null, null, null) == 0
+    assert lib.mbev_scatter_layernorm_supported(129, 64, 500, 500, null, null, null) == 0
+    n = ctypes.c_size_t()
+    assert lib.mbev_scatter_layernorm_workspace_bytes(16, ctypes.byref(n)) == 0 and n.value >= 16 * 64 * 16
+    assert lib.mbev_scatter_layernorm_workspace_bytes(0, ctypes.byref(n)) == -1
+    # K2 + K3 fused kernel: tcgen05 stack, T <= 32, plane a multiple of 4 cells and at least one strip
+    enc = M.MaskBevEncoder(**encoder_kwargs("kitti_b16"))
+    cfg = enc._voxel_encoder._config()
+    assert F_.pfn_scatter_supported(cfg, 32, 16, 800, 800)
+    assert not F_.pfn_scatter_supported(cfg, 100, 16, 800, 800)
+    assert not F_.pfn_scatter_supported(cfg, 32, 1, 8, 8)
+    assert F_.pfn_scatter_default() in (False, True)
+    # the pipelined entries refuse missing streams / events before touching the device
+    geo = F_.make_geometry([0.1, 0.1, 40], [0, -40, -20, 80, 40, 20], 32, 250000, 4, True)
+    off = (ctypes.c_int64 * 2)(0, 10)
+    params = F_._pfn_struct(cfg, [None] * 3, None, None)
+    st = lib.mbev_encode_batch_pipelined(null, null, off, 1, ctypes.byref(geo), ctypes.byref(params), null, null, null,
+                                         null, null, 10, null, null, null, 0, null, 0, null, null, null, null)
+    assert st == -1
+    st = lib.mbev_encode_batch_host_async(null, null, off, 1, ctypes.byref(geo), ctypes.byref(params), null, null, null,
+                                          null, null, 10, null, null, null, 0, null, null, null, null, null)
+    assert st == -1
+
+
 def test_state_dict_keys_and_shapes_match_upstream():
     import mask_bev_b200 as M
     enc = M.MaskBevEncoder(**ref_test_kwargs(feat_channels=(128, 128, 128), T=32))
