@@ -192,7 +192,7 @@ k_pfn(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, cons
           const float ex = __fsub_rn(x, s_ctr[pl * 4 + 0]), ey = __fsub_rn(y, s_ctr[pl * 4 + 1]),
                       ez = __fsub_rn(z, s_ctr[pl * 4 + 2]);
           const bool alias = k.vcenter && k.legacy;  // legacy: centre offset written in place over xyz
-          const float r0 = alias ? ex : x, r1 = alias ? ey : y, r2 = alias ? ez : z;
+          const float r0 = alias ? ex : x, r1 = alias ? ey : y, r2 = (alias && k.vcd > 2) ? ez : z;  // 2-channel centre: z stays raw
           int d = 0;
           x_in[(d++) * XP + row] = r0;
           x_in[(d++) * XP + row] = r1;

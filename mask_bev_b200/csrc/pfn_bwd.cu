@@ -109,7 +109,7 @@ k_decorate_rows(const float *__restrict__ rows_src, const int *__restrict__ kept
       const float x = q[0], y = q[1], z = q[2];
       const float ex = __fsub_rn(x, cx), ey = __fsub_rn(y, cy), ez = __fsub_rn(z, cz);
       const bool alias = k.vcenter && k.legacy;
-      const float a0 = alias ? ex : x, a1 = alias ? ey : y, a2 = alias ? ez : z;
+      const float a0 = alias ? ex : x, a1 = alias ? ey : y, a2 = (alias && k.vcd > 2) ? ez : z;
       float *o = x0 + static_cast<size_t>(r0 + t) * k.D0;
       int d = 0;
       o[d++] = a0; o[d++] = a1; o[d++] = a2;

@@ -160,7 +160,7 @@ __device__ __forceinline__ void build_x0(const Kargs &k, const Window &w, const 
     const float x = pv[0], y = pv[1], z = pv[2];
     const float ex = __fsub_rn(x, cx), ey = __fsub_rn(y, cy), ez = __fsub_rn(z, cz);
     const bool alias = k.vcenter && k.legacy;  // legacy: centre offset written in place over xyz
-    const float r0 = alias ? ex : x, r1 = alias ? ey : y, r2 = alias ? ez : z;
+    const float r0 = alias ? ex : x, r1 = alias ? ey : y, r2 = (alias && k.vcd > 2) ? ez : z;  // 2-channel centre: z stays raw
     int d = 0;
     xd[d++] = r0;
     xd[d++] = r1;

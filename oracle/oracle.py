@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY. Nothing under ``mask_bev_b200/`` imports this module; 
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs do, and there
 only as the checker or as the timed CPU baseline.
 
-PARITY UNPINNED. The reference path (``/root/reference/mask_bev/models/encoders/mask_bev_encoders.py:21-123``)
+PARITY UNPINNED, EXCEPT THE POINT DECORATION (see the last bullet). The reference path (``/root/reference/mask_bev/models/encoders/mask_bev_encoders.py:21-123``)
 delegates its arithmetic to ``mmcv==2.0.0`` (``mmcv.ops.Voxelization``) and ``mmdet3d==1.1.0``
 (``PillarFeatureNet`` / ``PFNLayer`` / ``PointPillarsScatter``), pinned in ``Dockerfile:25,28``; neither
 is vendored, installed or installable offline, and the reference's own tests
@@ -14,7 +14,10 @@ published upstream algorithms and is pinned by
   * three independent voxelizer restatements that must agree (pure-Python loop, numpy stable-sort, C),
   * two independent PFN restatements that must agree (dense upstream op sequence with torch CPU ops vs
     sparse "virtual row" float64 numpy form),
-  * the invariants of SURVEY.md A.5 under hypothesis.
+  * the invariants of SURVEY.md A.5 under hypothesis,
+  * and, for the decoration only, outputs of the reference's OWN code: the commented mmdet3d-0.x ``forward`` kept in
+    ``mask_bev_encoders.py:270-317`` is executed by ``tests/golden/make_golden_decoration.py`` where the reference
+    lies; ``decorate(voxel_center_dims=2)`` reproduces the committed vectors bit for bit (tests/test_oracle.py).
 
 Reference call sites each function follows are cited in its docstring.
 """
@@ -290,10 +293,14 @@ def make_pfn_oracle(in_channels=4, feat_channels=(64,), with_distance=False, wit
                 cy = coors[:, 2].type_as(features).unsqueeze(1) * self.vy + self.y_offset
                 cz = coors[:, 1].type_as(features).unsqueeze(1) * self.vz + self.z_offset
                 if legacy:
-                    f_center = features[:, :, :3]          # a VIEW: the in-place writes alias channels 0..2
+                    # a VIEW of the first `voxel_center_dims` raw channels: the in-place writes alias them. With the
+                    # 2-channel centre of mmdet3d 0.x only x, y are touched — pinned against the reference's own
+                    # (commented) forward, mask_bev_encoders.py:270-317, through tests/golden/decoration_vcd2.npz.
+                    f_center = features[:, :, :voxel_center_dims]
                     f_center[:, :, 0] = f_center[:, :, 0] - cx
                     f_center[:, :, 1] = f_center[:, :, 1] - cy
-                    f_center[:, :, 2] = f_center[:, :, 2] - cz
+                    if voxel_center_dims > 2:
+                        f_center[:, :, 2] = f_center[:, :, 2] - cz
                 else:
                     f_center = torch.zeros_like(features[:, :, :3])
                     f_center[:, :, 0] = features[:, :, 0] - cx
@@ -371,9 +378,12 @@ def pfn_sparse_np(voxels, num_points, coors4, weights, bn, voxel_size, pc_range,
                     (c32[:, 1].astype(f32) * f32(vz) + f32(zo))], axis=1).astype(np.float64)
     cluster = v[:, :, :3] - mean[:, None, :]
     centre = v[:, :, :3] - ctr[:, None, :]
-    parts = [centre, v[:, :, 3:], cluster, centre[:, :, :voxel_center_dims]]
+    aliased = centre.copy()  # legacy in-place write: only the first `voxel_center_dims` raw channels are overwritten
+    if voxel_center_dims < 3:
+        aliased[:, :, 2] = v[:, :, 2]
+    parts = [aliased, v[:, :, 3:], cluster, centre[:, :, :voxel_center_dims]]
     if with_distance:
-        parts.append(np.linalg.norm(centre, axis=2, keepdims=True))
+        parts.append(np.linalg.norm(aliased, axis=2, keepdims=True))
     dec = np.concatenate(parts, axis=2)
     pid, tt = np.nonzero(slot)
     x = dec[pid, tt]                                                            # (N_k, D) real rows

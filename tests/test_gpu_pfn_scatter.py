@@ -366,3 +366,27 @@ def test_runner_two_stage_pipeline_matches_device_entry():
         torch.cuda.synchronize()
         assert torch.equal(r.canvas, refs[0])
     r.close()
+
+
+@pytest.mark.parametrize("chans,gemm", [((64,), "auto"), ((32, 64), "auto"), ((128, 128, 128), "auto"), ((128, 128, 128), "fma")])
+@pytest.mark.parametrize("legacy", [True, False])
+def test_pfn_vcd2_on_the_reference_fossil_inputs(chans, gemm, legacy):
+    """2-channel pillar-centre offset (the mmdet3d-0.x form whose code survives in mask_bev_encoders.py:270-317) on the
+    inputs of tests/golden/decoration_vcd2.npz, whose z centre is NOT zero: in legacy mode only x, y are aliased, z
+    stays raw. The oracle's decoration is pinned bit-exactly to the reference's own code on these inputs
+    (tests/test_oracle.py); here every device implementation must agree with that oracle, forward and train-mode."""
+    import os
+    import mask_bev_b200 as M
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decoration_vcd2.npz"))
+    okw = dict(in_channels=4, feat_channels=chans, with_distance=True, voxel_size=tuple(g["voxel_size"]),
+               point_cloud_range=tuple(g["point_cloud_range"]), legacy=legacy, voxel_center_dims=2)
+    orc = O.randomise_pfn(O.make_pfn_oracle(**okw), seed=3).eval()
+    net = M.PillarFeatureNet(**okw)
+    net.gemm_path = gemm
+    net.load_state_dict(orc.state_dict())
+    net = net.to(DEV).eval()
+    vox, nump, coors = (torch.from_numpy(g[k]) for k in ("voxels", "num_points", "coors"))
+    with torch.no_grad():
+        ref = orc(vox, nump, coors).numpy()
+        out = net(vox.to(DEV), nump.to(DEV), coors.to(DEV))
+    assert_close(out.cpu().numpy(), ref, what=f"vcd2 legacy={legacy} {chans} {gemm}")
