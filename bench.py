@@ -436,6 +436,19 @@ def run_ours(args):
                          "frac_hbm": by_ln / t_ln / 1e6 / peak, "K3_then_torch_layernorm_ms": t_sc + t_torch,
                          "torch_layernorm_ms": t_torch,
                          "note": "mbev_scatter_layernorm_forward vs K3 followed by nn.LayerNorm([C,ny,nx]) (mask_bev_encoders.py:75,92)"}
+            # its backward (training): out_ln stands in for the incoming gradient (any dense tensor of that shape)
+            if F_.scatter_layernorm_backward_supported(B, Co, runner.ny, runner.nx):
+                stats_ln = fused_ln()[1]
+
+                def fused_ln_bwd():
+                    return F_.scatter_layernorm_backward(out_ln, runner.feats, runner.cell_table, runner.coors,
+                                                         runner.pillar_base[B:], ln.weight, stats_ln)
+                t_lnb = ev_time(fused_ln_bwd, iters, sync)
+                by_lnb = B * G * Co * 4 + 3 * G * Co * 4 + B * G * 4 + 5 * P * Co * 4
+                layernorm.update({"K3+LN_backward_ms": t_lnb, "backward_alg_bytes": by_lnb,
+                                  "backward_gbs": by_lnb / t_lnb / 1e6, "backward_frac_hbm": by_lnb / t_lnb / 1e6 / peak,
+                                  "backward_note": "mbev_scatter_layernorm_backward: dy read once, dweight / dbias "
+                                                   "written once, dfeats in pillar space"})
         del out_ln
     dom = max(("K1_voxelize", "K2_pfn", "K3_scatter"), key=lambda k: kernels[k]["ms"])
     roof = {"kernel": "K3_scatter (k_scatter_warp)", "bound": "hbm", "achieved": kernels["K3_scatter"]["gbs"], "peak": peak,

@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 6
+#define MBEV_ABI_VERSION 7
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -188,7 +188,7 @@ MBEV_API int mbev_scatter_backward(const float *dcanvas, const int32_t *cell_tab
                           int nx, float *dfeats, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
- * K3+LN  scatter fused with the LayerNorm that follows it (forward, inference) — SURVEY.md §8 row f1.
+ * K3+LN  scatter fused with the LayerNorm that follows it (forward and backward) — SURVEY.md §8 row f1.
  * Replaces: `self._layer_norm(self.middle_encode(...))` with nn.LayerNorm([C, ny, nx], eps=1e-3)
  *           (mask_bev_encoders.py:75, 91-92): per frame, normalisation over all C*ny*nx elements, element-wise affine.
  * The statistics come from the pillar features alone (all other cells are exact zeros; fp64, fixed order), then one
@@ -205,6 +205,26 @@ MBEV_API int mbev_scatter_layernorm_forward(const float *feats, const int32_t *c
                                             int batch, int c_out, int ny, int nx, const float *ln_weight,
                                             const float *ln_bias, float eps, float *out, float *stats_out,
                                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward of the above (autograd of mask_bev_encoders.py:91-92; the reference has no code for it, torch derives it).
+ * With xh = (x - mean_b) * rstd_b, g = dout * weight, M = C*ny*nx:
+ *   dbias = sum_b dout;  dweight = sum_b dout * xh  (dense);  dfeats[p,:] = rstd_b * (g - mean(g) - xh * mean(g*xh))
+ * at the pillar's cell. dout is read once, dweight / dbias are written once; the per-frame sums are fp64 and
+ * fixed-order (run-to-run identical).
+ *   dout (batch, C, ny, nx); feats (pillar_capacity, C) = the forward's input; coors (pillar_capacity, 4) (b,z,y,x);
+ *   num_pillars_dev = device pillar count (pillar_base + batch); stats (batch, 2) = the forward's stats_out;
+ *   dfeats (pillar_capacity, C): rows of pillars that are not in cell_table and rows >= the pillar count get zeros;
+ *   dweight, dbias (C, ny, nx).
+ * Needs C % 4 == 0, ny*nx % 4 == 0 (probe: mbev_scatter_layernorm_backward_supported) and 16-byte aligned pointers
+ * (MBEV_ERR_UNSUPPORTED otherwise). */
+MBEV_API int mbev_scatter_layernorm_backward_supported(int batch, int c_out, int ny, int nx);
+MBEV_API int mbev_scatter_layernorm_backward_workspace_bytes(int batch, int c_out, int ny, int nx, size_t *bytes);
+MBEV_API int mbev_scatter_layernorm_backward(const float *dout, const float *feats, const int32_t *cell_table,
+                                             const int32_t *coors, const int32_t *num_pillars_dev,
+                                             int64_t pillar_capacity, int batch, int c_out, int ny, int nx,
+                                             const float *ln_weight, const float *stats, float *dfeats,
+                                             float *dweight, float *dbias, void *workspace, size_t workspace_bytes,
+                                             void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2+K3 in one kernel (eval mode): PillarFeatureNet.forward and PointPillarsScatter.forward_batch

@@ -13,7 +13,7 @@ MAX_BATCH = 128
 MAX_LAYERS = 4
 MAX_UNITS = 128
 MAX_POINT_DIM = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 GEMM_AUTO, GEMM_FMA, GEMM_TCGEN05 = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -69,6 +69,10 @@ SIGNATURES = {
     "mbev_scatter_layernorm_workspace_bytes": (c_int, [c_int, POINTER(c_size_t)]),
     "mbev_scatter_layernorm_forward": (c_int, [_v, _v, _v, c_int, c_int, c_int, c_int, _v, _v, c_float, _v, _v, _v,
                                                c_size_t, _v]),
+    "mbev_scatter_layernorm_backward_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "mbev_scatter_layernorm_backward_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "mbev_scatter_layernorm_backward": (c_int, [_v, _v, _v, _v, _v, c_int64, c_int, c_int, c_int, c_int, _v, _v, _v,
+                                                _v, _v, _v, c_size_t, _v]),
     "mbev_pfn_scatter_supported": (c_int, [_P, c_int, c_int, c_int, c_int, _v]),
     "mbev_pfn_scatter_default": (c_int, []),
     "mbev_pfn_scatter_workspace_bytes": (c_int, [_P, c_int, c_int64, c_int, c_int, c_int, POINTER(c_size_t)]),

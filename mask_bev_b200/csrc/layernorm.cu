@@ -10,7 +10,8 @@
 //     k_scatter_warp; tasks are ordered so that all frames of a run are in flight together and the run's weight /
 //     bias come from HBM once and from L2 for the other frames: ~B*C*G*4 + 2*C*G*4 bytes of DRAM traffic instead of
 //     ~4*B*C*G*4 (measured history: a frame-inner loop with dependent table/feature loads per store 3.5-4.0 ms).
-// Forward only (inference / no-grad); the autograd path keeps torch's LayerNorm after K3.
+// The backward (mbev_scatter_layernorm_backward, lower half of this file) streams dy once for dweight / dbias and the
+// two per-frame sums, and finishes dfeats in the compact pillar space.
 #include <algorithm>
 #include <cmath>
 
@@ -158,10 +159,219 @@ k_scatter_ln(const float *__restrict__ feats, const int *__restrict__ table, con
   }
 }
 
+// ---- backward of the fused scatter + LayerNorm ------------------------------------------------------------------
+// With xh = (x - mean_b) * rstd_b (x = pillar feature or 0), g = dy * w and M = C*G elements per frame:
+//   dbias = sum_b dy,  dweight = sum_b dy * xh                       (dense: an empty cell has xh = -mean_b*rstd_b != 0)
+//   dx = rstd_b * (g - S1_b / M - xh * S2_b / M),  S1_b = sum g,  S2_b = sum g * xh   (sums over the whole frame)
+//   dfeats[p, :] = dx at the pillar's cell (the scatter's gather backward).
+// Pass 1 (k_ln_bwd_dense) streams dy once: a warp owns (128 cells, 4 channels) and walks the frames with dweight /
+// dbias in registers, so they are written once and dy / weight are read once; at occupied cells it parks g in the
+// dfeats row of the pillar (4 channels = one 16-byte piece) and it leaves per-(frame, CTA) partial sums of S1, S2
+// (fp32 over a lane's 16 terms, fp64 from there on, fixed order => run-to-run identical). Pass 2 folds the partials,
+// pass 3 (k_ln_bwd_feats) turns the parked g into dfeats in place, in the compact pillar space.
+constexpr int kBwdRun = 128;  // cells per warp task: lane owns 4 consecutive cells
+constexpr int kBwdCh = 4;     // channels per warp task
+
+__device__ __forceinline__ float4 ld_global_v4_stream(const float *p) {
+  float4 v;  // read once, never again: keep it out of the way of weight / table / feature lines in L1 / L2
+  asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_ln_bwd_dense(const float *__restrict__ dy, const float *__restrict__ feats, const int *__restrict__ table,
+               const float2 *__restrict__ stats, const float *__restrict__ lnw, const int batch, const int C,
+               const int G, const int nchunks, const long long tasks, float *__restrict__ dw, float *__restrict__ db,
+               float *__restrict__ gfeat, double2 *__restrict__ partial) {
+  __shared__ double2 s_part[MBEV_MAX_BATCH][kThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long task = static_cast<long long>(blockIdx.x) * (kThreads / 32) + warp;
+  const int run = static_cast<int>(task / nchunks);
+  const int ch0 = static_cast<int>(task - static_cast<long long>(run) * nchunks) * kBwdCh;
+  const int g0 = run * kBwdRun + 4 * lane;
+  const bool inb = task < tasks && g0 < G;  // G % 4 == 0: a lane's four cells are in or out together
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w[kBwdCh], aw[kBwdCh], ab[kBwdCh];
+#pragma unroll
+  for (int k = 0; k < kBwdCh; ++k) {
+    w[k] = inb ? __ldg(reinterpret_cast<const float4 *>(lnw + static_cast<size_t>(ch0 + k) * G + g0)) : z;
+    aw[k] = ab[k] = z;
+  }
+  int4 pid_n = make_int4(-1, -1, -1, -1);
+  float4 d_n[kBwdCh];
+  auto request = [&](int b) {  // table row and dy of frame b (issued one frame ahead of their use)
+    pid_n = __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g0));
+#pragma unroll
+    for (int k = 0; k < kBwdCh; ++k)
+      d_n[k] = ld_global_v4_stream(dy + (static_cast<size_t>(b) * C + ch0 + k) * G + g0);
+  };
+#pragma unroll
+  for (int k = 0; k < kBwdCh; ++k) d_n[k] = z;
+  if (inb) request(0);
+  for (int b = 0; b < batch; ++b) {
+    float s1 = 0.f, s2 = 0.f;
+    if (inb) {
+      const int4 pid = pid_n;
+      float4 d[kBwdCh];
+#pragma unroll
+      for (int k = 0; k < kBwdCh; ++k) d[k] = d_n[k];
+      float4 f[4];  // f[cell] = the 4 channels of that cell's pillar (zeros for an empty cell)
+      f[0] = pid.x >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.x) * C + ch0)) : z;
+      f[1] = pid.y >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.y) * C + ch0)) : z;
+      f[2] = pid.z >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.z) * C + ch0)) : z;
+      f[3] = pid.w >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.w) * C + ch0)) : z;
+      if (b + 1 < batch) request(b + 1);
+      const float2 st = __ldg(stats + b);
+      const float mean = st.x, rstd = st.y;
+      const float xk[kBwdCh][4] = {{f[0].x, f[1].x, f[2].x, f[3].x},
+                                   {f[0].y, f[1].y, f[2].y, f[3].y},
+                                   {f[0].z, f[1].z, f[2].z, f[3].z},
+                                   {f[0].w, f[1].w, f[2].w, f[3].w}};  // xk[channel][cell]
+      float4 g[kBwdCh];
+#pragma unroll
+      for (int k = 0; k < kBwdCh; ++k) {
+        float4 xh;
+        xh.x = (xk[k][0] - mean) * rstd;
+        xh.y = (xk[k][1] - mean) * rstd;
+        xh.z = (xk[k][2] - mean) * rstd;
+        xh.w = (xk[k][3] - mean) * rstd;
+        ab[k].x += d[k].x;
+        ab[k].y += d[k].y;
+        ab[k].z += d[k].z;
+        ab[k].w += d[k].w;
+        aw[k].x = fmaf(d[k].x, xh.x, aw[k].x);
+        aw[k].y = fmaf(d[k].y, xh.y, aw[k].y);
+        aw[k].z = fmaf(d[k].z, xh.z, aw[k].z);
+        aw[k].w = fmaf(d[k].w, xh.w, aw[k].w);
+        g[k].x = d[k].x * w[k].x;
+        g[k].y = d[k].y * w[k].y;
+        g[k].z = d[k].z * w[k].z;
+        g[k].w = d[k].w * w[k].w;
+        s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
+        s2 += fmaf(g[k].x, xh.x, g[k].y * xh.y) + fmaf(g[k].z, xh.z, g[k].w * xh.w);
+      }
+      if (pid.x >= 0)
+        *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.x) * C + ch0) = make_float4(g[0].x, g[1].x, g[2].x, g[3].x);
+      if (pid.y >= 0)
+        *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.y) * C + ch0) = make_float4(g[0].y, g[1].y, g[2].y, g[3].y);
+      if (pid.z >= 0)
+        *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.z) * C + ch0) = make_float4(g[0].z, g[1].z, g[2].z, g[3].z);
+      if (pid.w >= 0)
+        *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.w) * C + ch0) = make_float4(g[0].w, g[1].w, g[2].w, g[3].w);
+    }
+    double a = static_cast<double>(s1), q = static_cast<double>(s2);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) s_part[b][warp] = make_double2(a, q);
+  }
+  if (inb) {
+#pragma unroll
+    for (int k = 0; k < kBwdCh; ++k) {
+      st_global_v4_stream(dw + static_cast<size_t>(ch0 + k) * G + g0, aw[k]);
+      st_global_v4_stream(db + static_cast<size_t>(ch0 + k) * G + g0, ab[k]);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < batch; b += kThreads) {
+    double a = 0.0, q = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kThreads / 32; ++wv) {
+      a += s_part[b][wv].x;
+      q += s_part[b][wv].y;
+    }
+    partial[static_cast<size_t>(b) * gridDim.x + blockIdx.x] = make_double2(a, q);
+  }
+}
+
+// msum[b] = (S1_b / M, S2_b / M): one CTA per frame, fixed-order strided sums + shared-memory tree
+__global__ void __launch_bounds__(kThreads)
+k_ln_bwd_finalize(const double2 *__restrict__ partial, const int nblocks, const double count,
+                  float2 *__restrict__ msum) {
+  __shared__ double s_a[kThreads], s_q[kThreads];
+  const int b = blockIdx.x, t = threadIdx.x;
+  double a = 0.0, q = 0.0;
+  for (int j = t; j < nblocks; j += kThreads) {
+    const double2 v = partial[static_cast<size_t>(b) * nblocks + j];
+    a += v.x;
+    q += v.y;
+  }
+  s_a[t] = a;
+  s_q[t] = q;
+  __syncthreads();
+  for (int o = kThreads / 2; o; o >>= 1) {
+    if (t < o) {
+      s_a[t] += s_a[t + o];
+      s_q[t] += s_q[t + o];
+    }
+    __syncthreads();
+  }
+  if (t == 0) msum[b] = make_float2(static_cast<float>(s_a[0] / count), static_cast<float>(s_q[0] / count));
+}
+
+// dfeats[p, :] = rstd_b * (g - S1_b/M - xh * S2_b/M), in place over the g parked by pass 1; one warp per pillar row.
+// Rows that are not in the cell table (none for a table from mbev_voxelize; duplicates of a hand-made coors list) and
+// rows at or beyond the pillar count get zeros.
+__global__ void __launch_bounds__(kThreads)
+k_ln_bwd_feats(const float *__restrict__ feats, const int *__restrict__ coors, const int *__restrict__ num_pillars,
+               const int *__restrict__ table, const float2 *__restrict__ stats, const float2 *__restrict__ msum,
+               const long long capacity, const int batch, const int C, const int ny, const int nx,
+               float *__restrict__ dfeats) {
+  const int lane = threadIdx.x & 31;
+  const int P = *num_pillars;
+  const int G = ny * nx;
+  const long long nwarps = static_cast<long long>(gridDim.x) * (kThreads / 32);
+  for (long long p = static_cast<long long>(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5); p < capacity;
+       p += nwarps) {
+    bool ok = false;
+    int b = 0;
+    if (p < P) {
+      const int4 c = __ldg(reinterpret_cast<const int4 *>(coors) + p);  // (b, z, y, x)
+      if (c.x >= 0 && c.x < batch && c.z >= 0 && c.z < ny && c.w >= 0 && c.w < nx) {
+        b = c.x;
+        ok = __ldg(table + static_cast<size_t>(b) * G + c.z * nx + c.w) == static_cast<int>(p);
+      }
+    }
+    float *row = dfeats + static_cast<size_t>(p) * C;
+    if (!ok) {
+      for (int ch = lane; ch < C; ch += 32) row[ch] = 0.f;
+      continue;
+    }
+    const float2 st = __ldg(stats + b), ms = __ldg(msum + b);
+    const float *x = feats + static_cast<size_t>(p) * C;
+    for (int ch = lane; ch < C; ch += 32) {
+      const float xh = (__ldg(x + ch) - st.x) * st.y;
+      row[ch] = st.y * ((row[ch] - ms.x) - xh * ms.y);
+    }
+  }
+}
+
 struct LnWs {
   double2 *partial;
   size_t bytes;
 };
+
+struct LnBwdWs {
+  double2 *partial;  // (batch, blocks of pass 1)
+  float2 *msum;      // (batch)
+  size_t bytes;
+  long long tasks;
+  int blocks, nchunks;
+};
+
+LnBwdWs carve_bwd(void *ws, int batch, int c_out, int G) {
+  Carver c(ws);
+  LnBwdWs w;
+  w.nchunks = c_out / kBwdCh;
+  w.tasks = static_cast<long long>((G + kBwdRun - 1) / kBwdRun) * w.nchunks;
+  w.blocks = static_cast<int>((w.tasks + kThreads / 32 - 1) / (kThreads / 32));
+  w.partial = c.take<double2>(static_cast<size_t>(batch) * w.blocks);
+  w.msum = c.take<float2>(static_cast<size_t>(batch));
+  w.bytes = c.off;
+  return w;
+}
 
 LnWs carve(void *ws, int batch) {
   Carver c(ws);
@@ -220,5 +430,53 @@ extern "C" int mbev_scatter_layernorm_forward(const float *feats, const int32_t 
   k_scatter_ln<<<blocks, kThreads, 0, stream>>>(feats, cell_table, stats, ln_weight, ln_bias, batch, c_out, G, runs,
                                                 csplit, out);
   MBEV_CHECK_LAUNCH();
+  return MBEV_OK;
+}
+
+extern "C" int mbev_scatter_layernorm_backward_supported(int batch, int c_out, int ny, int nx) {
+  if (batch < 1 || batch > MBEV_MAX_BATCH || c_out < kBwdCh || (c_out % kBwdCh) || ny < 1 || nx < 1) return 0;
+  const int64_t G = static_cast<int64_t>(ny) * nx;
+  if ((G & 3) || G * batch > 0x7fffffffLL) return 0;
+  return 1;
+}
+
+extern "C" int mbev_scatter_layernorm_backward_workspace_bytes(int batch, int c_out, int ny, int nx, size_t *bytes) {
+  if (!bytes) return MBEV_ERR_BAD_ARG;
+  if (!mbev_scatter_layernorm_backward_supported(batch, c_out, ny, nx)) return MBEV_ERR_UNSUPPORTED;
+  *bytes = carve_bwd(nullptr, batch, c_out, ny * nx).bytes;
+  return MBEV_OK;
+}
+
+extern "C" int mbev_scatter_layernorm_backward(const float *dout, const float *feats, const int32_t *cell_table,
+                                               const int32_t *coors, const int32_t *num_pillars_dev,
+                                               int64_t pillar_capacity, int batch, int c_out, int ny, int nx,
+                                               const float *ln_weight, const float *stats, float *dfeats,
+                                               float *dweight, float *dbias, void *workspace, size_t workspace_bytes,
+                                               void *stream_) {
+  if (!dout || !cell_table || !num_pillars_dev || !ln_weight || !stats || !dweight || !dbias || !workspace)
+    return MBEV_ERR_BAD_ARG;
+  if (pillar_capacity < 0 || (pillar_capacity > 0 && (!feats || !coors || !dfeats))) return MBEV_ERR_BAD_ARG;
+  if (!mbev_scatter_layernorm_backward_supported(batch, c_out, ny, nx)) return MBEV_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(feats) | reinterpret_cast<uintptr_t>(ln_weight) |
+       reinterpret_cast<uintptr_t>(dfeats) | reinterpret_cast<uintptr_t>(dweight) | reinterpret_cast<uintptr_t>(dbias) |
+       reinterpret_cast<uintptr_t>(coors) | reinterpret_cast<uintptr_t>(cell_table)) & 15)
+    return MBEV_ERR_UNSUPPORTED;
+  const int G = ny * nx;
+  const LnBwdWs w = carve_bwd(workspace, batch, c_out, G);
+  if (workspace_bytes < w.bytes) return MBEV_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const float2 *st = reinterpret_cast<const float2 *>(stats);
+  k_ln_bwd_dense<<<w.blocks, kThreads, 0, stream>>>(dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks,
+                                                   w.tasks, dweight, dbias, dfeats, w.partial);
+  MBEV_CHECK_LAUNCH();
+  k_ln_bwd_finalize<<<batch, kThreads, 0, stream>>>(w.partial, w.blocks, static_cast<double>(c_out) * G, w.msum);
+  MBEV_CHECK_LAUNCH();
+  if (pillar_capacity > 0) {
+    const int64_t want = (pillar_capacity + kThreads / 32 - 1) / (kThreads / 32);
+    const int blocks = static_cast<int>(std::min<int64_t>(want, kNumSMs * 16));
+    k_ln_bwd_feats<<<blocks, kThreads, 0, stream>>>(feats, coors, num_pillars_dev, cell_table, st, w.msum,
+                                                   pillar_capacity, batch, c_out, ny, nx, dfeats);
+    MBEV_CHECK_LAUNCH();
+  }
   return MBEV_OK;
 }

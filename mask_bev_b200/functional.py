@@ -364,6 +364,39 @@ def scatter_layernorm_forward(feats: torch.Tensor, cell_table: torch.Tensor, pil
     return out, stats
 
 
+def _aligned16(t: torch.Tensor) -> torch.Tensor:
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
+def scatter_layernorm_backward_supported(batch: int, C: int, ny: int, nx: int) -> bool:
+    return bool(_lib.load().mbev_scatter_layernorm_backward_supported(batch, C, ny, nx))
+
+
+def scatter_layernorm_backward(dout: torch.Tensor, feats: torch.Tensor, cell_table: torch.Tensor, coors: torch.Tensor,
+                               num_pillars_dev: torch.Tensor, weight: torch.Tensor, stats: torch.Tensor):
+    """Backward of scatter_layernorm_forward: (dfeats (rows, C), dweight (C, ny, nx), dbias (C, ny, nx)).
+    `stats` is the forward's (B, 2) mean / rstd; `feats` the forward's input rows."""
+    lib = _lib.load()
+    _need_cuda(dout, "grad_output")
+    dev = dout.device
+    B, C, ny, nx = dout.shape
+    dout, feats, weight = _aligned16(_f32c(dout)), _aligned16(_f32c(feats)), _aligned16(_f32c(weight))
+    rows = feats.shape[0]
+    nbytes = ctypes.c_size_t()
+    check(lib.mbev_scatter_layernorm_backward_workspace_bytes(B, C, ny, nx, ctypes.byref(nbytes)),
+          "scatter_layernorm_backward_workspace_bytes")
+    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
+    dfeats = torch.empty((rows, C), dtype=torch.float32, device=dev)
+    dweight = torch.empty((C, ny, nx), dtype=torch.float32, device=dev)
+    dbias = torch.empty((C, ny, nx), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.mbev_scatter_layernorm_backward(ptr(dout), ptr(feats), ptr(cell_table), ptr(coors),
+                                                  ptr(num_pillars_dev), rows, B, C, ny, nx, ptr(weight),
+                                                  ptr(stats), ptr(dfeats), ptr(dweight), ptr(dbias), ptr(ws),
+                                                  ws.numel(), _stream()), "scatter_layernorm_backward")
+    return dfeats, dweight, dbias
+
+
 def scatter_backward(dcanvas: torch.Tensor, cell_table: torch.Tensor, num_rows: int) -> torch.Tensor:
     lib = _lib.load()
     B, C, ny, nx = dcanvas.shape

@@ -1,6 +1,7 @@
 """`PointPillarsScatter` — drop-in for mmdet3d==1.1.0's middle encoder as MaskBEV builds and calls it
 (/root/reference/mask_bev/models/encoders/mask_bev_encoders.py:74, :122-123). Same constructor and forward;
-the canvas is written once by K3 (csrc/scatter.cu) and the backward is the K3' gather. No CPU path.
+the canvas is written once by K3 (csrc/scatter.cu) and the backward is the K3' gather; the LayerNorm that follows
+the scatter in MaskBevEncoder.forward is fused into both directions (csrc/layernorm.cu). No CPU path.
 """
 from __future__ import annotations
 
@@ -30,6 +31,45 @@ def scatter_with_table(feats: torch.Tensor, cell_table: torch.Tensor, batch: int
     if feats.requires_grad and torch.is_grad_enabled():
         return _ScatterFunction.apply(feats, cell_table, batch, ny, nx)
     return F_.scatter_forward(feats.detach().to(torch.float32).contiguous(), cell_table, batch, ny, nx)
+
+
+class _ScatterLayerNormFunction(torch.autograd.Function):
+    """canvas = LayerNorm([C, ny, nx])(scatter(feats)) as ONE pass forward (K3+LN) and one streaming pass over the
+    incoming gradient backward (mask_bev_encoders.py:91-92 and its autograd)."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, cell_table, pillar_base, coors, batch, ny, nx, eps):
+        f = feats.detach().to(torch.float32).contiguous()
+        res = F_.scatter_layernorm_forward(f, cell_table, pillar_base, batch, ny, nx, weight.detach(), bias.detach(),
+                                           eps)
+        if res is None:
+            raise MbevError("fused scatter+LayerNorm does not support this shape (check layernorm_autograd_supported)")
+        out, stats = res
+        ctx.save_for_backward(f, weight, cell_table, pillar_base, coors, stats)
+        ctx.batch = batch
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        f, weight, cell_table, pillar_base, coors, stats = ctx.saved_tensors
+        dfeats, dweight, dbias = F_.scatter_layernorm_backward(dout, f, cell_table, coors, pillar_base[ctx.batch:],
+                                                               weight.detach(), stats)
+        return (dfeats, dweight.to(weight.dtype), dbias.to(weight.dtype)) + (None,) * 7
+
+
+def scatter_layernorm_with_table(feats: torch.Tensor, ln: nn.LayerNorm, cell_table: torch.Tensor,
+                                 pillar_base: torch.Tensor, coors: torch.Tensor, batch: int, ny: int, nx: int):
+    """Autograd-enabled fused scatter + LayerNorm; None when the shape does not fit the fused kernels (the caller then
+    runs K3 followed by torch's LayerNorm)."""
+    C = feats.shape[1]
+    if not ln.elementwise_affine or ln.weight is None or ln.bias is None:
+        return None
+    if tuple(ln.weight.shape) != (C, ny, nx) or ln.weight.dtype != torch.float32:
+        return None
+    if (ny * nx) % 4 or not F_.scatter_layernorm_backward_supported(batch, C, ny, nx):
+        return None
+    return _ScatterLayerNormFunction.apply(feats, ln.weight, ln.bias, cell_table, pillar_base, coors, batch, ny, nx,
+                                           ln.eps)
 
 
 class PointPillarsScatter(nn.Module):

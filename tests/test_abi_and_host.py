@@ -74,6 +74,17 @@ def test_capability_probes_without_gpu():
     n = ctypes.c_size_t()
     assert lib.mbev_scatter_layernorm_workspace_bytes(16, ctypes.byref(n)) == 0 and n.value >= 16 * 64 * 16
     assert lib.mbev_scatter_layernorm_workspace_bytes(0, ctypes.byref(n)) == -1
+    # backward of K3 + LayerNorm: channels in groups of 4, plane a multiple of 4 cells
+    assert lib.mbev_scatter_layernorm_backward_supported(16, 128, 800, 800) == 1
+    assert lib.mbev_scatter_layernorm_backward_supported(2, 6, 16, 16) == 0
+    assert lib.mbev_scatter_layernorm_backward_supported(2, 64, 25, 25) == 0
+    assert lib.mbev_scatter_layernorm_backward_supported(129, 64, 16, 16) == 0
+    assert lib.mbev_scatter_layernorm_backward_workspace_bytes(16, 128, 800, 800, ctypes.byref(n)) == 0
+    assert n.value >= 16 * (5000 * 32 // 8) * 16   # one fp64 (S1, S2) pair per frame and CTA of the streaming pass
+    assert lib.mbev_scatter_layernorm_backward_workspace_bytes(2, 6, 16, 16, ctypes.byref(n)) == -2
+    st = lib.mbev_scatter_layernorm_backward(null, null, null, null, null, 0, 1, 4, 8, 8, null, null, null, null, null,
+                                             null, 0, null)
+    assert st == -1
     # K2 + K3 fused kernel: tcgen05 stack, T <= 32, plane a multiple of 4 cells and at least one strip
     enc = M.MaskBevEncoder(**encoder_kwargs("kitti_b16"))
     cfg = enc._voxel_encoder._config()
