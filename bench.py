@@ -451,7 +451,7 @@ def run_ours(args):
                                                    "written once, dfeats in pillar space"})
         del out_ln
     dom = max(("K1_voxelize", "K2_pfn", "K3_scatter"), key=lambda k: kernels[k]["ms"])
-    roof = {"kernel": "K3_scatter (k_scatter_warp)", "bound": "hbm", "achieved": kernels["K3_scatter"]["gbs"], "peak": peak,
+    roof = {"kernel": "K3_scatter (k_scatter_run<2>)", "bound": "hbm", "achieved": kernels["K3_scatter"]["gbs"], "peak": peak,
             "unit": "GB/s", "frac": kernels["K3_scatter"]["frac_hbm"], "traffic": None, "peak_source": peak_src,
             "launch_ms": t_sc, "dominant_by_time": dom,
             "share_of_step": t_sc / (t_vox + t_pfn + t_sc)}

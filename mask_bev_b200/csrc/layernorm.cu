@@ -14,6 +14,7 @@
 // two per-frame sums, and finishes dfeats in the compact pillar space.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -286,6 +287,177 @@ k_ln_bwd_dense(const float *__restrict__ dy, const float *__restrict__ feats, co
   }
 }
 
+// Same pass with dy and the table rows staged through shared memory by cp.async (default; MBEV_LN_BWD=0 selects the
+// register-prefetch form above). ncu on k_ln_bwd_dense (profiles/r1g_lnbwd_full.txt): 16 warps per SM at 128 registers
+// with ONE frame (2 KB per warp) requested ahead = 48 % of the DRAM peak, long-scoreboard 5 per issue. Here every lane
+// copies its own 16-byte pieces of the next kStages-1 frames into its own ring slots (no cross-thread sharing: the
+// only synchronisation is cp.async.wait_group), so the bytes in flight no longer cost registers; the feature rows of
+// frame b+1 are requested while frame b is processed, xh is one FMA, a run without any pillar in a frame skips the
+// feature path warp-uniformly, and the per-frame sums are folded in fp32 inside the warp (512 terms), fp64 above it.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int kStages>
+__global__ void __launch_bounds__(kThreads, 2)
+k_ln_bwd_dense_async(const float *__restrict__ dy, const float *__restrict__ feats, const int *__restrict__ table,
+                     const float2 *__restrict__ stats, const float *__restrict__ lnw, const int batch, const int C,
+                     const int G, const int nchunks, const long long tasks, float *__restrict__ dw,
+                     float *__restrict__ db, float *__restrict__ gfeat, double2 *__restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *ring = reinterpret_cast<float4 *>(smem_raw);  // [kStages][kBwdCh + 1][kThreads]; plane kBwdCh = table row
+  double2 *s_part = reinterpret_cast<double2 *>(smem_raw + sizeof(float4) * kStages * (kBwdCh + 1) * kThreads);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long task = static_cast<long long>(blockIdx.x) * (kThreads / 32) + warp;
+  const int run = static_cast<int>(task / nchunks);
+  const int ch0 = static_cast<int>(task - static_cast<long long>(run) * nchunks) * kBwdCh;
+  const int g0 = run * kBwdRun + 4 * lane;
+  const bool inb = task < tasks && g0 < G;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w[kBwdCh], aw[kBwdCh], ab[kBwdCh];
+#pragma unroll
+  for (int k = 0; k < kBwdCh; ++k) {
+    w[k] = inb ? __ldg(reinterpret_cast<const float4 *>(lnw + static_cast<size_t>(ch0 + k) * G + g0)) : z;
+    aw[k] = ab[k] = z;
+  }
+  auto slot = [&](int stage, int k) { return ring + (stage * (kBwdCh + 1) + k) * kThreads + tid; };
+  const size_t frame_stride = static_cast<size_t>(C) * G;
+  const float *dy_lane = dy + static_cast<size_t>(ch0) * G + g0;
+  auto issue = [&](int b) {
+    const int st = b % kStages;
+    cp_async16(slot(st, kBwdCh), table + static_cast<size_t>(b) * G + g0);
+    const float *src = dy_lane + static_cast<size_t>(b) * frame_stride;
+#pragma unroll
+    for (int k = 0; k < kBwdCh; ++k) cp_async16(slot(st, k), src + static_cast<size_t>(k) * G);
+  };
+  auto features = [&](const int4 &pid, float4 (&f)[4]) {  // f[cell] = the 4 channels of that cell's pillar
+    f[0] = pid.x >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.x) * C + ch0)) : z;
+    f[1] = pid.y >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.y) * C + ch0)) : z;
+    f[2] = pid.z >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.z) * C + ch0)) : z;
+    f[3] = pid.w >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.w) * C + ch0)) : z;
+  };
+#pragma unroll
+  for (int s0 = 0; s0 < kStages - 1; ++s0) {
+    if (inb && s0 < batch) issue(s0);
+    cp_async_commit();
+  }
+  cp_async_wait<kStages - 2>();  // frame 0 has landed
+  int4 pid_n = make_int4(-1, -1, -1, -1);
+  float4 f_n[4] = {z, z, z, z};
+  bool occ_n = false;  // some cell of this warp's run holds a pillar in the frame
+  {
+    if (inb) pid_n = *reinterpret_cast<const int4 *>(slot(0, kBwdCh));
+    occ_n = __any_sync(0xffffffffu, (pid_n.x & pid_n.y & pid_n.z & pid_n.w) >= 0);
+    if (occ_n) features(pid_n, f_n);
+  }
+  for (int b = 0; b < batch; ++b) {
+    if (inb && b + kStages - 1 < batch) issue(b + kStages - 1);
+    cp_async_commit();
+    cp_async_wait<kStages - 2>();  // frames <= b + 1 have landed
+    const int4 pid = pid_n;
+    const bool occ = occ_n;
+    float4 f[4] = {f_n[0], f_n[1], f_n[2], f_n[3]};
+    if (b + 1 < batch) {  // warp-uniform
+      pid_n = make_int4(-1, -1, -1, -1);
+      if (inb) pid_n = *reinterpret_cast<const int4 *>(slot((b + 1) % kStages, kBwdCh));
+      occ_n = __any_sync(0xffffffffu, (pid_n.x & pid_n.y & pid_n.z & pid_n.w) >= 0);
+      if (occ_n) features(pid_n, f_n);
+    }
+    float s1 = 0.f, s2 = 0.f;
+    if (inb) {
+      const float2 st = __ldg(stats + b);
+      const float rstd = st.y, e = -st.x * st.y;  // xh = x * rstd + e; an empty cell has xh = e
+      const int stg = b % kStages;
+      if (!occ) {
+#pragma unroll
+        for (int k = 0; k < kBwdCh; ++k) {
+          const float4 d = *slot(stg, k);
+          ab[k].x += d.x;
+          ab[k].y += d.y;
+          ab[k].z += d.z;
+          ab[k].w += d.w;
+          aw[k].x = fmaf(d.x, e, aw[k].x);
+          aw[k].y = fmaf(d.y, e, aw[k].y);
+          aw[k].z = fmaf(d.z, e, aw[k].z);
+          aw[k].w = fmaf(d.w, e, aw[k].w);
+          s1 += fmaf(d.x, w[k].x, d.y * w[k].y) + fmaf(d.z, w[k].z, d.w * w[k].w);
+        }
+        s2 = e * s1;
+      } else {
+        const float xk[kBwdCh][4] = {{f[0].x, f[1].x, f[2].x, f[3].x},
+                                     {f[0].y, f[1].y, f[2].y, f[3].y},
+                                     {f[0].z, f[1].z, f[2].z, f[3].z},
+                                     {f[0].w, f[1].w, f[2].w, f[3].w}};  // xk[channel][cell]
+        float4 g[kBwdCh];
+#pragma unroll
+        for (int k = 0; k < kBwdCh; ++k) {
+          const float4 d = *slot(stg, k);
+          float4 xh;
+          xh.x = fmaf(xk[k][0], rstd, e);
+          xh.y = fmaf(xk[k][1], rstd, e);
+          xh.z = fmaf(xk[k][2], rstd, e);
+          xh.w = fmaf(xk[k][3], rstd, e);
+          ab[k].x += d.x;
+          ab[k].y += d.y;
+          ab[k].z += d.z;
+          ab[k].w += d.w;
+          aw[k].x = fmaf(d.x, xh.x, aw[k].x);
+          aw[k].y = fmaf(d.y, xh.y, aw[k].y);
+          aw[k].z = fmaf(d.z, xh.z, aw[k].z);
+          aw[k].w = fmaf(d.w, xh.w, aw[k].w);
+          g[k].x = d.x * w[k].x;
+          g[k].y = d.y * w[k].y;
+          g[k].z = d.z * w[k].z;
+          g[k].w = d.w * w[k].w;
+          s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
+          s2 += fmaf(g[k].x, xh.x, g[k].y * xh.y) + fmaf(g[k].z, xh.z, g[k].w * xh.w);
+        }
+        if (pid.x >= 0)
+          *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.x) * C + ch0) = make_float4(g[0].x, g[1].x, g[2].x, g[3].x);
+        if (pid.y >= 0)
+          *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.y) * C + ch0) = make_float4(g[0].y, g[1].y, g[2].y, g[3].y);
+        if (pid.z >= 0)
+          *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.z) * C + ch0) = make_float4(g[0].z, g[1].z, g[2].z, g[3].z);
+        if (pid.w >= 0)
+          *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.w) * C + ch0) = make_float4(g[0].w, g[1].w, g[2].w, g[3].w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) s_part[b * (kThreads / 32) + warp] = make_double2(static_cast<double>(s1), static_cast<double>(s2));
+  }
+  if (inb) {
+#pragma unroll
+    for (int k = 0; k < kBwdCh; ++k) {
+      st_global_v4_stream(dw + static_cast<size_t>(ch0 + k) * G + g0, aw[k]);
+      st_global_v4_stream(db + static_cast<size_t>(ch0 + k) * G + g0, ab[k]);
+    }
+  }
+  __syncthreads();
+  for (int b = tid; b < batch; b += kThreads) {
+    double a = 0.0, q = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kThreads / 32; ++wv) {
+      a += s_part[b * (kThreads / 32) + wv].x;
+      q += s_part[b * (kThreads / 32) + wv].y;
+    }
+    partial[static_cast<size_t>(b) * gridDim.x + blockIdx.x] = make_double2(a, q);
+  }
+}
+
+inline size_t bwd_async_smem(int stages, int batch) {
+  return sizeof(float4) * stages * (kBwdCh + 1) * kThreads + sizeof(double2) * static_cast<size_t>(batch) * (kThreads / 32);
+}
+
 // msum[b] = (S1_b / M, S2_b / M): one CTA per frame, fixed-order strided sums + shared-memory tree
 __global__ void __launch_bounds__(kThreads)
 k_ln_bwd_finalize(const double2 *__restrict__ partial, const int nblocks, const double count,
@@ -466,8 +638,28 @@ extern "C" int mbev_scatter_layernorm_backward(const float *dout, const float *f
   if (workspace_bytes < w.bytes) return MBEV_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const float2 *st = reinterpret_cast<const float2 *>(stats);
-  k_ln_bwd_dense<<<w.blocks, kThreads, 0, stream>>>(dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks,
-                                                   w.tasks, dweight, dbias, dfeats, w.partial);
+  // 1 (default): dy / table rows staged by cp.async, 5 ring stages (4 when batch > 64: two CTAs must fit an SM);
+  // 0: register prefetch of one frame
+  static const int variant = getenv("MBEV_LN_BWD") ? atoi(getenv("MBEV_LN_BWD")) : 1;
+  if (variant == 0) {
+    k_ln_bwd_dense<<<w.blocks, kThreads, 0, stream>>>(dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks,
+                                                     w.tasks, dweight, dbias, dfeats, w.partial);
+  } else {
+    static bool attr_done = false;  // idempotent; a benign race sets the same values twice
+    if (!attr_done) {
+      MBEV_CUDA(cudaFuncSetAttribute(k_ln_bwd_dense_async<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(bwd_async_smem(5, 64))));
+      MBEV_CUDA(cudaFuncSetAttribute(k_ln_bwd_dense_async<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(bwd_async_smem(4, MBEV_MAX_BATCH))));
+      attr_done = true;
+    }
+    if (batch <= 64)
+      k_ln_bwd_dense_async<5><<<w.blocks, kThreads, bwd_async_smem(5, batch), stream>>>(
+          dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks, w.tasks, dweight, dbias, dfeats, w.partial);
+    else
+      k_ln_bwd_dense_async<4><<<w.blocks, kThreads, bwd_async_smem(4, batch), stream>>>(
+          dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks, w.tasks, dweight, dbias, dfeats, w.partial);
+  }
   MBEV_CHECK_LAUNCH();
   k_ln_bwd_finalize<<<batch, kThreads, 0, stream>>>(w.partial, w.blocks, static_cast<double>(c_out) * G, w.msum);
   MBEV_CHECK_LAUNCH();

@@ -51,6 +51,8 @@ def _float64_reference(coors, feats, weight, bias, dout, B, C, ny, nx, P, eps):
     (1, 4, 8, 8, (20,), 3),                   # one channel chunk, G < one run
     (5, 12, 36, 36, (100, 200, 1, 1296, 40), 0),  # 3 chunks per run (CTA tasks straddle runs); a FULL frame
     (16, 32, 64, 64, tuple(200 + 10 * i for i in range(16)), 0),
+    (70, 8, 16, 16, tuple(3 + (i % 5) for i in range(70)), 0),   # batch > 64: the 4-stage ring
+    (2, 16, 20, 20, (30, 50), 0),             # fewer frames than ring stages
 ])
 def test_scatter_layernorm_backward_matches_float64_autograd(B, C, ny, nx, counts, extra):
     from mask_bev_b200 import functional as F_
