@@ -312,7 +312,7 @@ k_ln_bwd_dense_async(const float *__restrict__ dy, const float *__restrict__ fea
                      float *__restrict__ db, float *__restrict__ gfeat, double2 *__restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *ring = reinterpret_cast<float4 *>(smem_raw);  // [kStages][kBwdCh + 1][kThreads]; plane kBwdCh = table row
-  double2 *s_part = reinterpret_cast<double2 *>(smem_raw + sizeof(float4) * kStages * (kBwdCh + 1) * kThreads);
+  double *s_sum = reinterpret_cast<double *>(smem_raw + sizeof(float4) * kStages * (kBwdCh + 1) * kThreads);  // [batch][warp][2]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long task = static_cast<long long>(blockIdx.x) * (kThreads / 32) + warp;
   const int run = static_cast<int>(task / nchunks);
@@ -356,14 +356,17 @@ k_ln_bwd_dense_async(const float *__restrict__ dy, const float *__restrict__ fea
     occ_n = __any_sync(0xffffffffu, (pid_n.x & pid_n.y & pid_n.z & pid_n.w) >= 0);
     if (occ_n) features(pid_n, f_n);
   }
+  float2 st_n = __ldg(stats);
   for (int b = 0; b < batch; ++b) {
     if (inb && b + kStages - 1 < batch) issue(b + kStages - 1);
     cp_async_commit();
     cp_async_wait<kStages - 2>();  // frames <= b + 1 have landed
     const int4 pid = pid_n;
     const bool occ = occ_n;
+    const float2 st = st_n;
     float4 f[4] = {f_n[0], f_n[1], f_n[2], f_n[3]};
     if (b + 1 < batch) {  // warp-uniform
+      st_n = __ldg(stats + b + 1);
       pid_n = make_int4(-1, -1, -1, -1);
       if (inb) pid_n = *reinterpret_cast<const int4 *>(slot((b + 1) % kStages, kBwdCh));
       occ_n = __any_sync(0xffffffffu, (pid_n.x & pid_n.y & pid_n.z & pid_n.w) >= 0);
@@ -371,7 +374,6 @@ k_ln_bwd_dense_async(const float *__restrict__ dy, const float *__restrict__ fea
     }
     float s1 = 0.f, s2 = 0.f;
     if (inb) {
-      const float2 st = __ldg(stats + b);
       const float rstd = st.y, e = -st.x * st.y;  // xh = x * rstd + e; an empty cell has xh = e
       const int stg = b % kStages;
       if (!occ) {
@@ -428,12 +430,13 @@ k_ln_bwd_dense_async(const float *__restrict__ dy, const float *__restrict__ fea
           *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.w) * C + ch0) = make_float4(g[0].w, g[1].w, g[2].w, g[3].w);
       }
     }
+    // both sums in one butterfly: the lower half-warp keeps s1 and hands s2 over, the upper half the other way round;
+    // lane 0 ends up with S1, lane 16 with S2 (fixed order)
+    const bool upper = lane & 16;
+    float v = (upper ? s2 : s1) + __shfl_xor_sync(0xffffffffu, upper ? s1 : s2, 16);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) s_part[b * (kThreads / 32) + warp] = make_double2(static_cast<double>(s1), static_cast<double>(s2));
+    for (int o = 8; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((lane & 15) == 0) s_sum[(b * (kThreads / 32) + warp) * 2 + (lane >> 4)] = static_cast<double>(v);
   }
   if (inb) {
 #pragma unroll
@@ -447,8 +450,8 @@ k_ln_bwd_dense_async(const float *__restrict__ dy, const float *__restrict__ fea
     double a = 0.0, q = 0.0;
 #pragma unroll
     for (int wv = 0; wv < kThreads / 32; ++wv) {
-      a += s_part[b * (kThreads / 32) + wv].x;
-      q += s_part[b * (kThreads / 32) + wv].y;
+      a += s_sum[(b * (kThreads / 32) + wv) * 2];
+      q += s_sum[(b * (kThreads / 32) + wv) * 2 + 1];
     }
     partial[static_cast<size_t>(b) * gridDim.x + blockIdx.x] = make_double2(a, q);
   }
