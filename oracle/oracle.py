@@ -497,3 +497,17 @@ class MaskBevEncoderOracle:
         if self.layer_norm is not None:
             img = self.layer_norm(img)
         return img
+
+    def forward_autograd(self, point_clouds):
+        """The same forward with the scatter written in torch (``canvas[b, :, y, x] = feats[p]``, upstream's
+        ``canvas[:, indices] = voxels.t()`` per frame), so that autograd reaches the PFN and LayerNorm parameters — the
+        reference trains through exactly this graph. Returns the same values as ``forward``."""
+        torch = _torch()
+        voxels, num_points, coors, _ = self.voxelize(point_clouds)
+        feats = self.encode(voxels, num_points, coors)
+        c = torch.from_numpy(np.ascontiguousarray(coors)).long()
+        img = torch.zeros((len(point_clouds), self.C_out, self.geo["ny"], self.geo["nx"]), dtype=feats.dtype)
+        img[c[:, 0], :, c[:, 2], c[:, 3]] = feats
+        if self.layer_norm is not None:
+            img = self.layer_norm(img)
+        return img

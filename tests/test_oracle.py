@@ -224,3 +224,25 @@ def test_golden_decoration_regenerates_from_the_reference_when_present():
                                y_offset=float(vs[1]) / 2 + float(pcr[1]))
     res = fwd(me, torch.from_numpy(g["voxels"].copy()), torch.from_numpy(g["num_points"]), torch.from_numpy(g["coors"]))
     assert np.array_equal(res.numpy(), g["out_legacy1_dist1"])
+
+
+def test_forward_autograd_equals_forward_and_reaches_every_parameter():
+    """The differentiable restatement (torch scatter + LayerNorm) returns the numpy-scatter forward bit for bit, and
+    its autograd reaches every PFN and LayerNorm parameter (the graph the reference trains through)."""
+    import torch
+    from mask_bev_b200.synthetic import gen_frame
+    orc = O.MaskBevEncoderOracle(feat_channels=[16, 32], x_range=(-40, 40), y_range=(-40, 40), z_range=(-20, 20),
+                                 voxel_size_x=0.8, voxel_size_y=0.8, voxel_size_z=40, max_num_points=16,
+                                 pc_point_dim=4, with_distance=True, layer_norm=True)
+    O.randomise_pfn(orc.pfn, seed=3)
+    orc.pfn.eval()
+    frames = [gen_frame(3000, 4, 1), np.full((5, 4), 1000.0, np.float32), gen_frame(2000, 4, 2)]
+    with torch.no_grad():
+        a = orc.forward(frames)
+    b = orc.forward_autograd(frames)
+    assert torch.equal(a, b.detach())
+    b.sum().backward()
+    params = list(orc.pfn.parameters()) + list(orc.layer_norm.parameters())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
+    # LayerNorm: dbias of sum() is the batch size everywhere
+    assert torch.equal(orc.layer_norm.bias.grad, torch.full_like(orc.layer_norm.bias, float(len(frames))))
