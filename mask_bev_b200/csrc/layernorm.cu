@@ -523,6 +523,94 @@ k_ln_bwd_feats(const float *__restrict__ feats, const int *__restrict__ coors, c
   }
 }
 
+// ---- K3+LN forward, frame-walking form (OPT-IN: MBEV_LN_FWD=2; NOT yet run on a B200 — written at the end of round 1
+// after the GPU budget was spent; round 2 validates it with `MBEV_LN_FWD=2 pytest tests/test_gpu_layernorm.py` and
+// times it with bench.py before it may become the default). Same task shape as the backward's streaming pass: a warp
+// owns (128 cells, 4 channels) and walks the B frames with weight and bias IN REGISTERS, so they are read from HBM once
+// and never again from L2 (k_scatter_ln re-reads them from L2 for every frame: 15 x 0.66 GB of L2 -> SM traffic per
+// kitti_b16 batch, and two 16-byte loads per plane and group in its inner loop). Table rows are requested two frames
+// ahead, the feature rows (one 16-byte load per occupied cell) one frame ahead; a (run, frame) without a pillar writes
+// fma(e_b, w, bias) warp-uniformly. The arithmetic per element is the very expression of k_scatter_ln, so the two
+// forms agree bit for bit.
+__global__ void __launch_bounds__(kThreads, 2)
+k_scatter_ln_frames(const float *__restrict__ feats, const int *__restrict__ table, const float2 *__restrict__ stats,
+                    const float *__restrict__ lnw, const float *__restrict__ lnb, const int batch, const int C,
+                    const int G, const int nchunks, const long long tasks, float *__restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long task = static_cast<long long>(blockIdx.x) * (kThreads / 32) + warp;
+  const int run = static_cast<int>(task / nchunks);
+  const int ch0 = static_cast<int>(task - static_cast<long long>(run) * nchunks) * kBwdCh;
+  const int g0 = run * kBwdRun + 4 * lane;
+  const bool inb = task < tasks && g0 < G;  // G % 4 == 0: a lane's four cells are in or out together
+  if (task >= tasks) return;                // warp-uniform (no block-level synchronisation in this kernel)
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int4 none = make_int4(-1, -1, -1, -1);
+  float4 w[kBwdCh], bi[kBwdCh];
+#pragma unroll
+  for (int k = 0; k < kBwdCh; ++k) {
+    w[k] = inb ? __ldg(reinterpret_cast<const float4 *>(lnw + static_cast<size_t>(ch0 + k) * G + g0)) : z;
+    bi[k] = inb ? __ldg(reinterpret_cast<const float4 *>(lnb + static_cast<size_t>(ch0 + k) * G + g0)) : z;
+  }
+  auto row = [&](int b) {
+    return (inb && b < batch) ? __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g0)) : none;
+  };
+  auto features = [&](const int4 &pid, float4 (&f)[4]) {  // f[cell] = the 4 channels of that cell's pillar
+    f[0] = pid.x >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.x) * C + ch0)) : z;
+    f[1] = pid.y >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.y) * C + ch0)) : z;
+    f[2] = pid.z >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.z) * C + ch0)) : z;
+    f[3] = pid.w >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.w) * C + ch0)) : z;
+  };
+  int4 pid_n = row(0), pid_nn = row(1);
+  float4 f_n[4] = {z, z, z, z};
+  bool occ_n = __any_sync(0xffffffffu, (pid_n.x & pid_n.y & pid_n.z & pid_n.w) >= 0);
+  if (occ_n) features(pid_n, f_n);
+  float2 st_n = __ldg(stats);
+  float *o = out + static_cast<size_t>(ch0) * G + g0;
+  const size_t frame_stride = static_cast<size_t>(C) * G;
+  for (int b = 0; b < batch; ++b) {
+    const bool occ = occ_n;
+    const float2 st = st_n;
+    float4 f[4] = {f_n[0], f_n[1], f_n[2], f_n[3]};
+    if (b + 1 < batch) {  // warp-uniform
+      st_n = __ldg(stats + b + 1);
+      pid_n = pid_nn;
+      pid_nn = row(b + 2);
+      occ_n = __any_sync(0xffffffffu, (pid_n.x & pid_n.y & pid_n.z & pid_n.w) >= 0);
+      if (occ_n) features(pid_n, f_n);
+    }
+    if (inb) {
+      const float mean = st.x, rstd = st.y;
+      float *ob = o + static_cast<size_t>(b) * frame_stride;
+      if (!occ) {
+        const float e = __fmul_rn(__fsub_rn(0.f, mean), rstd);  // ((0 - mean) * rstd), the general expression at x = 0
+#pragma unroll
+        for (int k = 0; k < kBwdCh; ++k) {
+          float4 y;
+          y.x = __fmaf_rn(e, w[k].x, bi[k].x);
+          y.y = __fmaf_rn(e, w[k].y, bi[k].y);
+          y.z = __fmaf_rn(e, w[k].z, bi[k].z);
+          y.w = __fmaf_rn(e, w[k].w, bi[k].w);
+          st_global_v4_stream_nc(ob + static_cast<size_t>(k) * G, y);
+        }
+      } else {
+        const float xk[kBwdCh][4] = {{f[0].x, f[1].x, f[2].x, f[3].x},
+                                     {f[0].y, f[1].y, f[2].y, f[3].y},
+                                     {f[0].z, f[1].z, f[2].z, f[3].z},
+                                     {f[0].w, f[1].w, f[2].w, f[3].w}};  // xk[channel][cell]
+#pragma unroll
+        for (int k = 0; k < kBwdCh; ++k) {
+          float4 y;  // ((x - mean) * rstd) * w + b, the operation order of torch's LayerNorm kernel
+          y.x = __fmaf_rn(__fmul_rn(__fsub_rn(xk[k][0], mean), rstd), w[k].x, bi[k].x);
+          y.y = __fmaf_rn(__fmul_rn(__fsub_rn(xk[k][1], mean), rstd), w[k].y, bi[k].y);
+          y.z = __fmaf_rn(__fmul_rn(__fsub_rn(xk[k][2], mean), rstd), w[k].z, bi[k].z);
+          y.w = __fmaf_rn(__fmul_rn(__fsub_rn(xk[k][3], mean), rstd), w[k].w, bi[k].w);
+          st_global_v4_stream_nc(ob + static_cast<size_t>(k) * G, y);
+        }
+      }
+    }
+  }
+}
+
 struct LnWs {
   double2 *partial;
   size_t bytes;
@@ -594,6 +682,18 @@ extern "C" int mbev_scatter_layernorm_forward(const float *feats, const int32_t 
   k_ln_finalize<<<(batch + 127) / 128, 128, 0, stream>>>(w.partial, batch, static_cast<double>(c_out) * G,
                                                         static_cast<double>(eps), stats);
   MBEV_CHECK_LAUNCH();
+  // 1 (default): k_scatter_ln, a warp per (256-cell run, channel chunk, frame); 2: k_scatter_ln_frames, a warp per
+  // (128 cells, 4 channels) walking the frames — opt-in until it has been run and timed on a B200 (see its comment)
+  static const int fwd_variant = getenv("MBEV_LN_FWD") ? atoi(getenv("MBEV_LN_FWD")) : 1;
+  if (fwd_variant == 2 && c_out % kBwdCh == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
+    const int nchunks = c_out / kBwdCh;
+    const long long ftasks = static_cast<long long>((G + kBwdRun - 1) / kBwdRun) * nchunks;
+    const int fblocks = static_cast<int>((ftasks + kThreads / 32 - 1) / (kThreads / 32));
+    k_scatter_ln_frames<<<fblocks, kThreads, 0, stream>>>(feats, cell_table, stats, ln_weight, ln_bias, batch, c_out, G,
+                                                         nchunks, ftasks, out);
+    MBEV_CHECK_LAUNCH();
+    return MBEV_OK;
+  }
   const int runs = (G + kRun - 1) / kRun;
   const int want_warps = kNumSMs * 3 * (kThreads / 32) * 4;  // several tasks per resident warp (tail balance)
   int csplit = 1;

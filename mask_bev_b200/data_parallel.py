@@ -11,7 +11,7 @@ parameters, over `torch.distributed` (NCCL over NVLink / NVSwitch on GPUs, gloo 
   enough to run at link bandwidth on their own, so they are reduced in place without a staging copy;
 * all collectives are issued asynchronously before the first wait, so NCCL pipelines them on its own stream.
 
-Train-mode BatchNorm statistics stay per rank (the reference has no SyncBN), so a sharded step equals the oracle run on
+Train-mode BatchNorm statistics stay per rank (the reference has no SyncBN), so a sharded step equals the reference run on
 each shard, not on the unsharded batch; eval-mode BN makes the sharded gradients' mean equal to the unsharded mean over
 frames.
 """
