@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY. Nothing under ``mask_bev_b200/`` imports this module; 
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs do, and there
 only as the checker or as the timed CPU baseline.
 
-PARITY UNPINNED, EXCEPT THE POINT DECORATION (see the last bullet). The reference path (``/root/reference/mask_bev/models/encoders/mask_bev_encoders.py:21-123``)
+PARITY UNPINNED, EXCEPT THE POINT DECORATION AND THE SCATTER / GATHER INDEX ARITHMETIC (see the last two bullets). The reference path (``/root/reference/mask_bev/models/encoders/mask_bev_encoders.py:21-123``)
 delegates its arithmetic to ``mmcv==2.0.0`` (``mmcv.ops.Voxelization``) and ``mmdet3d==1.1.0``
 (``PillarFeatureNet`` / ``PFNLayer`` / ``PointPillarsScatter``), pinned in ``Dockerfile:25,28``; neither
 is vendored, installed or installable offline, and the reference's own tests
@@ -17,7 +17,12 @@ published upstream algorithms and is pinned by
   * the invariants of SURVEY.md A.5 under hypothesis,
   * and, for the decoration only, outputs of the reference's OWN code: the commented mmdet3d-0.x ``forward`` kept in
     ``mask_bev_encoders.py:270-317`` is executed by ``tests/golden/make_golden_decoration.py`` where the reference
-    lies; ``decorate(voxel_center_dims=2)`` reproduces the committed vectors bit for bit (tests/test_oracle.py).
+    lies; ``decorate(voxel_center_dims=2)`` reproduces the committed vectors bit for bit (tests/test_oracle.py),
+  * and, for the scatter and its gather backward, the commented ``map_voxel_center_to_point`` of the same file
+    (``canvas[:, b*ny*nx + y*nx + x] = rows.t()`` then a per-coordinate gather), executed by
+    ``tests/golden/make_golden_scatter.py``; ``scatter_np`` reproduces ``scatter_fossil.npz`` bit for bit.
+  The voxelizer (mmcv's compiled op) and the PFN layers (Linear / BN1d / max / concat of mmdet3d's ``PFNLayer``) have no
+  code on disk to execute: they stay pinned by the restatement agreements above only.
 
 Reference call sites each function follows are cited in its docstring.
 """

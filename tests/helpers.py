@@ -59,3 +59,23 @@ def ref_test_kwargs(feat_channels=(16, 32, 64), T=100, C=4, x_range=(-40, 40), y
                 voxel_size_x=vs, voxel_size_y=vs, voxel_size_z=z_range[1] - z_range[0], max_num_points=T,
                 encoding_type="vanilla", fourier_enc_group=1, max_voxels=max_voxels,
                 encoder_params=dict(with_distance=True), pc_point_dim=C)
+
+
+def scatter_fossil():
+    """Golden vectors of the scatter's index arithmetic from the reference's own (commented) code —
+    tests/golden/make_golden_scatter.py. Returns the dict of arrays."""
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "scatter_fossil.npz")))
+
+
+def check_canvas_against_scatter_fossil(canvas, g):
+    """`canvas` (B, C, ny, nx) built from g['voxel_mean'] / g['voxel_coors'] must, read back at g['pts_coors'], give the
+    reference's `center_per_point` bit for bit; every voxel row must sit at its own cell; everything else is zero."""
+    B, C, ny, nx = (int(v) for v in g["shape"])
+    canvas = np.asarray(canvas)
+    assert canvas.shape == (B, C, ny, nx) and canvas.dtype == np.float32
+    pc, vc = g["pts_coors"].astype(np.int64), g["voxel_coors"].astype(np.int64)
+    assert np.array_equal(canvas[pc[:, 0], :, pc[:, 2], pc[:, 3]], g["center_per_point"])
+    assert np.array_equal(canvas[vc[:, 0], :, vc[:, 2], vc[:, 3]], g["voxel_mean"])
+    occ = np.zeros((B, ny, nx), bool)
+    occ[vc[:, 0], vc[:, 2], vc[:, 3]] = True
+    assert np.count_nonzero(canvas.transpose(0, 2, 3, 1)[~occ]) == 0

@@ -246,3 +246,37 @@ def test_forward_autograd_equals_forward_and_reaches_every_parameter():
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
     # LayerNorm: dbias of sum() is the batch size everywhere
     assert torch.equal(orc.layer_norm.bias.grad, torch.full_like(orc.layer_norm.bias, float(len(frames))))
+
+
+def test_scatter_matches_the_reference_fossil():
+    """The oracle's scatter against outputs of the reference's OWN code: the commented `map_voxel_center_to_point` kept in
+    mask_bev_encoders.py (scatter `canvas[:, b*ny*nx + y*nx + x] = rows.t()` followed by a per-coordinate gather),
+    executed by tests/golden/make_golden_scatter.py where the reference lies; vectors committed as scatter_fossil.npz.
+    Bit-exact — this pins A.5 of SURVEY.md (index arithmetic, coordinate columns, zeros elsewhere) and the gather that
+    is the scatter's backward."""
+    from helpers import check_canvas_against_scatter_fossil, scatter_fossil
+    g = scatter_fossil()
+    B, C, ny, nx = (int(v) for v in g["shape"])
+    geo = O.encoder_geometry((g["point_cloud_range"][0], g["point_cloud_range"][3]),
+                             (g["point_cloud_range"][1], g["point_cloud_range"][4]), (-3.0, 1.0),
+                             float(g["voxel_size"][0]), float(g["voxel_size"][1]), 4.0)
+    assert (geo["ny"], geo["nx"]) == (ny, nx)          # int((hi - lo) / v) as the fossil sizes its canvas
+    canvas = O.scatter_np(g["voxel_mean"], g["voxel_coors"], B, ny, nx)
+    check_canvas_against_scatter_fossil(canvas, g)
+    assert np.array_equal(O.occupancy_np(g["voxel_coors"], B, ny, nx), np.abs(canvas).sum(1) > 0)
+
+
+def test_golden_scatter_regenerates_from_the_reference_when_present():
+    """Where /root/reference is mounted (this container), re-execute the fossil and compare with the committed file."""
+    if not os.path.exists("/root/reference/mask_bev/models/encoders/mask_bev_encoders.py"):
+        pytest.skip("reference tree not mounted (GPU box)")
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_scatter", os.path.join(here, "golden", "make_golden_scatter.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    d = mod.make_inputs()
+    g = np.load(os.path.join(here, "golden", "scatter_fossil.npz"))
+    for k, v in d.items():
+        assert np.array_equal(v, g[k]), k
+    assert np.array_equal(mod.run_fossil(mod.fossil_scatter_gather(), d), g["center_per_point"])
