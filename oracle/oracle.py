@@ -21,6 +21,10 @@ published upstream algorithms and is pinned by
   * and, for the scatter and its gather backward, the commented ``map_voxel_center_to_point`` of the same file
     (``canvas[:, b*ny*nx + y*nx + x] = rows.t()`` then a per-coordinate gather), executed by
     ``tests/golden/make_golden_scatter.py``; ``scatter_np`` reproduces ``scatter_fossil.npz`` bit for bit.
+  * and, for everything the reference file itself does (geometry, strict filter, per-frame loop, concatenation, batch
+    column, LayerNorm), the reference's OWN ``MaskBevEncoder`` class executed end to end by
+    ``tests/golden/make_golden_encoder.py`` with stand-ins for the three absent upstream classes;
+    ``MaskBevEncoderOracle`` reproduces ``encoder_reference.npz`` bit for bit.
   The voxelizer (mmcv's compiled op) and the PFN layers (Linear / BN1d / max / concat of mmdet3d's ``PFNLayer``) have no
   code on disk to execute: they stay pinned by the restatement agreements above only.
 

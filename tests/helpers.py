@@ -79,3 +79,16 @@ def check_canvas_against_scatter_fossil(canvas, g):
     occ = np.zeros((B, ny, nx), bool)
     occ[vc[:, 0], vc[:, 2], vc[:, 3]] = True
     assert np.count_nonzero(canvas.transpose(0, 2, 3, 1)[~occ]) == 0
+
+
+def encoder_reference():
+    """Inputs, weights and outputs of the reference's OWN MaskBevEncoder (tests/golden/make_golden_encoder.py):
+    (frames, state_dict of numpy arrays, dict of outputs, constructor kwargs)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "encoder_reference.npz"))
+    frames = [g[f"frame{i}"] for i in range(sum(1 for k in g.files if k.startswith("frame")))]
+    weights = {k[2:]: g[k] for k in g.files if k.startswith("w:")}
+    out = {k: g[k] for k in ("voxels", "num_points", "coors", "pseudo_img", "canvas_shape")}
+    kw = dict(feat_channels=[16, 32], x_range=(-8, 8), y_range=(-6, 6), z_range=(-2, 2), voxel_size_x=0.5,
+              voxel_size_y=0.5, voxel_size_z=4, max_num_points=8, encoding_type='vanilla', fourier_enc_group=1,
+              max_voxels=250000, encoder_params=dict(with_distance=True), pc_point_dim=4)
+    return frames, weights, out, kw

@@ -171,3 +171,15 @@ def test_reference_encoder_file_imports_unchanged_against_shims():
         sys.path[:] = saved
         for m in [m for m in sys.modules if m.split(".")[0] in ("mmcv", "mmdet3d", "mask_bev")]:
             del sys.modules[m]
+
+
+def test_reference_checkpoint_of_the_golden_run_loads_strictly():
+    """The state dict saved from the reference's own MaskBevEncoder (tests/golden/encoder_reference.npz) loads into the
+    product encoder with strict=True: same keys, same shapes (mask_bev_module.py:113-126 loads checkpoints by name)."""
+    import mask_bev_b200 as M
+    from helpers import encoder_reference
+    _, weights, out, kw = encoder_reference()
+    enc = M.MaskBevEncoder(**kw)
+    res = enc.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert [enc._num_voxel_y, enc._num_voxel_x] == [int(v) for v in out["canvas_shape"]]

@@ -391,25 +391,3 @@ def test_pfn_vcd2_on_the_reference_fossil_inputs(chans, gemm, legacy):
         out = net(vox.to(DEV), nump.to(DEV), coors.to(DEV))
     assert_close(out.cpu().numpy(), ref, what=f"vcd2 legacy={legacy} {chans} {gemm}")
 
-
-def test_scatter_and_gather_on_the_reference_fossil_inputs():
-    """K3 / K3' against outputs of the reference's own (commented) scatter + gather code on the committed inputs
-    (tests/golden/scatter_fossil.npz, generator make_golden_scatter.py): canvas read back at the reference's query
-    coordinates equals its `center_per_point` bit for bit, and the backward is that same gather."""
-    import mask_bev_b200 as M
-    from helpers import check_canvas_against_scatter_fossil, scatter_fossil
-    g = scatter_fossil()
-    B, C, ny, nx = (int(v) for v in g["shape"])
-    sc = M.PointPillarsScatter(C, [ny, nx])
-    f = torch.from_numpy(g["voxel_mean"]).to(DEV).requires_grad_(True)
-    out = sc(f, torch.from_numpy(g["voxel_coors"]).to(DEV), B)
-    check_canvas_against_scatter_fossil(out.detach().cpu().numpy(), g)
-    out.backward(out.detach().clone())           # K3': dfeats[p] = dcanvas[b, :, y, x] — here the canvas itself
-    assert np.array_equal(f.grad.cpu().numpy(), g["voxel_mean"])
-    pc = g["pts_coors"].astype(np.int64)         # and the reference's own gather, through the backward kernel
-    q = M.PointPillarsScatter(C, [ny, nx])
-    uniq, first = np.unique(pc[:, [0, 2, 3]], axis=0, return_index=True)
-    qc = g["pts_coors"][np.sort(first)]          # query cells, each once (a coors list names a cell once)
-    z = torch.zeros((len(qc), C), device=DEV, requires_grad=True)
-    q(z, torch.from_numpy(qc).to(DEV), B).backward(out.detach().clone())
-    assert np.array_equal(z.grad.cpu().numpy(), g["center_per_point"][np.sort(first)])

@@ -280,3 +280,61 @@ def test_golden_scatter_regenerates_from_the_reference_when_present():
     for k, v in d.items():
         assert np.array_equal(v, g[k]), k
     assert np.array_equal(mod.run_fossil(mod.fossil_scatter_gather(), d), g["center_per_point"])
+
+
+def _oracle_for_encoder_reference():
+    import torch
+    from helpers import encoder_reference
+    frames, weights, out, kw = encoder_reference()
+    orc = O.MaskBevEncoderOracle(feat_channels=kw["feat_channels"], x_range=kw["x_range"], y_range=kw["y_range"],
+                                 z_range=kw["z_range"], voxel_size_x=kw["voxel_size_x"], voxel_size_y=kw["voxel_size_y"],
+                                 voxel_size_z=kw["voxel_size_z"], max_num_points=kw["max_num_points"],
+                                 max_voxels=kw["max_voxels"], pc_point_dim=4, with_distance=True, layer_norm=True)
+    orc.pfn.load_state_dict({k[len("_voxel_encoder."):]: torch.from_numpy(v) for k, v in weights.items()
+                             if k.startswith("_voxel_encoder.")})
+    orc.pfn.eval()
+    orc.layer_norm.load_state_dict({k[len("_layer_norm."):]: torch.from_numpy(v) for k, v in weights.items()
+                                    if k.startswith("_layer_norm.")})
+    return orc, frames, out
+
+
+@pytest.mark.parametrize("voxelizer", ["c", "np", "py"])
+def test_oracle_matches_the_reference_encoder_run(voxelizer):
+    """The whole oracle path against outputs of the reference's OWN `MaskBevEncoder` (mask_bev_encoders.py:21-123
+    executed by tests/golden/make_golden_encoder.py with stand-ins for the three absent upstream classes): geometry,
+    strict range filter (points ON a bound are dropped), per-frame loop + concatenation + batch column, an empty
+    frame, truncation to T points, scatter, LayerNorm — bit for bit."""
+    import torch
+    orc, frames, out = _oracle_for_encoder_reference()
+    orc._vox = dict(c=O.hard_voxelize_c, np=O.hard_voxelize_np, py=O.hard_voxelize_py)[voxelizer]
+    assert (orc.geo["ny"], orc.geo["nx"]) == tuple(int(v) for v in out["canvas_shape"])
+    voxels, nump, coors, kept = orc.voxelize(frames)
+    assert np.array_equal(coors, out["coors"]) and coors.dtype == out["coors"].dtype
+    assert np.array_equal(nump, out["num_points"])
+    assert np.array_equal(voxels, out["voxels"])
+    assert int(nump.max()) == 8 and 1 not in set(coors[:, 0].tolist())      # truncation happened; frame 1 is empty
+    # kept_idx addresses rows of the UNFILTERED frame: the six points on the bounds (rows 0..5 of frame 0) never appear
+    assert not (set(kept[coors[:, 0] == 0].ravel().tolist()) & set(range(6)))
+    with torch.no_grad():
+        img = orc.forward(frames)
+    assert np.array_equal(img.numpy(), out["pseudo_img"])
+
+
+def test_golden_encoder_regenerates_from_the_reference_when_present():
+    if not os.path.exists("/root/reference/mask_bev/models/encoders/mask_bev_encoders.py"):
+        pytest.skip("reference tree not mounted (GPU box)")
+    import importlib.util
+    from helpers import encoder_reference
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_encoder", os.path.join(here, "golden", "make_golden_encoder.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    frames, weights, out, kw = encoder_reference()
+    assert kw == mod.KW
+    new_frames = mod.make_frames()
+    assert all(np.array_equal(a, b) for a, b in zip(frames, new_frames))
+    new_out, new_w = mod.run_reference(new_frames)
+    for k, v in out.items():
+        assert np.array_equal(new_out[k], v), k
+    for k, v in weights.items():
+        assert np.array_equal(new_w["w:" + k], v), k
