@@ -318,6 +318,8 @@ def test_oracle_matches_the_reference_encoder_run(voxelizer):
     with torch.no_grad():
         img = orc.forward(frames)
     assert np.array_equal(img.numpy(), out["pseudo_img"])
+    # the differentiable restatement (the arbiter of the gradient tests and of smoke()) is the same function
+    assert np.array_equal(orc.forward_autograd(frames).detach().numpy(), out["pseudo_img"])
 
 
 def test_golden_encoder_regenerates_from_the_reference_when_present():
