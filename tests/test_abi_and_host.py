@@ -183,3 +183,38 @@ def test_reference_checkpoint_of_the_golden_run_loads_strictly():
     res = enc.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     assert [enc._num_voxel_y, enc._num_voxel_x] == [int(v) for v in out["canvas_shape"]]
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: the header compiles as strict C99 (and as C++17), and a C program that takes the address
+    of every declared entry point links against libmask_bev_b200.so and runs its host-only calls."""
+    import shutil
+    import subprocess
+    from mask_bev_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "mask_bev_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    _lib.load()
+    syms = _header_symbols()
+    src = tmp_path / "link_all.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "mask_bev_b200.h"\n'
+        "int main(void) {\n"
+        "  const void *fns[] = {" + ", ".join(f"(const void *)&{s}" for s in syms) + "};\n"
+        "  size_t n = sizeof fns / sizeof fns[0], i, bytes = 0;\n"
+        "  for (i = 0; i < n; ++i) if (!fns[i]) return 2;\n"
+        "  if (mbev_abi_version() != MBEV_ABI_VERSION) return 3;\n"
+        "  if (!strstr(mbev_build_info(), \"sm_100a\")) return 4;\n"
+        "  if (mbev_scatter_layernorm_workspace_bytes(16, &bytes) != 0 || bytes == 0) return 5;\n"
+        "  if (mbev_scatter_layernorm_backward_supported(16, 128, 800, 800) != 1) return 6;\n"
+        "  printf(\"%u entry points, ABI %d\\n\", (unsigned)n, mbev_abi_version());\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "link_all"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    assert f"{len(syms)} entry points, ABI {_lib.ABI_VERSION}" in r.stdout
