@@ -18,7 +18,6 @@ from typing import Dict, List, Optional, Union
 
 import torch
 from torch import nn
-from torch.nn import functional as F
 
 from . import functional as F_
 from ._lib import MbevError

@@ -6,7 +6,7 @@ autograd-aware equivalent.
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 

@@ -2,7 +2,6 @@
 torch autograd through `nn.LayerNorm([C, ny, nx], eps=1e-3)` applied to the scatter output (mask_bev_encoders.py:75,
 91-92; the reference has no backward code of its own, autograd derives it). The arbiter is float64 autograd on a dense
 canvas built from the same rows; tolerance 1e-5 of max|ref| (fp32). Through the C ABI."""
-import numpy as np
 import pytest
 import torch
 
