@@ -340,3 +340,57 @@ def test_golden_encoder_regenerates_from_the_reference_when_present():
         assert np.array_equal(new_out[k], v), k
     for k, v in weights.items():
         assert np.array_equal(new_w["w:" + k], v), k
+
+
+def test_oracle_equals_the_reference_encoder_on_random_batches_when_present():
+    """Beyond the committed fixture: where the reference tree is mounted, run ITS MaskBevEncoder (stand-ins for the three
+    absent upstream classes) and the oracle on random batches — ragged frame sizes, empty frames, points snapped onto the
+    range bounds, two geometries — and require bit-identical voxelize outputs and pseudo images."""
+    if not os.path.exists("/root/reference/mask_bev/models/encoders/mask_bev_encoders.py"):
+        pytest.skip("reference tree not mounted (GPU box)")
+    import importlib.util
+    import torch
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_encoder", os.path.join(here, "golden", "make_golden_encoder.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    Ref = mod.reference_encoder_class()
+    rng = np.random.default_rng(5)
+    geos = [dict(x_range=(-8, 8), y_range=(-6, 6), z_range=(-2, 2), vs=0.5, T=8, C=4),
+            dict(x_range=(0, 7.04), y_range=(-4, 4), z_range=(-3, 1), vs=0.16, T=5, C=3)]
+    for case in range(8):
+        geo = geos[case % 2]
+        kw = dict(feat_channels=[16, 32], x_range=geo["x_range"], y_range=geo["y_range"], z_range=geo["z_range"],
+                  voxel_size_x=geo["vs"], voxel_size_y=geo["vs"], voxel_size_z=geo["z_range"][1] - geo["z_range"][0],
+                  max_num_points=geo["T"], encoding_type='vanilla', fourier_enc_group=1, max_voxels=(60, 250000),
+                  encoder_params=dict(with_distance=True), pc_point_dim=geo["C"])
+        frames = []
+        for _ in range(int(rng.integers(1, 4))):
+            n = int(rng.choice([0, 1, 50, 700]))
+            lo = np.array([geo["x_range"][0], geo["y_range"][0], geo["z_range"][0]])
+            hi = np.array([geo["x_range"][1], geo["y_range"][1], geo["z_range"][1]])
+            p = np.empty((n, geo["C"]), np.float32)
+            p[:, :3] = rng.uniform(lo - 1, hi + 1, (n, 3))
+            p[:, 3:] = rng.uniform(0, 1, (n, geo["C"] - 3))
+            snap = rng.random(n) < 0.05                     # some coordinates exactly ON a bound
+            p[snap, 0] = np.float32(rng.choice([lo[0], hi[0]]))
+            frames.append(p)
+        ref = Ref(**kw)
+        mod.randomise(ref, seed=case)
+        ref.eval()                                           # eval: max_voxels[1]
+        orc = O.MaskBevEncoderOracle(feat_channels=kw["feat_channels"], x_range=kw["x_range"], y_range=kw["y_range"],
+                                     z_range=kw["z_range"], voxel_size_x=geo["vs"], voxel_size_y=geo["vs"],
+                                     voxel_size_z=kw["voxel_size_z"], max_num_points=geo["T"], max_voxels=250000,
+                                     pc_point_dim=geo["C"], with_distance=True, layer_norm=True, voxelizer="np")
+        orc.pfn.load_state_dict(ref._voxel_encoder.state_dict())
+        orc.pfn.eval()
+        orc.layer_norm.load_state_dict(ref._layer_norm.state_dict())
+        assert (orc.geo["ny"], orc.geo["nx"]) == (ref._num_voxel_y, ref._num_voxel_x)
+        pcs = [torch.from_numpy(f) for f in frames]
+        with torch.no_grad():
+            rv, rn, rc = ref.voxelize(pcs)
+            rimg = ref(pcs)
+            ov, on, oc, _ = orc.voxelize(frames)
+            oimg = orc.forward(frames)
+        assert np.array_equal(rc.numpy(), oc) and np.array_equal(rn.numpy(), on) and np.array_equal(rv.numpy(), ov), case
+        assert np.array_equal(rimg.numpy(), oimg.numpy()), case
