@@ -218,3 +218,62 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stderr)
     assert f"{len(syms)} entry points, ABI {_lib.ABI_VERSION}" in r.stdout
+
+
+def _training_configs():
+    import json
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "training_configs.json")))
+
+
+def _encoder_kwargs_of(cfg):
+    """As MaskBevModule.__init__ derives them (mask_bev_module.py:39-43 defaults, :62, :72-75)."""
+    z = cfg["z_range"]
+    return dict(feat_channels=list(cfg["encoder_feat_channels"]), x_range=cfg["x_range"], y_range=cfg["y_range"],
+                z_range=z, voxel_size_x=cfg["voxel_size"], voxel_size_y=cfg["voxel_size"], voxel_size_z=z[1] - z[0],
+                max_num_points=cfg["max_num_points"], encoding_type=cfg.get("encoder_encoding_type", "vanilla"),
+                fourier_enc_group=cfg.get("encoder_fourier_enc_group", 1), encoder_params=dict(with_distance=True),
+                pc_point_dim=cfg.get("pc_point_dim", 4))
+
+
+def test_every_reference_training_config_builds_and_fits_the_kernels():
+    """SURVEY.md §8a parameter envelope: every file under the reference's configs/training (collected into
+    tests/golden/training_configs.json by make_training_configs.py) builds the product encoder with the canvas the
+    reference derives, and its shapes are inside what the kernels and their fused forms accept (host-side probes)."""
+    import mask_bev_b200 as M
+    from mask_bev_b200 import functional as F_
+    cfgs = _training_configs()
+    assert len(cfgs) == 11
+    seen = set()
+    for name, cfg in cfgs.items():
+        kw = _encoder_kwargs_of(cfg)
+        enc = M.MaskBevEncoder(**kw)
+        nx = int((cfg["x_range"][1] - cfg["x_range"][0]) / cfg["voxel_size"])     # mask_bev_module.py:67-68
+        ny = int((cfg["y_range"][1] - cfg["y_range"][0]) / cfg["voxel_size"])
+        assert (enc._num_voxel_x, enc._num_voxel_y) == (nx, ny), name
+        assert tuple(enc._layer_norm.weight.shape) == (kw["feat_channels"][-1], ny, nx), name
+        C, B, T = kw["feat_channels"][-1], cfg.get("batch_size", 1), kw["max_num_points"]
+        pcfg = enc._voxel_encoder._config()
+        assert pcfg.in_dims[0] == kw["pc_point_dim"] + 3 + 3 + 1, name           # decoration width D
+        assert F_.pfn_path(pcfg, T) in ("tcgen05", "fma"), name
+        assert F_.scatter_layernorm_backward_supported(B, C, ny, nx), name       # fused LayerNorm pair usable
+        assert _lib_probe_ln(B, C, ny, nx), name
+        seen.add((tuple(kw["feat_channels"]), kw["pc_point_dim"], nx, ny))
+    assert ((256, 128, 128), 4, 500, 500) in seen and ((128, 64, 128), 4, 500, 500) in seen
+    assert any(s[1] == 3 for s in seen) and any(s[2] == 800 for s in seen)
+
+
+def _lib_probe_ln(B, C, ny, nx):
+    from mask_bev_b200 import _lib
+    null = ctypes.c_void_p(None)
+    return _lib.load().mbev_scatter_layernorm_supported(B, C, ny, nx, null, null, null) == 1
+
+
+def test_training_configs_fixture_matches_the_reference_when_present():
+    if not os.path.isdir("/root/reference/configs/training"):
+        pytest.skip("reference tree not mounted (GPU box)")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_training_configs",
+                                                  os.path.join(ROOT, "tests", "golden", "make_training_configs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.collect() == _training_configs()
