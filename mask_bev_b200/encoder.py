@@ -21,9 +21,20 @@ from torch import nn
 
 from . import functional as F_
 from ._lib import MbevError
+from .collate import PackedFrames
 from .pillar_encoder import PillarFeatureNet
 from .scatter import PointPillarsScatter, scatter_layernorm_with_table, scatter_with_table
 from .voxelize import Voxelization
+
+
+def _as_points(point_clouds):
+    """(points (sum N_i, C) contiguous, frame sizes) of a batch given as the reference's list of per-frame tensors
+    (mask_bev_encoders.py:77-81) or as a `PackedFrames` (already one tensor: no concatenation)."""
+    if isinstance(point_clouds, PackedFrames):
+        return point_clouds.points.contiguous(), [int(s) for s in point_clouds.sizes]
+    sizes = [int(pc.shape[0]) for pc in point_clouds]
+    pts = point_clouds[0] if len(point_clouds) == 1 else torch.cat(point_clouds, dim=0)
+    return pts.contiguous(), sizes
 
 
 class EncodingType:
@@ -96,9 +107,7 @@ class MaskBevEncoder(nn.Module):
         if canvas_dtype != torch.float32:
             if torch.is_grad_enabled() and any(p.requires_grad for p in self._voxel_encoder.parameters()):
                 raise MbevError("a bfloat16 canvas is forward-only: call under torch.no_grad()")
-        sizes = [int(pc.shape[0]) for pc in point_clouds]
-        pts = point_clouds[0] if len(point_clouds) == 1 else torch.cat(point_clouds, dim=0)
-        pts = pts.contiguous()
+        pts, sizes = _as_points(point_clouds)
         geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
         vb = F_.voxelize_batch(pts, sizes, geo)
         fused = None
@@ -136,8 +145,7 @@ class MaskBevEncoder(nn.Module):
     def _forward_fused_layer_norm_autograd(self, point_clouds):
         """Training: K1 -> K2 (autograd) -> (K3 + LayerNorm) with the fused backward; the canvas is never written
         un-normalised and torch's LayerNorm (224 ms forward on the kitti_b16 canvas) is not on the path."""
-        sizes = [int(pc.shape[0]) for pc in point_clouds]
-        pts = (point_clouds[0] if len(point_clouds) == 1 else torch.cat(point_clouds, dim=0)).contiguous()
+        pts, sizes = _as_points(point_clouds)
         geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
         vb = F_.voxelize_batch(pts, sizes, geo)
         feats = self._voxel_encoder.apply_rows(pts, vb.kept_idx, vb.num_points, vb.coors, vb.num_pillars_dev,
@@ -154,8 +162,7 @@ class MaskBevEncoder(nn.Module):
         ln = self._layer_norm
         if len(point_clouds) == 0 or not ln.elementwise_affine or ln.weight is None or ln.bias is None:
             return None
-        sizes = [int(pc.shape[0]) for pc in point_clouds]
-        pts = (point_clouds[0] if len(point_clouds) == 1 else torch.cat(point_clouds, dim=0)).contiguous()
+        pts, sizes = _as_points(point_clouds)
         geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
         vb = F_.voxelize_batch(pts, sizes, geo)
         with torch.no_grad():
@@ -171,8 +178,7 @@ class MaskBevEncoder(nn.Module):
     # -- module-level methods with the reference's semantics ---------------------------------------------
     def voxelize(self, point_clouds):
         """mask_bev_encoders.py:95-111: voxels (P,T,C), num_points (P,), coors_batch (P,4) = (b,z,y,x)."""
-        sizes = [int(pc.shape[0]) for pc in point_clouds]
-        pts = (point_clouds[0] if len(point_clouds) == 1 else torch.cat(point_clouds, dim=0)).contiguous()
+        pts, sizes = _as_points(point_clouds)
         geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
         vb = F_.voxelize_batch(pts, sizes, geo)
         P = int(vb.pillar_base[-1].item())
