@@ -5,12 +5,15 @@
 
 A "step" is one pass of the hot path over one batch of synthetic frames (BASELINE.json configs[1]: KITTI-shaped
 frames, batch 16, x 0..80 / y +-40 @ 0.1 m -> 800x800 canvas, [128,128,128] PFN, fp32 forward, eval-mode BN).
-N > 1: one process per GPU (torchrun), frames shard by rank (weak scaling: every rank runs its own batch of 16),
-no data-path collective; barrier + synchronize on both sides, device time via CUDA events, max over ranks.
+N > 1: one process per GPU (torchrun), frames shard by rank (weak scaling: every rank runs its own batch of 16;
+`--scaling strong`: the workload's batch is split over the ranks, BASELINE configs[2]), no data-path collective;
+barrier + synchronize on both sides, device time via CUDA events, max over ranks.
 
-Keys beyond the base contract: `roofline` (dominant kernel, algorithmic bytes / event time vs MEASURED_PEAKS.json),
-`kernels` (per-kernel breakdown), `cpu_baseline` (oracle port timed on this box's host cores), `e2e` (same metric
-through the C-ABI host entry: pinned host points -> H2D -> K1,K2,K3 -> D2H of the per-frame pillar counts).
+Keys beyond the base contract: `roofline` (dominant kernel, algorithmic bytes / event time vs MEASURED_PEAKS.json, and
+`step_frac` = the whole step against the fused-path HBM floor), `kernels` (per-kernel breakdown), `cpu_baseline`
+(oracle port timed on this box's host cores at 1 / 6 / all threads), `e2e` (same metric through the C-ABI pipelined
+entry with HOST points: pinned host points -> H2D -> K1,K2,K3 -> D2H of the per-frame pillar counts), `train` (N > 1 or
+--train: forward + backward + NCCL gradient allreduce of the encoder incl. LayerNorm, the north star's only collective).
 `--impl reference` times the oracle port (the reference's CPU path cannot be installed: mmcv/mmdet3d absent).
 """
 from __future__ import annotations
@@ -204,22 +207,29 @@ def run_reference_arm(args):
     O.build_c_oracle()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_frames = 2
-    cfg, kwargs, frames = build_workload(args.workload, 0, batch=sample_frames)
+    cfg = build_workload(args.workload, 0, batch=1)[0]
+    B = cfg["batch"] if args.batch is None else args.batch
+    _, kwargs, frames = build_workload(args.workload, 0, batch=B)
     _, pfn = make_encoder_cpu_only(kwargs)
+    cpu_path_once(frames[:1], kwargs, pfn)
+    t0 = time.perf_counter()
+    cpu_path_once(frames[:1], kwargs, pfn)
+    t_frame = time.perf_counter() - t0
+    # bounded sample: as many frames of the B-frame batch per step as keep the whole --steps/--warmup run near 2 minutes
+    sample_frames = int(max(1, min(B, 120.0 / (t_frame * (args.steps + max(args.warmup, 1))))))
     for _ in range(max(args.warmup, 1)):
-        cpu_path_once(frames[:1], kwargs, pfn)
+        cpu_path_once(frames[:sample_frames], kwargs, pfn)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_path_once(frames, kwargs, pfn)
+        cpu_path_once(frames[:sample_frames], kwargs, pfn)
     dt = time.perf_counter() - t0
     fps = sample_frames * args.steps / dt
-    sample = (f"{sample_frames} frames of the {cfg['batch']}-frame batch per step; serial C voxelizer (mmcv's CPU kernel "
-              f"is serial) + dense torch-CPU PFN over all P*T slots + scatter, torch threads={cores}")
+    sample = (f"{sample_frames} frames of the {B}-frame batch per step (frames/s is batch-normalised); serial C voxelizer "
+              f"(mmcv's CPU kernel is serial) + dense torch-CPU PFN over all P*T slots + scatter, torch threads={cores}")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, cfg, sample_frames),
+            "config": workload_config(args.workload, cfg, B), "sample_frames_per_step": sample_frames,
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "oracle port: the reference's own CPU path (mmcv==2.0.0 / mmdet3d==1.1.0) is not installable offline"}
@@ -259,6 +269,91 @@ def ev_time(fn, iters, stream_sync):
     return s.elapsed_time(e) / iters  # ms
 
 
+def time_cpu_threads(frames, kwargs, pfn, threads, nframes, budget_s):
+    import torch
+    torch.set_num_threads(threads)
+    t, reps = time_cpu(frames[:nframes], kwargs, pfn, budget_s=budget_s, min_reps=1, max_reps=5)
+    return {"value": nframes / t, "frames": nframes, "reps": reps}
+
+
+def train_block(args, enc, kwargs, rank, world, dev, barrier):
+    """Forward + backward of MaskBevEncoder.forward (K1, K2, K3+LayerNorm and their backward kernels, train-mode BN)
+    on this rank's frames, then the gradient allreduce of mask_bev_b200.data_parallel over NCCL — the only collective
+    of the north star (train_mask_bev.py:92-96 strategy='ddp'). Timed with CUDA events, MAX over ranks."""
+    import torch
+    import torch.distributed as dist
+    import mask_bev_b200 as M
+    from mask_bev_b200.data_parallel import FrontEndDataParallel, gradient_bytes
+    from mask_bev_b200.synthetic import gen_batch
+    tb = args.train_batch
+    torch.manual_seed(0)  # identical initial weights on every rank
+    tenc = M.MaskBevEncoder(**kwargs).to(dev)
+    tenc._voxel_encoder.load_state_dict(enc._voxel_encoder.state_dict())
+    tenc.train()
+    frames = [torch.from_numpy(f).to(dev) for f in gen_batch(args.workload, batch=tb, first_frame=10_000 + rank * tb)]
+    out = {}
+    g = None
+    for overlap in (False, True):
+        dp = FrontEndDataParallel(tenc, overlap=overlap)
+
+        def step(reduce=True):
+            nonlocal g
+            tenc.zero_grad(set_to_none=False)
+            y = tenc(frames)
+            if g is None:
+                g = torch.randn_like(y)
+            y.backward(g)
+            return dp.reduce_gradients() if reduce else None
+
+        def timed(n, reduce):
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(n):
+                rep = step(reduce)
+            e.record()
+            barrier()
+            t = torch.tensor([s.elapsed_time(e) / n], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t), rep
+
+        for _ in range(2):
+            step()
+        n = max(2, min(args.steps, 5))
+        if not overlap:
+            out["fwd_bwd_ms"], _ = timed(n, False)
+        ms, rep = timed(n, True)
+        out["step_overlapped_ms" if overlap else "step_serial_ms"] = ms
+        dp.close()
+    nbytes = gradient_bytes(tenc)
+    out.update({"what": "encoder training step (train-mode BN, fused scatter+LayerNorm fwd/bwd) + gradient allreduce; "
+                        "overlapped = the LayerNorm-gradient allreduce is issued from a post-accumulate hook and runs "
+                        "under the PFN backward",
+                "frames_per_gpu": tb, "allreduce_bytes_per_rank": nbytes, "collectives_per_step": rep.collectives if rep else 0,
+                "frames_per_s": world * tb / (out["step_overlapped_ms"] * 1e-3)})
+    if world > 1:  # the collective alone, back to back, for its bus bandwidth
+        big = [p.grad for p in tenc.parameters() if p.grad is not None and p.grad.numel() * 4 >= (1 << 20)]
+        for _ in range(2):
+            for t in big:
+                dist.all_reduce(t)
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(3):
+            for t in big:
+                dist.all_reduce(t)
+        e.record()
+        barrier()
+        t_ar = torch.tensor([s.elapsed_time(e) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_ar, op=dist.ReduceOp.MAX)
+        by = sum(t.numel() * 4 for t in big)
+        out.update({"allreduce_alone_ms": float(t_ar), "allreduce_bus_gbs": 2.0 * (world - 1) / world * by / float(t_ar) / 1e6,
+                    "allreduce_exposed_ms": out["step_overlapped_ms"] - out["fwd_bwd_ms"],
+                    "nvlink_reference": "8-rank all-reduce bus bandwidth 725 GB/s at 1 GiB (B200_PROFILING.md)"})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -280,10 +375,20 @@ def run_ours(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
-    cfg, kwargs, frames = build_workload(args.workload, rank, batch=args.batch)
+    from mask_bev_b200.synthetic import CONFIGS, encoder_kwargs, gen_batch
+    cfg = CONFIGS[args.workload]
+    kwargs = encoder_kwargs(args.workload)
+    strong = args.scaling == "strong"
+    if strong:  # BASELINE configs[2]: ONE batch of the workload's size split over the ranks (frame i -> rank i mod N)
+        Bg = cfg["batch"] if args.batch is None else args.batch
+        frames = [f for i, f in enumerate(gen_batch(args.workload, batch=Bg)) if i % world == rank]
+    else:
+        frames = gen_batch(args.workload, batch=args.batch, first_frame=rank * (cfg["batch"] if args.batch is None else args.batch))
     B = len(frames)
+    if B == 0:
+        raise SystemExit(f"bench.py: rank {rank} owns no frame (batch smaller than the number of GPUs)")
     enc, pfn_cpu = make_encoder(kwargs, dev)
-    runner = FusedEncoderRunner(enc, [len(f) for f in frames], dev, overlap=args.overlap)
+    runner = FusedEncoderRunner(enc, [len(f) for f in frames], dev, scatter_ctas_per_sm=args.scatter_ctas)
     host = torch.from_numpy(np.concatenate(frames, 0)).pin_memory()
     runner.points_dev.copy_(host)
     counts_host = torch.empty((B + 1,), dtype=torch.int32).pin_memory()
@@ -294,8 +399,9 @@ def run_ours(args):
             dist.barrier()
         sync()
 
-    # ---- device-resident throughput (`value`): a stream of batches through mbev_encode_batch_pipelined (K1 of
-    # step i+1 on a prep stream under K2 / K3 of step i); `serial_ms_per_step` = mbev_encode_batch, one stream ----
+    # ---- device-resident throughput (`value`): a stream of batches through mbev_encode_batch_pipelined (K1 of step
+    # i+2 on a prep stream, K2 of step i+1 on a PFN stream, K3 of step i on the current stream);
+    # `serial_ms_per_step` = mbev_encode_batch, everything on one stream ----
     step_fn = runner.run_device if args.serial else runner.run_pipelined
     for _ in range(args.warmup):
         runner.run_device()
@@ -324,10 +430,10 @@ def run_ours(args):
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     # ---- end to end through the host entry (`e2e`): pinned host points in, per-frame pillar counts out, every
-    # step; pipelined = the H2D copy of step i+1 overlaps the kernels of step i (two device point buffers) ----
+    # step; pipelined = the H2D copy and K1 of step i+2 overlap K2 / K3 of the steps before ----
     host2 = host.clone().pin_memory()  # alternate two host batches so that no step can reuse a stale device copy
 
-    def e2e_loop(fn):
+    def e2e_loop(fn, base_of):
         for i in range(max(1, args.warmup // 2)):
             fn(host2 if i & 1 else host)
         barrier()
@@ -335,25 +441,30 @@ def run_ours(args):
         s2.record()
         for i in range(args.steps):
             fn(host2 if i & 1 else host)
-            counts_host.copy_(runner.pillar_base, non_blocking=True)
+            counts_host.copy_(base_of(), non_blocking=True)  # ordered on the current stream, after this step's K3
         e2.record()
         barrier()
         return s2.elapsed_time(e2)
 
-    ms2s = e2e_loop(runner.run_host)
-    if args.serial:
-        ms2 = e2e_loop(runner.run_host_pipelined)
-    else:
-        def e2e_pipe(h):
-            runner.run_pipelined(h)
-            runner.pillar_base = runner.last_pillar_base  # the D2H below reads the counts of the batch just enqueued
-        base0 = runner.pillar_base
-        ms2 = e2e_loop(e2e_pipe)
-        runner.pillar_base = base0
+    ms2s = e2e_loop(runner.run_host, lambda: runner.pillar_base)
+    ms2 = ms2s if args.serial else e2e_loop(runner.run_pipelined, lambda: runner.last_pillar_base)
     t = torch.tensor([ms, ms2, ms2s, ms_serial], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms2, ms2s, ms_serial = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    nfr = torch.tensor([B], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(nfr)
+    frames_all = int(nfr.item())  # frames all ranks process per step
+
+    train = None
+    if (world > 1 or args.train) and not args.no_train:
+        runner_state = None
+        try:
+            train = train_block(args, enc, kwargs, rank, world, dev, barrier)
+        except Exception as ex:  # noqa: BLE001  (never lose the headline line to the auxiliary block)
+            train = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        del runner_state
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -371,40 +482,33 @@ def run_ours(args):
     t_vox = ev_time(runner.run_voxelize, iters, sync)
     t_pfn = ev_time(runner.run_pfn, iters, sync)
     t_sc = ev_time(runner.run_scatter, iters, sync)
-    fused_ok = bool(runner.lib.mbev_pfn_scatter_supported(ctypes.byref(runner.params), T, B, runner.ny, runner.nx,
-                                                          ctypes.c_void_p(runner.canvas.data_ptr())))
-    t_fused = ev_time(runner.run_pfn_scatter, iters, sync) if fused_ok else None
-    split_ok = bool(runner.lib.mbev_scatter_split_supported(runner.ny, runner.nx, ctypes.c_void_p(runner.canvas.data_ptr())))
-    t_sc2 = ev_time(runner.run_scatter_split, iters, sync) if split_ok else None
-    t_fill = ev_time(runner.run_fill_empty, iters, sync) if split_ok else None
-    t_occ = ev_time(runner.run_scatter_occupied, iters, sync) if split_ok else None
+    stream_ok = bool(runner.lib.mbev_scatter_stream_supported(Co, runner.ny, runner.nx, ctypes.c_void_p(runner.canvas.data_ptr())))
+    t_st = {c: ev_time(lambda c=c: runner.run_scatter_stream(c), iters, sync) for c in (1, 2, 4, 8)} if stream_ok else {}
+    t_nhwc = ev_time(runner.run_scatter_nhwc, iters, sync) if Co % 4 == 0 else None
+    runner.run_scatter(); sync()
     # algorithmic bytes per launch (per frame x frames in the batch; DESIGN.md "Roofline accounting")
     by_vox = N * C * 4 + N * 4 + P * 20
     by_pfn = nk * (C * 4 + 4) + P * 20 + P * Co * 4
     by_sc = P * Co * 4 + P * 16 + B * G * Co * 4
+    by_floor = N * C * 4 + B * G * Co * 4   # fused-path floor: read the points once, write the canvas once
     units = [l.units for l in enc._voxel_encoder.pfn_layers]
     ins = [l.linear.in_features for l in enc._voxel_encoder.pfn_layers]
     mac_row = sum(i * u for i, u in zip(ins, units))
     fl_pfn = 2.0 * mac_row * (nk + P)
+
+    def hbm(by, t):
+        return {"ms": t, "alg_bytes": by, "gbs": by / t / 1e6, "frac_hbm": by / t / 1e6 / peak}
+
     kernels = {
-        "K1_voxelize": {"ms": t_vox, "alg_bytes": by_vox, "gbs": by_vox / t_vox / 1e6, "frac_hbm": by_vox / t_vox / 1e6 / peak},
-        "K2_pfn": {"ms": t_pfn, "alg_bytes": by_pfn, "gbs": by_pfn / t_pfn / 1e6, "frac_hbm": by_pfn / t_pfn / 1e6 / peak,
-                   "alg_tflops_upstream_equiv": fl_pfn / t_pfn / 1e9, "fp32_fma_peak_tflops": 74.4},
-        "K3_scatter": {"ms": t_sc, "alg_bytes": by_sc, "gbs": by_sc / t_sc / 1e6, "frac_hbm": by_sc / t_sc / 1e6 / peak},
+        "K1_voxelize": hbm(by_vox, t_vox),
+        "K2_pfn": {**hbm(by_pfn, t_pfn), "alg_tflops_upstream_equiv": fl_pfn / t_pfn / 1e9, "fp32_fma_peak_tflops": 74.4,
+                   "path": "tcgen05 3xTF32" if runner.lib.mbev_pfn_path(ctypes.byref(runner.params), T) == 2 else "fp32 FMA"},
+        "K3_scatter": {**hbm(by_sc, t_sc), "kernel": "k_scatter_run (registers -> st.global.cs.v4, machine-filling grid)"},
     }
-    if t_sc2 is not None:
-        kernels["K3ab_fill_empty+scatter_occupied"] = {"ms": t_sc2, "alg_bytes": by_sc, "gbs": by_sc / t_sc2 / 1e6,
-                                                       "frac_hbm": by_sc / t_sc2 / 1e6 / peak,
-                                                       "note": "two-kernel form of K3 used by the fused path; timed back to "
-                                                               "back on one stream here, K3a overlaps K2 in the step",
-                                                       "K3a_fill_empty_ms": t_fill, "K3b_scatter_occupied_ms": t_occ}
-    if t_fused is not None:
-        kernels["K2+K3_fused_kernel"] = {"ms": t_fused, "alg_bytes": by_pfn + by_sc - 2 * P * Co * 4,
-                                         "gbs": (by_pfn + by_sc - 2 * P * Co * 4) / t_fused / 1e6,
-                                         "frac_hbm": (by_pfn + by_sc - 2 * P * Co * 4) / t_fused / 1e6 / peak,
-                                         "default": bool(runner.lib.mbev_pfn_scatter_default()),
-                                         "note": "single kernel (PFN in cell order + canvas writer warps); opt-in with "
-                                                 "MBEV_FUSED_CANVAS=1"}
+    for c, tt in t_st.items():
+        kernels[f"K3_scatter_stream_{c}cta"] = {**hbm(by_sc, tt), "kernel": f"k_scatter_bulk (TMA bulk stores), {c} x 148 CTAs of 128 threads"}
+    if t_nhwc is not None:
+        kernels["K3_scatter_channels_last"] = {**hbm(by_sc, t_nhwc), "kernel": "k_scatter_nhwc ((B, ny, nx, C) canvas)"}
     # BASELINE config 4 flavour (not the headline, which is fp32): same path with a bfloat16 canvas
     bf16 = None
     if (G & 3) == 0:
@@ -424,21 +528,24 @@ def run_ours(args):
         ln = enc._layer_norm
         out_ln = torch.empty_like(runner.canvas)
 
-        def fused_ln():
+        def fused_ln(walk):
             return F_.scatter_layernorm_forward(runner.feats, runner.cell_table, runner.pillar_base, B, runner.ny,
-                                                runner.nx, ln.weight, ln.bias, ln.eps, out=out_ln)
-        if fused_ln() is not None:
-            t_ln = ev_time(fused_ln, iters, sync)
+                                                runner.nx, ln.weight, ln.bias, ln.eps, out=out_ln, walk=walk)
+        if fused_ln(_lib.LN_WALK_RUNS) is not None:
+            t_ln = ev_time(lambda: fused_ln(_lib.LN_WALK_RUNS), iters, sync)
+            t_lnf = ev_time(lambda: fused_ln(_lib.LN_WALK_FRAMES), iters, sync) if Co % 4 == 0 else None
             with torch.no_grad():
                 t_torch = ev_time(lambda: ln(runner.canvas), 2, sync)
             by_ln = B * G * Co * 4 + 2 * G * Co * 4 + P * Co * 4 + B * G * 4
-            layernorm = {"K3+LN_fused_ms": t_ln, "alg_bytes": by_ln, "gbs": by_ln / t_ln / 1e6,
-                         "frac_hbm": by_ln / t_ln / 1e6 / peak, "K3_then_torch_layernorm_ms": t_sc + t_torch,
-                         "torch_layernorm_ms": t_torch,
+            layernorm = {"K3+LN_walk_runs_ms": t_ln, "K3+LN_walk_frames_ms": t_lnf, "alg_bytes": by_ln,
+                         "default_walk": "frames" if F_.LN_WALK_DEFAULT == _lib.LN_WALK_FRAMES else "runs",
+                         "K3_then_torch_layernorm_ms": t_sc + t_torch, "torch_layernorm_ms": t_torch,
                          "note": "mbev_scatter_layernorm_forward vs K3 followed by nn.LayerNorm([C,ny,nx]) (mask_bev_encoders.py:75,92)"}
+            t_best = min(x for x in (t_ln, t_lnf) if x is not None)
+            layernorm.update({"K3+LN_fused_ms": t_best, "gbs": by_ln / t_best / 1e6, "frac_hbm": by_ln / t_best / 1e6 / peak})
             # its backward (training): out_ln stands in for the incoming gradient (any dense tensor of that shape)
             if F_.scatter_layernorm_backward_supported(B, Co, runner.ny, runner.nx):
-                stats_ln = fused_ln()[1]
+                stats_ln = fused_ln(_lib.LN_WALK_RUNS)[1]
 
                 def fused_ln_bwd():
                     return F_.scatter_layernorm_backward(out_ln, runner.feats, runner.cell_table, runner.coors,
@@ -450,45 +557,62 @@ def run_ours(args):
                                   "backward_note": "mbev_scatter_layernorm_backward: dy read once, dweight / dbias "
                                                    "written once, dfeats in pillar space"})
         del out_ln
-    dom = max(("K1_voxelize", "K2_pfn", "K3_scatter"), key=lambda k: kernels[k]["ms"])
-    roof = {"kernel": "K3_scatter (k_scatter_run<2>)", "bound": "hbm", "achieved": kernels["K3_scatter"]["gbs"], "peak": peak,
-            "unit": "GB/s", "frac": kernels["K3_scatter"]["frac_hbm"], "traffic": None, "peak_source": peak_src,
-            "launch_ms": t_sc, "dominant_by_time": dom,
-            "share_of_step": t_sc / (t_vox + t_pfn + t_sc)}
+    # the K3 form the timed step used: its stand-alone launch time is the roofline line; step_frac is the whole step
+    use_stream = (not args.serial) and stream_ok and args.scatter_ctas > 0
+    k3_key = f"K3_scatter_stream_{args.scatter_ctas}cta" if use_stream and args.scatter_ctas in t_st else "K3_scatter"
+    k3 = kernels[k3_key]
+    dom = max(("K1_voxelize", "K2_pfn", k3_key), key=lambda k: kernels[k]["ms"])
+    step_ms = ms / args.steps
+    roof = {"kernel": f"{k3_key} ({k3['kernel']})", "bound": "hbm", "achieved": k3["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": k3["frac_hbm"], "traffic": None, "peak_source": peak_src, "launch_ms": k3["ms"],
+            "dominant_by_time": dom, "share_of_serial_step": k3["ms"] / (t_vox + t_pfn + k3["ms"]),
+            "timed": "stand-alone launches (CUDA events on the launching stream, inputs resident); inside the "
+                     "pipelined step this kernel shares the SMs with K2 of the next batch",
+            "step_floor_bytes": by_floor, "step_frac": by_floor / step_ms / 1e6 / peak,
+            "step_frac_note": "fused-path HBM floor (points read once + canvas written once) / ms_per_step / peak",
+            "serial_step_frac": by_floor / (ms_serial / args.steps) / 1e6 / peak}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roof["traffic"] = json.load(open(prof)).get("K3_scatter_dram_bytes_per_launch")
+            tj = json.load(open(prof))
+            roof["traffic"] = tj.get(k3_key + "_dram_bytes_per_launch", tj.get("K3_scatter_dram_bytes_per_launch"))
         except Exception:  # noqa: BLE001
             pass
 
-    # ---- CPU baseline: oracle port on this box's host cores, bounded sample ----
+    # ---- CPU baseline: oracle port on this box's host cores, bounded samples at 1 / 6 (the reference's
+    # OMP_NUM_THREADS, train_mask_bev.py:14) / all threads ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build_c_oracle()
         cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        nfr = 2
-        tcpu, reps = time_cpu(frames[:nfr], kwargs, pfn_cpu, budget_s=15.0)
-        cpu = {"value": nfr / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{nfr} frames of this workload x {reps} reps (median); serial C voxelizer + dense torch-CPU PFN "
-                         f"(threads={cores}) + scatter"}
-    fps = world * B * args.steps / (ms * 1e-3)
-    fps2 = world * B * args.steps / (ms2 * 1e-3)
+        by_threads = {}
+        for th, nf, bud in ((1, 1, 4.0), (min(6, cores), 1, 4.0), (cores, 2, 10.0)):
+            by_threads[str(th)] = time_cpu_threads(frames, kwargs, pfn_cpu, th, min(nf, B), bud)
+        allc = by_threads[str(cores)]
+        cpu = {"value": allc["value"], "unit": UNIT, "cores": cores, "kind": "port", "by_threads": by_threads,
+               "sample": f"{allc['frames']} frames of this workload x {allc['reps']} reps (median) at {cores} threads "
+                         f"(1 frame at 1 and 6 threads); serial C voxelizer + dense torch-CPU PFN + scatter"}
+    fps = frames_all * args.steps / (ms * 1e-3)
+    fps2 = frames_all * args.steps / (ms2 * 1e-3)
+    wcfg = workload_config(args.workload, cfg, B)
+    if strong:
+        wcfg["global_batch"] = frames_all
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "serial_ms_per_step": ms_serial / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, cfg, B),
+            "ms_per_step": step_ms, "serial_ms_per_step": ms_serial / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": wcfg,
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps2, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
                     "d2h_bytes_per_step": int(counts_host.numel() * 4),
-                    "serial_value": world * B * args.steps / (ms2s * 1e-3),
-                    "what": "mbev_encode_batch_pipelined, every step: pinned host points -> H2D + K1 on a prep stream "
-                            "(two buffer sets: overlaps K2 / K3 of the previous step) -> K2,K3 -> canvas in HBM "
-                            "(where the reference's consumer reads it) + D2H of per-frame pillar counts; serial_value "
-                            "= same through mbev_encode_batch_host (copy and kernels on one stream)"},
+                    "serial_value": frames_all * args.steps / (ms2s * 1e-3),
+                    "what": "mbev_encode_batch_pipelined with HOST points, every step: pinned host points -> H2D + K1 on "
+                            "a prep stream -> K2 on a PFN stream -> K3 on the caller's stream (two buffer sets: three "
+                            "batches in flight) -> canvas in HBM, where the reference's consumer (LayerNorm / Swin) "
+                            "reads it + D2H of the per-frame pillar counts (the canvas itself, 5.2 GB per step, is NOT "
+                            "copied back); serial_value = same through mbev_encode_batch_host on one stream"},
             "roofline": roof, "kernels": kernels, "layernorm_f1": layernorm, "bf16_canvas": bf16, "cpu_baseline": cpu,
-            "pillars_per_step": P, "kept_points_per_step": nk, "points_per_step": N}
+            "train": train, "pillars_per_step": P, "kept_points_per_step": nk, "points_per_step": N}
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -507,10 +631,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti_b16")
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (default: the workload's own)")
-    ap.add_argument("--serial", action="store_true", help="value / e2e without the K1-under-K3 pipeline")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: ONE batch of the workload's size split over the ranks (BASELINE configs[2])")
+    ap.add_argument("--serial", action="store_true", help="value / e2e on one stream (no three-stage pipeline)")
+    ap.add_argument("--scatter-ctas", type=int, default=1,
+                    help="K3 of the pipelined step: CTAs per SM of the TMA-engine scatter (0: the register scatter)")
+    ap.add_argument("--train", action="store_true", help="also time the encoder's training step (always on when N > 1)")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=4, help="frames per GPU of the training step (semantic_kitti/01:28)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layernorm", action="store_true", help="skip the K3+LayerNorm (SURVEY f1) timing")
-    ap.add_argument("--overlap", action="store_true", help="two streams: K3a zero-fill under K2, then K3b (default: one stream, one-pass K3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -11,8 +11,8 @@
  *
  * Conventions
  *   - All pointers are DEVICE pointers unless the name ends in _host. The caller (PyTorch) owns every
- *     buffer, including the workspace; the library never allocates or frees device memory and keeps no
- *     global state. All work is enqueued on `stream`; no entry point synchronises.
+ *     buffer, including the workspace; the library never allocates or frees device memory, keeps no global
+ *     state and reads no environment variable. All work is enqueued on `stream`; no entry point synchronises.
  *   - Return value: 0 ok; negative = MbevStatus (bad argument / unsupported shape / workspace too small);
  *     positive = cudaError_t of a failed launch. No exceptions cross this boundary.
  *   - `stream` is a cudaStream_t passed as void* so that this header needs no CUDA include.
@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 7
+#define MBEV_ABI_VERSION 8
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -97,8 +97,11 @@ MBEV_API const char *mbev_status_string(int status);
  *   kept_idx          (pillar_capacity, T) int32 OUT: row in `points` of slot t; slots >= num_points undefined
  *   pillar_base       (batch+1) int32 OUT: first global pillar id of each frame; [batch] = total P
  * Pillars are numbered frame by frame, inside a frame in order of first appearance; slots in input order.
- * pillar_capacity must be >= min(total_points, batch*V).
+ * pillar_capacity must be >= mbev_pillar_capacity(): sum over frames of min(points of the frame, V, cells) — a
+ * frame cannot hold more pillars than it has points, than max_voxels, or than cells (host only, no GPU needed;
+ * -1 on a bad argument).
  * ---------------------------------------------------------------------------------------------- */
+MBEV_API int64_t mbev_pillar_capacity(const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo);
 MBEV_API int mbev_voxelize_workspace_bytes(const MbevGeometry *geo, int batch, int64_t total_points, size_t *bytes);
 MBEV_API int mbev_voxelize(const float *points, const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
                   int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
@@ -169,23 +172,31 @@ MBEV_API int mbev_build_cell_table(const int32_t *coors, const int32_t *num_pill
                           int batch, int ny, int nx, int32_t *cell_table, void *stream);
 MBEV_API int mbev_scatter_forward(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny, int nx,
                          float *canvas, void *stream);
+/* The same scatter with the stores handed to the TMA engine (cp.async.bulk shared -> global): a persistent grid of
+ * ctas_per_sm x 148 CTAs of 128 threads / <= 64 registers / 17 KB of shared memory. With ctas_per_sm = 1 such a CTA fits
+ * on an SM next to K2's persistent CTA, so this scatter can run UNDER the pillar feature net of the next batch
+ * (mbev_encode_batch_pipelined); stand-alone use wants ctas_per_sm >= 4. Bit-identical canvas. Needs C_out % 4 == 0,
+ * ny*nx % 4 == 0, 16-byte aligned feats / canvas (probe: mbev_scatter_stream_supported; MBEV_ERR_UNSUPPORTED otherwise). */
+MBEV_API int mbev_scatter_stream_supported(int c_out, int ny, int nx, const float *canvas);
+MBEV_API int mbev_scatter_forward_stream(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny,
+                                         int nx, float *canvas, int ctas_per_sm, void *stream);
 /* Same scatter with a bfloat16 canvas (BASELINE.json config 4; north star tolerance 1e-2 in bf16): every value is
  * the fp32 feature rounded to nearest-even bf16, so the result equals the fp32 canvas cast to bf16 bit for bit.
  * canvas_bf16: (batch, C_out, ny, nx) bfloat16; needs ny*nx % 4 == 0 and an 8-byte aligned canvas. Forward only. */
 MBEV_API int mbev_scatter_forward_bf16(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny,
                                        int nx, void *canvas_bf16, void *stream);
-/* Two-kernel form of the same scatter (G = ny*nx a multiple of 8 and a 32-byte aligned canvas; probe with
- * mbev_scatter_split_supported): fill_empty zeroes every 32-byte sector (8 cells of one channel plane) that holds
- * no pillar and needs only the cell table, so it can run on a second stream while K2 computes; occupied writes
- * the remaining sectors whole. Together they write every canvas byte exactly once. */
-MBEV_API int mbev_scatter_split_supported(int ny, int nx, const float *canvas);
-MBEV_API int mbev_scatter_fill_empty(const int32_t *cell_table, int batch, int c_out, int ny, int nx, float *canvas,
-                            void *stream);
-MBEV_API int mbev_scatter_occupied(const float *feats, const int32_t *coors, const int32_t *num_pillars_dev,
-                          int64_t pillar_capacity, const int32_t *cell_table, int batch, int c_out, int ny, int nx,
-                          float *canvas, void *stream);
+/* Channels-last canvas (north star item 3): canvas_nhwc is (batch, ny, nx, C_out) float32 — i.e. the (batch, C_out, ny,
+ * nx) tensor in torch.channels_last memory format. One pass over the cell table; every cell is one contiguous
+ * 4*C_out-byte piece (the pillar's feature row or zeros), every byte written once. Needs C_out % 4 == 0 and 16-byte
+ * aligned feats / canvas. Backward: dfeats[p, :] = dcanvas_nhwc[b, y, x, :] (rows >= the pillar count and rows whose
+ * cell the table gives to another pillar get zeros). */
+MBEV_API int mbev_scatter_forward_nhwc(const float *feats, const int32_t *cell_table, int batch, int c_out, int ny,
+                                       int nx, float *canvas_nhwc, void *stream);
 MBEV_API int mbev_scatter_backward(const float *dcanvas, const int32_t *cell_table, int batch, int c_out, int ny,
                           int nx, float *dfeats, void *stream);
+MBEV_API int mbev_scatter_backward_nhwc(const float *dcanvas_nhwc, const int32_t *cell_table, const int32_t *coors,
+                                        const int32_t *num_pillars_dev, int64_t rows, int batch, int c_out, int ny,
+                                        int nx, float *dfeats, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3+LN  scatter fused with the LayerNorm that follows it (forward and backward) — SURVEY.md §8 row f1.
@@ -197,14 +208,19 @@ MBEV_API int mbev_scatter_backward(const float *dcanvas, const int32_t *cell_tab
  *   pillar_base (batch+1) device int32 from mbev_voxelize (pillars of frame b are [pillar_base[b], pillar_base[b+1]))
  *   ln_weight, ln_bias (C, ny, nx) float32;  out (batch, C, ny, nx) float32;  stats_out (batch, 2) = mean, rstd
  * Needs ny*nx % 4 == 0 and 16-byte aligned out / weight / bias (probe: mbev_scatter_layernorm_supported).
+ * walk: the schedule of the streaming pass, same arithmetic per element (bit-identical results):
+ *   MBEV_LN_WALK_RUNS    a warp owns (256-cell run, channel chunk, ONE frame); weight / bias re-read from L2 per frame
+ *   MBEV_LN_WALK_FRAMES  a warp owns (128 cells, 4 channels) and walks the frames with weight / bias in registers
+ *                        (needs C_out % 4 == 0 and 16-byte aligned feats)
  * ---------------------------------------------------------------------------------------------- */
+enum { MBEV_LN_WALK_RUNS = 0, MBEV_LN_WALK_FRAMES = 1 };
 MBEV_API int mbev_scatter_layernorm_supported(int batch, int c_out, int ny, int nx, const float *out,
                                               const float *ln_weight, const float *ln_bias);
 MBEV_API int mbev_scatter_layernorm_workspace_bytes(int batch, size_t *bytes);
 MBEV_API int mbev_scatter_layernorm_forward(const float *feats, const int32_t *cell_table, const int32_t *pillar_base,
                                             int batch, int c_out, int ny, int nx, const float *ln_weight,
-                                            const float *ln_bias, float eps, float *out, float *stats_out,
-                                            void *workspace, size_t workspace_bytes, void *stream);
+                                            const float *ln_bias, float eps, int walk, float *out,
+                                            float *stats_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Backward of the above (autograd of mask_bev_encoders.py:91-92; the reference has no code for it, torch derives it).
  * With xh = (x - mean_b) * rstd_b, g = dout * weight, M = C*ny*nx:
@@ -227,34 +243,8 @@ MBEV_API int mbev_scatter_layernorm_backward(const float *dout, const float *fea
                                              void *stream);
 
 /* ------------------------------------------------------------------------------------------------
- * K2+K3 in one kernel (eval mode): PillarFeatureNet.forward and PointPillarsScatter.forward_batch
- * (mask_bev_encoders.py:119-123) fused — the PFN walks the pillars in cell order and writer warps of the same
- * persistent kernel stream the finished canvas region out (zeros or features, every byte once) while the next
- * pillars compute, so the HBM-bound canvas write hides under the compute-bound PFN. Needs the tcgen05 path, T <= 32,
- * ny*nx a multiple of 4 (>= 128) and a 16-byte aligned canvas: probe with mbev_pfn_scatter_supported (canvas may be
- * NULL for a shape-only probe). `cell_table` must be the table of exactly these pillars (mbev_voxelize /
- * mbev_build_cell_table); `feats` is still written (pillar_capacity, units[L-1]). Results are bit-identical to
- * mbev_pfn_forward + mbev_scatter_forward.
- * ---------------------------------------------------------------------------------------------- */
-MBEV_API int mbev_pfn_scatter_supported(const MbevPfnParams *params, int T, int batch, int ny, int nx,
-                                        const float *canvas);
-MBEV_API int mbev_pfn_scatter_default(void); /* 1 when mbev_encode_batch takes the fused kernel (MBEV_FUSED_CANVAS=1) */
-MBEV_API int mbev_pfn_scatter_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity, int batch,
-                                              int ny, int nx, size_t *bytes);
-MBEV_API int mbev_pfn_scatter_forward(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
-                                      const int32_t *coors, int64_t pillar_capacity, int T,
-                                      const MbevPfnParams *params, const int32_t *cell_table, int batch, int ny,
-                                      int nx, float *feats, float *canvas, void *workspace, size_t workspace_bytes,
-                                      void *stream);
-
-/* ------------------------------------------------------------------------------------------------
- * Fused batch entry (additive): K1 -> K2(eval) -> K3, no host sync.
+ * Fused batch entry (additive): K1 -> K2(eval) -> K3 on one stream, no host sync.
  * Equivalent to MaskBevEncoder.forward (mask_bev_encoders.py:77-91) without the trailing LayerNorm.
- * K2 and K3 run as the single fused kernel above when mbev_pfn_scatter_default() and mbev_pfn_scatter_supported() say so.
- * aux_stream: optional second stream (NULL = everything on `stream`); only used when the fused kernel is not. When given and the canvas allows the
- * two-kernel scatter, the zero-fill of the empty sectors runs on aux_stream concurrently with K2 (HBM-bound
- * writes under a compute-bound kernel); the call forks and joins with events, so the caller only ever orders
- * against `stream`.
  * ---------------------------------------------------------------------------------------------- */
 MBEV_API int mbev_encode_batch_workspace_bytes(const MbevGeometry *geo, const MbevPfnParams *params, int batch,
                                       int64_t total_points, int64_t pillar_capacity, size_t *bytes);
@@ -262,45 +252,40 @@ MBEV_API int mbev_encode_batch(const float *points, const int64_t *frame_offsets
                       const MbevGeometry *geo, const MbevPfnParams *params, int32_t *cell_table,
                       int32_t *coors, int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
                       int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
-                      size_t workspace_bytes, void *stream, void *aux_stream);
+                      size_t workspace_bytes, void *stream);
 
-/* Same, with HOST input: copies `points_host` (pinned or pageable) to `points_dev` on `stream` first.
- * This is the call bench.py's e2e leg times. */
+/* Same, with HOST input: copies `points_host` (pinned or pageable) to `points_dev` on `stream` first. */
 MBEV_API int mbev_encode_batch_host(const float *points_host, float *points_dev, const int64_t *frame_offsets_host,
                            int batch, const MbevGeometry *geo, const MbevPfnParams *params,
                            int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
                            int32_t *pillar_base, int64_t pillar_capacity, float *feats, float *canvas,
-                           void *workspace, size_t workspace_bytes, void *stream, void *aux_stream);
+                           void *workspace, size_t workspace_bytes, void *stream);
 
-/* Pipelined form of the host entry for a stream of batches: the copy of `points_host` runs on `copy_stream`
- * (first waiting for `ev_consumed`: the previous batch that read this `points_dev` buffer is done with it), then
- * `stream` waits for `ev_copied` and runs K1..K3, then records `ev_consumed`. With two `points_dev` buffers and two
- * event pairs used alternately, the H2D copy of batch i+1 overlaps the kernels of batch i; everything else (tables,
- * canvas, workspace) is ordered by `stream` as usual. Events come from mbev_event_create (cudaEventDisableTiming). */
+/* Three-stage pipeline for a stream of batches — the call bench.py times (`value` with points_host = NULL: points
+ * already resident in points_dev; `e2e` with pinned host points).
+ *   stage 1 on `prep_stream`: wait `ev_consumed` (the batch that used THIS buffer set two calls ago has left K3), copy
+ *           `points_host` to `points_dev` when points_host != NULL, K1; record `ev_ready`.
+ *   stage 2 on `pfn_stream` : wait `ev_ready`, K2 into `feats`; record `ev_feats`.
+ *   stage 3 on `stream`     : wait `ev_feats`, K3 into `canvas`; record `ev_consumed`. The canvas is ordered by the
+ *           caller's `stream` like any other output.
+ * The caller alternates TWO buffer sets (points_dev when copying, cell_table, coors, num_points, kept_idx, pillar_base,
+ * vox_workspace, feats, and the three events): K1 (+ the H2D copy) of batch i+2, K2 of batch i+1 and K3 of batch i are
+ * then in flight together. K2 is bound by the tensor / epilogue pipes and moves almost no DRAM bytes, K3 is a pure HBM
+ * write stream; with scatter_ctas_per_sm = 1 the TMA-engine scatter (mbev_scatter_forward_stream) shares every SM with
+ * K2's persistent CTA. scatter_ctas_per_sm = 0 selects mbev_scatter_forward. `canvas` and `workspace`
+ * (mbev_pfn_workspace_bytes) stay single: stage 2 is ordered by pfn_stream, stage 3 by stream. vox_workspace:
+ * mbev_voxelize_workspace_bytes. Events come from mbev_event_create (cudaEventDisableTiming). Results are bit-identical
+ * to mbev_encode_batch. */
 MBEV_API int mbev_event_create(void **event);
 MBEV_API int mbev_event_destroy(void *event);
-MBEV_API int mbev_encode_batch_host_async(const float *points_host, float *points_dev,
-                                          const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
-                                          const MbevPfnParams *params, int32_t *cell_table, int32_t *coors,
-                                          int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
-                                          int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
-                                          size_t workspace_bytes, void *stream, void *aux_stream, void *copy_stream,
-                                          void *ev_copied, void *ev_consumed);
-
-/* Two-stage pipeline for a stream of batches. Stage 1 runs on `prep_stream`: wait `ev_consumed` (the previous batch
- * that used THIS buffer set is done), copy `points_host` to `points_dev` if points_host != NULL (else the points are
- * already resident), K1; record `ev_ready`. Stage 2 runs on `stream`: wait `ev_ready`, K2, K3, record `ev_consumed`.
- * The caller alternates TWO buffer sets (points_dev when copying, cell_table, coors, num_points, kept_idx,
- * pillar_base, vox_workspace, and the event pair): K1 — latency / L2 bound — and the H2D copy of batch i+1 then
- * overlap K2 / K3 of batch i. feats, canvas and `workspace` (mbev_pfn_workspace_bytes) stay single: stage 2 is
- * ordered by `stream`. vox_workspace: mbev_voxelize_workspace_bytes. */
 MBEV_API int mbev_encode_batch_pipelined(const float *points_host, float *points_dev,
                                          const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
                                          const MbevPfnParams *params, int32_t *cell_table, int32_t *coors,
                                          int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
                                          int64_t pillar_capacity, float *feats, float *canvas, void *vox_workspace,
                                          size_t vox_workspace_bytes, void *workspace, size_t workspace_bytes,
-                                         void *stream, void *prep_stream, void *ev_ready, void *ev_consumed);
+                                         int scatter_ctas_per_sm, void *stream, void *prep_stream, void *pfn_stream,
+                                         void *ev_ready, void *ev_feats, void *ev_consumed);
 
 /* Launch counter: number of library kernels enqueued by this process since load (for bench.py's
  * `gpu_launches`). Thread-safe. */

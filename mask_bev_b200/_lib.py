@@ -13,8 +13,9 @@ MAX_BATCH = 128
 MAX_LAYERS = 4
 MAX_UNITS = 128
 MAX_POINT_DIM = 8
-ABI_VERSION = 7
+ABI_VERSION = 8
 GEMM_AUTO, GEMM_FMA, GEMM_TCGEN05 = 0, 1, 2
+LN_WALK_RUNS, LN_WALK_FRAMES = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libmask_bev_b200.so")
@@ -47,6 +48,7 @@ SIGNATURES = {
     "mbev_abi_version": (c_int, []),
     "mbev_build_info": (c_char_p, []),
     "mbev_status_string": (c_char_p, [c_int]),
+    "mbev_pillar_capacity": (c_int64, [POINTER(c_int64), c_int, _G]),
     "mbev_voxelize_workspace_bytes": (c_int, [_G, c_int, c_int64, POINTER(c_size_t)]),
     "mbev_voxelize": (c_int, [_v, POINTER(c_int64), c_int, _G, _v, _v, _v, _v, _v, c_int64, _v, c_size_t, _v]),
     "mbev_gather_voxels": (c_int, [_v, _v, _v, _v, c_int64, c_int, c_int, _v, _v]),
@@ -60,35 +62,29 @@ SIGNATURES = {
                                   POINTER(_PTRS), POINTER(_PTRS), POINTER(_PTRS), _v, c_size_t, _v]),
     "mbev_build_cell_table": (c_int, [_v, _v, c_int64, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_forward": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, _v]),
+    "mbev_scatter_stream_supported": (c_int, [c_int, c_int, c_int, _v]),
+    "mbev_scatter_forward_stream": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, c_int, _v]),
     "mbev_scatter_forward_bf16": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, _v]),
-    "mbev_scatter_split_supported": (c_int, [c_int, c_int, _v]),
-    "mbev_scatter_fill_empty": (c_int, [_v, c_int, c_int, c_int, c_int, _v, _v]),
-    "mbev_scatter_occupied": (c_int, [_v, _v, _v, c_int64, _v, c_int, c_int, c_int, c_int, _v, _v]),
+    "mbev_scatter_forward_nhwc": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, _v]),
+    "mbev_scatter_backward_nhwc": (c_int, [_v, _v, _v, _v, c_int64, c_int, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_backward": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_layernorm_supported": (c_int, [c_int, c_int, c_int, c_int, _v, _v, _v]),
     "mbev_scatter_layernorm_workspace_bytes": (c_int, [c_int, POINTER(c_size_t)]),
-    "mbev_scatter_layernorm_forward": (c_int, [_v, _v, _v, c_int, c_int, c_int, c_int, _v, _v, c_float, _v, _v, _v,
-                                               c_size_t, _v]),
+    "mbev_scatter_layernorm_forward": (c_int, [_v, _v, _v, c_int, c_int, c_int, c_int, _v, _v, c_float, c_int, _v, _v,
+                                               _v, c_size_t, _v]),
     "mbev_scatter_layernorm_backward_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "mbev_scatter_layernorm_backward_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "mbev_scatter_layernorm_backward": (c_int, [_v, _v, _v, _v, _v, c_int64, c_int, c_int, c_int, c_int, _v, _v, _v,
                                                 _v, _v, _v, c_size_t, _v]),
-    "mbev_pfn_scatter_supported": (c_int, [_P, c_int, c_int, c_int, c_int, _v]),
-    "mbev_pfn_scatter_default": (c_int, []),
-    "mbev_pfn_scatter_workspace_bytes": (c_int, [_P, c_int, c_int64, c_int, c_int, c_int, POINTER(c_size_t)]),
-    "mbev_pfn_scatter_forward": (c_int, [_v, c_int, _v, _v, _v, c_int64, c_int, _P, _v, c_int, c_int, c_int, _v, _v,
-                                         _v, c_size_t, _v]),
     "mbev_encode_batch_workspace_bytes": (c_int, [_G, _P, c_int, c_int64, c_int64, POINTER(c_size_t)]),
     "mbev_encode_batch": (c_int, [_v, POINTER(c_int64), c_int, _G, _P, _v, _v, _v, _v, _v, c_int64, _v, _v, _v,
-                                  c_size_t, _v, _v]),
+                                  c_size_t, _v]),
     "mbev_encode_batch_host": (c_int, [_v, _v, POINTER(c_int64), c_int, _G, _P, _v, _v, _v, _v, _v, c_int64, _v,
-                                       _v, _v, c_size_t, _v, _v]),
+                                       _v, _v, c_size_t, _v]),
     "mbev_event_create": (c_int, [POINTER(c_void_p)]),
     "mbev_event_destroy": (c_int, [_v]),
-    "mbev_encode_batch_host_async": (c_int, [_v, _v, POINTER(c_int64), c_int, _G, _P, _v, _v, _v, _v, _v, c_int64, _v,
-                                             _v, _v, c_size_t, _v, _v, _v, _v, _v]),
     "mbev_encode_batch_pipelined": (c_int, [_v, _v, POINTER(c_int64), c_int, _G, _P, _v, _v, _v, _v, _v, c_int64, _v, _v,
-                                            _v, c_size_t, _v, c_size_t, _v, _v, _v, _v]),
+                                            _v, c_size_t, _v, c_size_t, c_int, _v, _v, _v, _v, _v, _v]),
     "mbev_launch_count": (c_int64, []),
 }
 

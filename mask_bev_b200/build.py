@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OUT_DIR = os.path.join(_HERE, "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libmask_bev_b200.so")
 SOURCES = ["api.cu", "voxelize.cu", "scatter.cu", "layernorm.cu", "pfn.cu", "pfn_bwd.cu"]
-HEADERS = ["common.cuh", "pfn_tc.cuh", "pfn_tcw.cuh", "pfn_tcw2.cuh", "pfn_canvas.cuh", os.path.join("..", "..", "include", "mask_bev_b200.h")]
+HEADERS = ["common.cuh", "pfn_tc.cuh", "pfn_tcw2.cuh", os.path.join("..", "..", "include", "mask_bev_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

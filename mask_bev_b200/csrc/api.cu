@@ -1,4 +1,4 @@
-// C-ABI glue: version probes, launch counter, and the fused batch entry K1 -> K2(eval) -> K3.
+// C-ABI glue: version probes, launch counter, and the fused batch entries K1 -> K2(eval) -> K3.
 #include <algorithm>
 
 #include "common.cuh"
@@ -42,12 +42,6 @@ int fused_ws(const MbevGeometry *geo, const MbevPfnParams *params, int batch, in
   if (st) return st;
   st = mbev_pfn_workspace_bytes(params, geo->max_points, pillar_capacity, 0, &pb);
   if (st) return st;
-  if (mbev_pfn_scatter_supported(params, geo->max_points, batch, geo->grid[1], geo->grid[0], nullptr)) {
-    size_t fb = 0;
-    st = mbev_pfn_scatter_workspace_bytes(params, geo->max_points, pillar_capacity, batch, geo->grid[1], geo->grid[0], &fb);
-    if (st) return st;
-    pb = std::max(pb, fb);
-  }
   w->vox_off = 0;
   w->vox_bytes = vb;
   w->pfn_off = align_up(vb);
@@ -71,8 +65,9 @@ extern "C" int mbev_encode_batch(const float *points, const int64_t *frame_offse
                                  const MbevGeometry *geo, const MbevPfnParams *params, int32_t *cell_table,
                                  int32_t *coors, int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
                                  int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
-                                 size_t workspace_bytes, void *stream, void *aux_stream) {
+                                 size_t workspace_bytes, void *stream) {
   if (!geo || !params || !frame_offsets_host || !workspace || !feats || !canvas) return MBEV_ERR_BAD_ARG;
+  if (batch < 1 || batch > MBEV_MAX_BATCH) return MBEV_ERR_BAD_ARG;
   if (geo->grid[2] != 1) return MBEV_ERR_UNSUPPORTED;  // pillars: one cell along z (mask_bev_module.py:62)
   FusedWs w;
   int st = fused_ws(geo, params, batch, frame_offsets_host[batch], pillar_capacity, &w);
@@ -82,45 +77,18 @@ extern "C" int mbev_encode_batch(const float *points, const int64_t *frame_offse
   st = mbev_voxelize(points, frame_offsets_host, batch, geo, cell_table, coors, num_points, kept_idx, pillar_base,
                      pillar_capacity, ws + w.vox_off, w.vox_bytes, stream);
   if (st) return st;
-  const int c_out = params->units[params->num_layers - 1], ny = geo->grid[1], nx = geo->grid[0];
-  if (mbev_pfn_scatter_default() &&
-      mbev_pfn_scatter_supported(params, geo->max_points, batch, ny, nx, canvas))  // K2 + K3 as one kernel (opt-in)
-    return mbev_pfn_scatter_forward(points, geo->num_feats, kept_idx, num_points, coors, pillar_capacity,
-                                    geo->max_points, params, cell_table, batch, ny, nx, feats, canvas, ws + w.pfn_off,
-                                    w.pfn_bytes, stream);
-  const bool split = aux_stream && aux_stream != stream && mbev_scatter_split_supported(ny, nx, canvas);
-  cudaStream_t main_s = static_cast<cudaStream_t>(stream), aux_s = static_cast<cudaStream_t>(aux_stream);
-  cudaEvent_t e_fork = nullptr, e_join = nullptr;
-  int st_fill = MBEV_OK;
-  if (split) {  // fork: the zero-fill needs the cell table only
-    MBEV_CUDA(cudaEventCreateWithFlags(&e_fork, cudaEventDisableTiming));
-    MBEV_CUDA(cudaEventCreateWithFlags(&e_join, cudaEventDisableTiming));
-    st_fill = static_cast<int>(cudaEventRecord(e_fork, main_s));
-    if (!st_fill) st_fill = static_cast<int>(cudaStreamWaitEvent(aux_s, e_fork, 0));
-    if (!st_fill) st_fill = mbev_scatter_fill_empty(cell_table, batch, c_out, ny, nx, canvas, aux_stream);
-    if (!st_fill) st_fill = static_cast<int>(cudaEventRecord(e_join, aux_s));
-  }
   st = mbev_pfn_forward(points, geo->num_feats, kept_idx, num_points, coors, pillar_base + batch, pillar_capacity,
                         geo->max_points, params, feats, ws + w.pfn_off, w.pfn_bytes, stream);
-  if (split) {  // join (also on error, so that the two streams stay ordered); destruction is deferred by the runtime
-    const cudaError_t ej = cudaStreamWaitEvent(main_s, e_join, 0);
-    cudaEventDestroy(e_fork);
-    cudaEventDestroy(e_join);
-    if (st_fill) return st_fill;
-    if (ej != cudaSuccess) return static_cast<int>(ej);
-  }
   if (st) return st;
-  if (split)
-    return mbev_scatter_occupied(feats, coors, pillar_base + batch, pillar_capacity, cell_table, batch, c_out, ny, nx,
-                                 canvas, stream);
-  return mbev_scatter_forward(feats, cell_table, batch, c_out, ny, nx, canvas, stream);
+  return mbev_scatter_forward(feats, cell_table, batch, params->units[params->num_layers - 1], geo->grid[1],
+                              geo->grid[0], canvas, stream);
 }
 
 extern "C" int mbev_encode_batch_host(const float *points_host, float *points_dev, const int64_t *frame_offsets_host,
                                       int batch, const MbevGeometry *geo, const MbevPfnParams *params,
                                       int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
                                       int32_t *pillar_base, int64_t pillar_capacity, float *feats, float *canvas,
-                                      void *workspace, size_t workspace_bytes, void *stream, void *aux_stream) {
+                                      void *workspace, size_t workspace_bytes, void *stream) {
   if (!geo || !frame_offsets_host || batch < 1 || batch > MBEV_MAX_BATCH) return MBEV_ERR_BAD_ARG;
   const int64_t total = frame_offsets_host[batch];
   if (total > 0) {
@@ -129,10 +97,9 @@ extern "C" int mbev_encode_batch_host(const float *points_host, float *points_de
                               cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
   }
   return mbev_encode_batch(points_dev, frame_offsets_host, batch, geo, params, cell_table, coors, num_points,
-                           kept_idx, pillar_base, pillar_capacity, feats, canvas, workspace, workspace_bytes, stream, aux_stream);
+                           kept_idx, pillar_base, pillar_capacity, feats, canvas, workspace, workspace_bytes, stream);
 }
 
-// ---- pipelined host entry: the H2D copy of batch i+1 overlaps the kernels of batch i ---------------------------
 extern "C" int mbev_event_create(void **event) {
   if (!event) return MBEV_ERR_BAD_ARG;
   cudaEvent_t e = nullptr;
@@ -147,54 +114,36 @@ extern "C" int mbev_event_destroy(void *event) {
   return MBEV_OK;
 }
 
-extern "C" int mbev_encode_batch_host_async(const float *points_host, float *points_dev,
-                                            const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
-                                            const MbevPfnParams *params, int32_t *cell_table, int32_t *coors,
-                                            int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
-                                            int64_t pillar_capacity, float *feats, float *canvas, void *workspace,
-                                            size_t workspace_bytes, void *stream, void *aux_stream, void *copy_stream,
-                                            void *ev_copied, void *ev_consumed) {
-  if (!geo || !frame_offsets_host || batch < 1 || batch > MBEV_MAX_BATCH) return MBEV_ERR_BAD_ARG;
-  if (!copy_stream || !ev_copied || !ev_consumed || copy_stream == stream) return MBEV_ERR_BAD_ARG;
-  cudaStream_t cs = static_cast<cudaStream_t>(copy_stream), ms = static_cast<cudaStream_t>(stream);
-  cudaEvent_t e_copied = static_cast<cudaEvent_t>(ev_copied), e_consumed = static_cast<cudaEvent_t>(ev_consumed);
-  const int64_t total = frame_offsets_host[batch];
-  // the previous batch that read points_dev must be done with it (a never-recorded event counts as complete)
-  MBEV_CUDA(cudaStreamWaitEvent(cs, e_consumed, 0));
-  if (total > 0) {
-    if (!points_host || !points_dev) return MBEV_ERR_BAD_ARG;
-    MBEV_CUDA(cudaMemcpyAsync(points_dev, points_host, sizeof(float) * static_cast<size_t>(total) * geo->num_feats,
-                              cudaMemcpyHostToDevice, cs));
-  }
-  MBEV_CUDA(cudaEventRecord(e_copied, cs));
-  MBEV_CUDA(cudaStreamWaitEvent(ms, e_copied, 0));
-  const int st = mbev_encode_batch(points_dev, frame_offsets_host, batch, geo, params, cell_table, coors, num_points,
-                                   kept_idx, pillar_base, pillar_capacity, feats, canvas, workspace, workspace_bytes,
-                                   stream, aux_stream);
-  MBEV_CUDA(cudaEventRecord(e_consumed, ms));  // also on error, so that the copy stream never waits forever
-  return st;
-}
-
-// ---- two-stage pipeline for a stream of batches: [H2D +] K1 of batch i+1 on a prep stream under K2 / K3 of batch i ----
+// ---- three-stage pipeline for a stream of batches ---------------------------------------------------------------
+//   prep_stream : [H2D +] K1 of batch i+2      (latency / L2-bound integer work, short kernels)
+//   pfn_stream  : K2 of batch i+1              (tensor / epilogue pipes, ~no DRAM traffic, one 576-thread CTA per SM)
+//   stream      : K3 of batch i                (pure HBM write stream; the TMA-engine form needs one 128-thread CTA per SM)
+// K2 and K3 sit on different rooflines and, with scatter_ctas_per_sm = 1, fit on the same SM at the same time.
 extern "C" int mbev_encode_batch_pipelined(const float *points_host, float *points_dev,
                                            const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
                                            const MbevPfnParams *params, int32_t *cell_table, int32_t *coors,
                                            int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
                                            int64_t pillar_capacity, float *feats, float *canvas, void *vox_workspace,
                                            size_t vox_workspace_bytes, void *workspace, size_t workspace_bytes,
-                                           void *stream, void *prep_stream, void *ev_ready, void *ev_consumed) {
+                                           int scatter_ctas_per_sm, void *stream, void *prep_stream, void *pfn_stream,
+                                           void *ev_ready, void *ev_feats, void *ev_consumed) {
   if (!geo || !params || !frame_offsets_host || batch < 1 || batch > MBEV_MAX_BATCH) return MBEV_ERR_BAD_ARG;
-  if (!prep_stream || !ev_ready || !ev_consumed || prep_stream == stream || !feats || !canvas || !workspace)
+  if (!prep_stream || !pfn_stream || !ev_ready || !ev_feats || !ev_consumed || prep_stream == stream ||
+      pfn_stream == stream || prep_stream == pfn_stream || !feats || !canvas || !workspace || scatter_ctas_per_sm < 0)
     return MBEV_ERR_BAD_ARG;
   if (geo->grid[2] != 1) return MBEV_ERR_UNSUPPORTED;
-  cudaStream_t ps = static_cast<cudaStream_t>(prep_stream), ms = static_cast<cudaStream_t>(stream);
-  cudaEvent_t e_ready = static_cast<cudaEvent_t>(ev_ready), e_consumed = static_cast<cudaEvent_t>(ev_consumed);
+  cudaStream_t ps = static_cast<cudaStream_t>(prep_stream), fs = static_cast<cudaStream_t>(pfn_stream),
+               ms = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e_ready = static_cast<cudaEvent_t>(ev_ready), e_feats = static_cast<cudaEvent_t>(ev_feats),
+              e_consumed = static_cast<cudaEvent_t>(ev_consumed);
   const int64_t total = frame_offsets_host[batch];
+  const int c_out = params->units[params->num_layers - 1], ny = geo->grid[1], nx = geo->grid[0];
   size_t pb = 0;
   int st = mbev_pfn_workspace_bytes(params, geo->max_points, pillar_capacity, 0, &pb);
   if (st) return st;
   if (workspace_bytes < pb) return MBEV_ERR_WORKSPACE;
-  // stage 1 (prep stream): the previous batch that used THIS buffer set must be done with it
+  // stage 1 (prep stream): the batch that used THIS buffer set two calls ago has left K3 (a never-recorded event
+  // counts as complete)
   MBEV_CUDA(cudaStreamWaitEvent(ps, e_consumed, 0));
   if (points_host && total > 0) {
     if (!points_dev) return MBEV_ERR_BAD_ARG;
@@ -204,14 +153,20 @@ extern "C" int mbev_encode_batch_pipelined(const float *points_host, float *poin
   st = mbev_voxelize(points_dev, frame_offsets_host, batch, geo, cell_table, coors, num_points, kept_idx, pillar_base,
                      pillar_capacity, vox_workspace, vox_workspace_bytes, prep_stream);
   MBEV_CUDA(cudaEventRecord(e_ready, ps));
-  // stage 2 (main stream)
-  MBEV_CUDA(cudaStreamWaitEvent(ms, e_ready, 0));
+  // stage 2 (pfn stream): K2 into this set's feats
+  MBEV_CUDA(cudaStreamWaitEvent(fs, e_ready, 0));
   if (!st)
     st = mbev_pfn_forward(points_dev, geo->num_feats, kept_idx, num_points, coors, pillar_base + batch, pillar_capacity,
-                          geo->max_points, params, feats, workspace, workspace_bytes, stream);
-  if (!st)
-    st = mbev_scatter_forward(feats, cell_table, batch, params->units[params->num_layers - 1], geo->grid[1],
-                              geo->grid[0], canvas, stream);
+                          geo->max_points, params, feats, workspace, workspace_bytes, pfn_stream);
+  MBEV_CUDA(cudaEventRecord(e_feats, fs));
+  // stage 3 (the caller's stream): K3; the canvas is ordered by `stream` like any other output
+  MBEV_CUDA(cudaStreamWaitEvent(ms, e_feats, 0));
+  if (!st) {
+    if (scatter_ctas_per_sm > 0 && mbev_scatter_stream_supported(c_out, ny, nx, canvas))
+      st = mbev_scatter_forward_stream(feats, cell_table, batch, c_out, ny, nx, canvas, scatter_ctas_per_sm, stream);
+    else
+      st = mbev_scatter_forward(feats, cell_table, batch, c_out, ny, nx, canvas, stream);
+  }
   MBEV_CUDA(cudaEventRecord(e_consumed, ms));  // also on error, so that the prep stream never waits forever
   return st;
 }

@@ -7,14 +7,13 @@
 //   * the statistics come from the pillar features alone (every other cell is an exact zero):
 //     sum = sum_p sum_c f, sumsq likewise, N = C*ny*nx; fp64, fixed-order two-stage reduction (deterministic);
 //   * one streaming pass writes y = ((x - mean_b) * rstd_b) * w + bias with x = feature or 0, composed as in
-//     k_scatter_warp; tasks are ordered so that all frames of a run are in flight together and the run's weight /
+//     k_scatter_run; tasks are ordered so that all frames of a run are in flight together and the run's weight /
 //     bias come from HBM once and from L2 for the other frames: ~B*C*G*4 + 2*C*G*4 bytes of DRAM traffic instead of
 //     ~4*B*C*G*4 (measured history: a frame-inner loop with dependent table/feature loads per store 3.5-4.0 ms).
 // The backward (mbev_scatter_layernorm_backward, lower half of this file) streams dy once for dweight / dbias and the
 // two per-frame sums, and finishes dfeats in the compact pillar space.
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -82,7 +81,7 @@ __global__ void k_ln_finalize(const double2 *__restrict__ partial, const int bat
   stats[b] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + eps)));
 }
 
-// A warp owns (run of 256 cells, channel chunk, ONE frame) and composes x exactly as k_scatter_warp does (pillar
+// A warp owns (run of 256 cells, channel chunk, ONE frame) and composes x exactly as k_scatter_run does (pillar
 // ids in registers, feature values requested one plane ahead), multiplies by the run's weight / adds its bias and
 // streams the result out. Weight and bias of plane ch+1 are requested one plane ahead as well: they come from L2
 // (or HBM for the first frame that touches them) and were the kernel's main stall when loaded at the point of use
@@ -165,7 +164,7 @@ k_scatter_ln(const float *__restrict__ feats, const int *__restrict__ table, con
 //   dbias = sum_b dy,  dweight = sum_b dy * xh                       (dense: an empty cell has xh = -mean_b*rstd_b != 0)
 //   dx = rstd_b * (g - S1_b / M - xh * S2_b / M),  S1_b = sum g,  S2_b = sum g * xh   (sums over the whole frame)
 //   dfeats[p, :] = dx at the pillar's cell (the scatter's gather backward).
-// Pass 1 (k_ln_bwd_dense) streams dy once: a warp owns (128 cells, 4 channels) and walks the frames with dweight /
+// Pass 1 (k_ln_bwd_dense_async) streams dy once: a warp owns (128 cells, 4 channels) and walks the frames with dweight /
 // dbias in registers, so they are written once and dy / weight are read once; at occupied cells it parks g in the
 // dfeats row of the pillar (4 channels = one 16-byte piece) and it leaves per-(frame, CTA) partial sums of S1, S2
 // (fp32 over a lane's 16 terms, fp64 from there on, fixed order => run-to-run identical). Pass 2 folds the partials,
@@ -179,117 +178,9 @@ __device__ __forceinline__ float4 ld_global_v4_stream(const float *p) {
   return v;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
-k_ln_bwd_dense(const float *__restrict__ dy, const float *__restrict__ feats, const int *__restrict__ table,
-               const float2 *__restrict__ stats, const float *__restrict__ lnw, const int batch, const int C,
-               const int G, const int nchunks, const long long tasks, float *__restrict__ dw, float *__restrict__ db,
-               float *__restrict__ gfeat, double2 *__restrict__ partial) {
-  __shared__ double2 s_part[MBEV_MAX_BATCH][kThreads / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long task = static_cast<long long>(blockIdx.x) * (kThreads / 32) + warp;
-  const int run = static_cast<int>(task / nchunks);
-  const int ch0 = static_cast<int>(task - static_cast<long long>(run) * nchunks) * kBwdCh;
-  const int g0 = run * kBwdRun + 4 * lane;
-  const bool inb = task < tasks && g0 < G;  // G % 4 == 0: a lane's four cells are in or out together
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 w[kBwdCh], aw[kBwdCh], ab[kBwdCh];
-#pragma unroll
-  for (int k = 0; k < kBwdCh; ++k) {
-    w[k] = inb ? __ldg(reinterpret_cast<const float4 *>(lnw + static_cast<size_t>(ch0 + k) * G + g0)) : z;
-    aw[k] = ab[k] = z;
-  }
-  int4 pid_n = make_int4(-1, -1, -1, -1);
-  float4 d_n[kBwdCh];
-  auto request = [&](int b) {  // table row and dy of frame b (issued one frame ahead of their use)
-    pid_n = __ldg(reinterpret_cast<const int4 *>(table + static_cast<size_t>(b) * G + g0));
-#pragma unroll
-    for (int k = 0; k < kBwdCh; ++k)
-      d_n[k] = ld_global_v4_stream(dy + (static_cast<size_t>(b) * C + ch0 + k) * G + g0);
-  };
-#pragma unroll
-  for (int k = 0; k < kBwdCh; ++k) d_n[k] = z;
-  if (inb) request(0);
-  for (int b = 0; b < batch; ++b) {
-    float s1 = 0.f, s2 = 0.f;
-    if (inb) {
-      const int4 pid = pid_n;
-      float4 d[kBwdCh];
-#pragma unroll
-      for (int k = 0; k < kBwdCh; ++k) d[k] = d_n[k];
-      float4 f[4];  // f[cell] = the 4 channels of that cell's pillar (zeros for an empty cell)
-      f[0] = pid.x >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.x) * C + ch0)) : z;
-      f[1] = pid.y >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.y) * C + ch0)) : z;
-      f[2] = pid.z >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.z) * C + ch0)) : z;
-      f[3] = pid.w >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(pid.w) * C + ch0)) : z;
-      if (b + 1 < batch) request(b + 1);
-      const float2 st = __ldg(stats + b);
-      const float mean = st.x, rstd = st.y;
-      const float xk[kBwdCh][4] = {{f[0].x, f[1].x, f[2].x, f[3].x},
-                                   {f[0].y, f[1].y, f[2].y, f[3].y},
-                                   {f[0].z, f[1].z, f[2].z, f[3].z},
-                                   {f[0].w, f[1].w, f[2].w, f[3].w}};  // xk[channel][cell]
-      float4 g[kBwdCh];
-#pragma unroll
-      for (int k = 0; k < kBwdCh; ++k) {
-        float4 xh;
-        xh.x = (xk[k][0] - mean) * rstd;
-        xh.y = (xk[k][1] - mean) * rstd;
-        xh.z = (xk[k][2] - mean) * rstd;
-        xh.w = (xk[k][3] - mean) * rstd;
-        ab[k].x += d[k].x;
-        ab[k].y += d[k].y;
-        ab[k].z += d[k].z;
-        ab[k].w += d[k].w;
-        aw[k].x = fmaf(d[k].x, xh.x, aw[k].x);
-        aw[k].y = fmaf(d[k].y, xh.y, aw[k].y);
-        aw[k].z = fmaf(d[k].z, xh.z, aw[k].z);
-        aw[k].w = fmaf(d[k].w, xh.w, aw[k].w);
-        g[k].x = d[k].x * w[k].x;
-        g[k].y = d[k].y * w[k].y;
-        g[k].z = d[k].z * w[k].z;
-        g[k].w = d[k].w * w[k].w;
-        s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
-        s2 += fmaf(g[k].x, xh.x, g[k].y * xh.y) + fmaf(g[k].z, xh.z, g[k].w * xh.w);
-      }
-      if (pid.x >= 0)
-        *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.x) * C + ch0) = make_float4(g[0].x, g[1].x, g[2].x, g[3].x);
-      if (pid.y >= 0)
-        *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.y) * C + ch0) = make_float4(g[0].y, g[1].y, g[2].y, g[3].y);
-      if (pid.z >= 0)
-        *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.z) * C + ch0) = make_float4(g[0].z, g[1].z, g[2].z, g[3].z);
-      if (pid.w >= 0)
-        *reinterpret_cast<float4 *>(gfeat + static_cast<size_t>(pid.w) * C + ch0) = make_float4(g[0].w, g[1].w, g[2].w, g[3].w);
-    }
-    double a = static_cast<double>(s1), q = static_cast<double>(s2);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (lane == 0) s_part[b][warp] = make_double2(a, q);
-  }
-  if (inb) {
-#pragma unroll
-    for (int k = 0; k < kBwdCh; ++k) {
-      st_global_v4_stream(dw + static_cast<size_t>(ch0 + k) * G + g0, aw[k]);
-      st_global_v4_stream(db + static_cast<size_t>(ch0 + k) * G + g0, ab[k]);
-    }
-  }
-  __syncthreads();
-  for (int b = threadIdx.x; b < batch; b += kThreads) {
-    double a = 0.0, q = 0.0;
-#pragma unroll
-    for (int wv = 0; wv < kThreads / 32; ++wv) {
-      a += s_part[b][wv].x;
-      q += s_part[b][wv].y;
-    }
-    partial[static_cast<size_t>(b) * gridDim.x + blockIdx.x] = make_double2(a, q);
-  }
-}
-
-// Same pass with dy and the table rows staged through shared memory by cp.async (default; MBEV_LN_BWD=0 selects the
-// register-prefetch form above). ncu on k_ln_bwd_dense (profiles/r1g_lnbwd_full.txt): 16 warps per SM at 128 registers
-// with ONE frame (2 KB per warp) requested ahead = 48 % of the DRAM peak, long-scoreboard 5 per issue. Here every lane
+// dy and the table rows are staged through shared memory by cp.async. (Round 1's first form kept ONE frame ahead in
+// registers: 16 warps per SM at 128 registers = 48 % of the DRAM peak, long-scoreboard 5 per issue,
+// profiles/r1g_lnbwd_full.txt.) Here every lane
 // copies its own 16-byte pieces of the next kStages-1 frames into its own ring slots (no cross-thread sharing: the
 // only synchronisation is cp.async.wait_group), so the bytes in flight no longer cost registers; the feature rows of
 // frame b+1 are requested while frame b is processed, xh is one FMA, a run without any pillar in a frame skips the
@@ -523,9 +414,7 @@ k_ln_bwd_feats(const float *__restrict__ feats, const int *__restrict__ coors, c
   }
 }
 
-// ---- K3+LN forward, frame-walking form (OPT-IN: MBEV_LN_FWD=2; NOT yet run on a B200 — written at the end of round 1
-// after the GPU budget was spent; round 2 validates it with `MBEV_LN_FWD=2 pytest tests/test_gpu_layernorm.py` and
-// times it with bench.py before it may become the default). Same task shape as the backward's streaming pass: a warp
+// ---- K3+LN forward, frame-walking schedule (walk = MBEV_LN_WALK_FRAMES). Same task shape as the backward's streaming pass: a warp
 // owns (128 cells, 4 channels) and walks the B frames with weight and bias IN REGISTERS, so they are read from HBM once
 // and never again from L2 (k_scatter_ln re-reads them from L2 for every frame: 15 x 0.66 GB of L2 -> SM traffic per
 // kitti_b16 batch, and two 16-byte loads per plane and group in its inner loop). Table rows are requested two frames
@@ -667,11 +556,14 @@ extern "C" int mbev_scatter_layernorm_workspace_bytes(int batch, size_t *bytes) 
 
 extern "C" int mbev_scatter_layernorm_forward(const float *feats, const int32_t *cell_table, const int32_t *pillar_base,
                                               int batch, int c_out, int ny, int nx, const float *ln_weight,
-                                              const float *ln_bias, float eps, float *out, float *stats_out,
+                                              const float *ln_bias, float eps, int walk, float *out, float *stats_out,
                                               void *workspace, size_t workspace_bytes, void *stream_) {
   if (!cell_table || !pillar_base || !ln_weight || !ln_bias || !out || !stats_out || !workspace) return MBEV_ERR_BAD_ARG;
   if (!mbev_scatter_layernorm_supported(batch, c_out, ny, nx, out, ln_weight, ln_bias)) return MBEV_ERR_UNSUPPORTED;
   if (!(eps >= 0.f)) return MBEV_ERR_BAD_ARG;
+  if (walk != MBEV_LN_WALK_RUNS && walk != MBEV_LN_WALK_FRAMES) return MBEV_ERR_BAD_ARG;
+  if (walk == MBEV_LN_WALK_FRAMES && (c_out % kBwdCh || (reinterpret_cast<uintptr_t>(feats) & 15)))
+    return MBEV_ERR_UNSUPPORTED;
   const LnWs w = carve(workspace, batch);
   if (workspace_bytes < w.bytes) return MBEV_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -682,10 +574,9 @@ extern "C" int mbev_scatter_layernorm_forward(const float *feats, const int32_t 
   k_ln_finalize<<<(batch + 127) / 128, 128, 0, stream>>>(w.partial, batch, static_cast<double>(c_out) * G,
                                                         static_cast<double>(eps), stats);
   MBEV_CHECK_LAUNCH();
-  // 1 (default): k_scatter_ln, a warp per (256-cell run, channel chunk, frame); 2: k_scatter_ln_frames, a warp per
-  // (128 cells, 4 channels) walking the frames — opt-in until it has been run and timed on a B200 (see its comment)
-  static const int fwd_variant = getenv("MBEV_LN_FWD") ? atoi(getenv("MBEV_LN_FWD")) : 1;
-  if (fwd_variant == 2 && c_out % kBwdCh == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
+  // MBEV_LN_WALK_RUNS: k_scatter_ln, a warp per (256-cell run, channel chunk, frame); MBEV_LN_WALK_FRAMES:
+  // k_scatter_ln_frames, a warp per (128 cells, 4 channels) walking the frames with weight / bias in registers
+  if (walk == MBEV_LN_WALK_FRAMES) {
     const int nchunks = c_out / kBwdCh;
     const long long ftasks = static_cast<long long>((G + kBwdRun - 1) / kBwdRun) * nchunks;
     const int fblocks = static_cast<int>((ftasks + kThreads / 32 - 1) / (kThreads / 32));
@@ -741,27 +632,18 @@ extern "C" int mbev_scatter_layernorm_backward(const float *dout, const float *f
   if (workspace_bytes < w.bytes) return MBEV_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const float2 *st = reinterpret_cast<const float2 *>(stats);
-  // 1 (default): dy / table rows staged by cp.async, 5 ring stages (4 when batch > 64: two CTAs must fit an SM);
-  // 0: register prefetch of one frame
-  static const int variant = getenv("MBEV_LN_BWD") ? atoi(getenv("MBEV_LN_BWD")) : 1;
-  if (variant == 0) {
-    k_ln_bwd_dense<<<w.blocks, kThreads, 0, stream>>>(dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks,
-                                                     w.tasks, dweight, dbias, dfeats, w.partial);
+  // dy / table rows staged by cp.async, 5 ring stages (4 when batch > 64: two CTAs must fit an SM). The opt-in to
+  // > 48 KB of dynamic shared memory is per device and cheap: set on every launch (no process-global flag).
+  if (batch <= 64) {
+    MBEV_CUDA(cudaFuncSetAttribute(k_ln_bwd_dense_async<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(bwd_async_smem(5, 64))));
+    k_ln_bwd_dense_async<5><<<w.blocks, kThreads, bwd_async_smem(5, batch), stream>>>(
+        dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks, w.tasks, dweight, dbias, dfeats, w.partial);
   } else {
-    static bool attr_done = false;  // idempotent; a benign race sets the same values twice
-    if (!attr_done) {
-      MBEV_CUDA(cudaFuncSetAttribute(k_ln_bwd_dense_async<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(bwd_async_smem(5, 64))));
-      MBEV_CUDA(cudaFuncSetAttribute(k_ln_bwd_dense_async<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(bwd_async_smem(4, MBEV_MAX_BATCH))));
-      attr_done = true;
-    }
-    if (batch <= 64)
-      k_ln_bwd_dense_async<5><<<w.blocks, kThreads, bwd_async_smem(5, batch), stream>>>(
-          dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks, w.tasks, dweight, dbias, dfeats, w.partial);
-    else
-      k_ln_bwd_dense_async<4><<<w.blocks, kThreads, bwd_async_smem(4, batch), stream>>>(
-          dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks, w.tasks, dweight, dbias, dfeats, w.partial);
+    MBEV_CUDA(cudaFuncSetAttribute(k_ln_bwd_dense_async<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(bwd_async_smem(4, MBEV_MAX_BATCH))));
+    k_ln_bwd_dense_async<4><<<w.blocks, kThreads, bwd_async_smem(4, batch), stream>>>(
+        dout, feats, cell_table, st, ln_weight, batch, c_out, G, w.nchunks, w.tasks, dweight, dbias, dfeats, w.partial);
   }
   MBEV_CHECK_LAUNCH();
   k_ln_bwd_finalize<<<batch, kThreads, 0, stream>>>(w.partial, w.blocks, static_cast<double>(c_out) * G, w.msum);

@@ -21,10 +21,9 @@
 // accumulates sum / sum-of-squares in fp64, fixed reduction order => run-to-run identical), then once in
 // FULL mode.
 #include <algorithm>
-#include <cstdlib>
 
 #include "common.cuh"
-#include "pfn_canvas.cuh"
+#include "pfn_tcw2.cuh"
 
 namespace mbev {
 namespace {
@@ -522,11 +521,8 @@ int launch_pfn(const Plan &pl, const float *rows, const int32_t *kept_idx, const
                cudaStream_t stream) {
   PfnK k = pl.k;
   k.stat_layer = stat_layer;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MBEV_CUDA(cudaFuncSetAttribute(k_pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
-  }
+  // per device and cheap: set on every launch (no process-global "done" flag)
+  MBEV_CUDA(cudaFuncSetAttribute(k_pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int64_t groups = (cap + kGroup - 1) / kGroup;
   // STATS launches always use the full grid so that the partials array is fully written
   const int grid = stat_layer >= 0 ? pl.grid : static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(groups, pl.grid)));
@@ -688,54 +684,4 @@ extern "C" int mbev_pfn_forward_train(const float *rows, int C, const int32_t *k
     MBEV_CHECK_LAUNCH();
   }
   return launch_pfn(pl, rows, kept_idx, num_points, coors, num_pillars_dev, pillar_capacity, feats, -1, stream);
-}
-
-// ---- K2 + K3 fused: eval-mode PFN forward that also writes the canvas (pfn_canvas.cuh) -------------------------
-extern "C" int mbev_pfn_scatter_supported(const MbevPfnParams *params, int T, int batch, int ny, int nx,
-                                          const float *canvas) {
-  if (!params || batch < 1 || ny < 1 || nx < 1) return 0;
-  const int C = raw_point_dim(params);
-  if (select_path(params, C, T) != MBEV_GEMM_TCGEN05) return 0;
-  tc::Plan tp;
-  if (tc::make_plan(params, C, T, 1, nullptr, &tp) != MBEV_OK) return 0;
-  return tc::canvas_supported(tp, batch, ny, nx, canvas) ? 1 : 0;
-}
-
-extern "C" int mbev_pfn_scatter_default(void) { return tc::canvas_default_on() ? 1 : 0; }
-
-extern "C" int mbev_pfn_scatter_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity, int batch,
-                                                int ny, int nx, size_t *bytes) {
-  if (!bytes || !params) return MBEV_ERR_BAD_ARG;
-  if (!mbev_pfn_scatter_supported(params, T, batch, ny, nx, nullptr)) return MBEV_ERR_UNSUPPORTED;
-  tc::Plan tp;
-  const int st = tc::make_plan(params, raw_point_dim(params), T, pillar_capacity, nullptr, &tp);
-  if (st) return st;
-  tc::CanvasPlan cp;
-  tc::make_canvas_plan(tp, batch, ny, nx, pillar_capacity, nullptr, &cp);
-  *bytes = cp.ws_bytes;
-  return MBEV_OK;
-}
-
-extern "C" int mbev_pfn_scatter_forward(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
-                                        const int32_t *coors, int64_t pillar_capacity, int T,
-                                        const MbevPfnParams *params, const int32_t *cell_table, int batch, int ny,
-                                        int nx, float *feats, float *canvas, void *workspace, size_t workspace_bytes,
-                                        void *stream_) {
-  if (!params || !num_points || !coors || !cell_table || !feats || !canvas || !workspace) return MBEV_ERR_BAD_ARG;
-  if (!mbev_pfn_scatter_supported(params, T, batch, ny, nx, canvas)) return MBEV_ERR_UNSUPPORTED;
-  if (C != raw_point_dim(params)) return MBEV_ERR_BAD_ARG;
-  if (pillar_capacity > 0 && !rows) return MBEV_ERR_BAD_ARG;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  tc::Plan tp;
-  int st = tc::make_plan(params, C, T, pillar_capacity, workspace, &tp);
-  if (st) return st;
-  tc::CanvasPlan cp;
-  tc::make_canvas_plan(tp, batch, ny, nx, pillar_capacity, workspace, &cp);
-  if (workspace_bytes < cp.ws_bytes) return MBEV_ERR_WORKSPACE;
-  for (int l = 0; l < tp.k.L; ++l) {
-    if (!params->scale[l] || !params->shift[l]) return MBEV_ERR_BAD_ARG;
-    tp.k.scale[l] = params->scale[l];
-    tp.k.shift[l] = params->shift[l];
-  }
-  return tc::launch_canvas(params, tp, cp, rows, kept_idx, num_points, coors, cell_table, feats, canvas, stream);
 }

@@ -16,7 +16,8 @@
 //   per layer  l = L-1..0 :  k_dz (arg-max routing + ReLU mask + BN sums) ; k_bn_finalize (dgamma, dbeta) ;
 //                            k_dy ; dW_l = dY^T X_l (split-K, fixed-order reduce) ; dX = dY W_l
 // Every reduction has a fixed order => run-to-run identical gradients. fp32 FMA throughout (1e-5 parity).
-#include <cstdlib>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -400,16 +401,26 @@ k_dz(const float *__restrict__ Y, const int U, const float *__restrict__ scale, 
   }
 }
 
-__global__ void k_bn_finalize(const double *__restrict__ partials, const int nblocks, const int U,
-                              const int *__restrict__ num_pillars, const int T, const int train,
-                              float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ c12) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per unit: lane j sums partials j, j+32, ... in that order, then a fixed xor-shuffle tree folds the 32 lane
+// sums — deterministic, and ~32x shorter than one thread walking all kDzBlocks partials (the serial form was the top
+// user kernel of a training step: ~99 us per launch).
+__global__ void __launch_bounds__(256)
+k_bn_finalize(const double *__restrict__ partials, const int nblocks, const int U, const int *__restrict__ num_pillars,
+              const int T, const int train, float *__restrict__ dgamma, float *__restrict__ dbeta,
+              float *__restrict__ c12) {
+  const int u = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (u >= U) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = lane; b < nblocks; b += 32) {
     s1 += partials[(static_cast<size_t>(b) * 2 + 0) * U + u];
     s2 += partials[(static_cast<size_t>(b) * 2 + 1) * U + u];
   }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if (lane) return;
   dbeta[u] = static_cast<float>(s1);
   dgamma[u] = static_cast<float>(s2);
   const double M = static_cast<double>(*num_pillars) * T;
@@ -468,8 +479,7 @@ BwdWs carve_bwd(void *ws, const MbevPfnParams *p, int64_t cap, int64_t rows_cap)
 }
 
 int launch_gemm(const GemmK &g, int m_tiles_cap, int n, int splits, cudaStream_t stream) {
-  static const bool old_gemm = getenv("MBEV_BWD_GEMM64") != nullptr;  // developer knob: the 64 x 64 kernel everywhere
-  if (!old_gemm && splits == 1 && g.sAk == 1 && g.m_dev != nullptr && (g.sBn == 1 || g.sBk == 1)) {
+  if (splits == 1 && g.sAk == 1 && g.m_dev != nullptr && (g.sBn == 1 || g.sBk == 1)) {
     const int tiles = std::max(1, std::min((m_tiles_cap + 1) / 2, kNumSMs * 4));
     if (n > 64) {
       k_gemm_rows<128><<<dim3(tiles, (n + 127) / 128), 256, 0, stream>>>(g);
@@ -585,7 +595,7 @@ extern "C" int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_i
         w.Y[l], U, SC(l), SH(l), MEAN(l), VAR(l), eps, w.Mx[l], dfeats, (l == L - 1) ? nullptr : w.DX,
         (l == L - 1) ? 0 : params->in_dim[l + 1], w.row_off, num_pillars_dev, w.DZ, w.partials);
     MBEV_CHECK_LAUNCH();
-    k_bn_finalize<<<(U + 127) / 128, 128, 0, stream>>>(w.partials, kDzBlocks, U, num_pillars_dev, T, train, dgamma[l],
+    k_bn_finalize<<<(U + 7) / 8, 256, 0, stream>>>(w.partials, kDzBlocks, U, num_pillars_dev, T, train, dgamma[l],
                                                        dbeta[l], w.c12);
     MBEV_CHECK_LAUNCH();
     k_dy<<<ew_blocks, kThreads, 0, stream>>>(w.Y[l], U, SC(l), MEAN(l), VAR(l), eps, w.c12, w.row_w, w.num_rows, w.DZ);

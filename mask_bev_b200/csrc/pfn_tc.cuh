@@ -42,6 +42,12 @@ constexpr int kScrPitch = 33;   // transposition scratch [128][33] floats
 constexpr int kDecoPitch = 20;  // decorated layer-0 input staging [128][20] floats (float4-aligned, conflict-free)
 constexpr int kPtPitch = 8;
 constexpr int kK0Pad = 16;
+// Layer-0 input columns in TENSOR MEMORY use a fixed "wide" order so that the decoration needs only statically
+// indexed registers whatever the configuration: [0,3) xyz (legacy: the in-place centre offset), [3,8) the other raw
+// point features, [8,11) cluster offset, [11,14) centre offset, [14] distance, [15] zero. k_prep_weights_tc puts the
+// Linear weight column of upstream's dense order (raw | cluster | centre | distance) at its wide slot and zeros at
+// the unused ones, so the products are the same numbers.
+constexpr int kWideExtra = 3, kWideCluster = 8, kWideCentre = 11, kWideDist = 14;
 constexpr uint32_t kColAH = 0, kColAL = 128, kColD = 256, kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -59,11 +65,10 @@ struct Kargs {
   int cluster, vcenter, dist, legacy, vcd;
   float vx, vy, vz, xo, yo, zo;
   int um;
-  uint32_t o_scr, o_ss, o_tab, o_bar, o_zero;  // byte offsets in dynamic shared memory
+  uint32_t o_scr, o_ss, o_tab, o_bar;  // byte offsets in dynamic shared memory
   int smem_bytes;
   int stat_layer;    // -1: full forward; s: accumulate the statistics of layer s and stop
   double *partials;  // (gridDim.x, 2, um)
-  int dbg;           // profiling knobs (MBEV_TC_DBG, developer only): results are wrong when non-zero
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -534,23 +539,22 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
                       ez = __fsub_rn(z, s_ctr[pl * 4 + 2]);
           const bool alias = k.vcenter && k.legacy;  // legacy: centre offset written in place over xyz
           const float r0 = alias ? ex : x, r1 = alias ? ey : y, r2 = (alias && k.vcd > 2) ? ez : z;  // 2-channel centre: z stays raw
-          int d = 0;
-          xd[d++] = r0;
-          xd[d++] = r1;
-          xd[d++] = r2;
-          for (int c = 3; c < k.C; ++c) xd[d++] = pp[c];
+          xd[0] = r0;
+          xd[1] = r1;
+          xd[2] = r2;
+          for (int c = 3; c < k.C; ++c) xd[kWideExtra + c - 3] = pp[c];
           if (k.cluster) {
-            xd[d++] = __fsub_rn(x, s_mean[pl * 4 + 0]);
-            xd[d++] = __fsub_rn(y, s_mean[pl * 4 + 1]);
-            xd[d++] = __fsub_rn(z, s_mean[pl * 4 + 2]);
+            xd[kWideCluster + 0] = __fsub_rn(x, s_mean[pl * 4 + 0]);
+            xd[kWideCluster + 1] = __fsub_rn(y, s_mean[pl * 4 + 1]);
+            xd[kWideCluster + 2] = __fsub_rn(z, s_mean[pl * 4 + 2]);
           }
           if (k.vcenter) {
-            xd[d++] = ex;
-            xd[d++] = ey;
-            if (k.vcd > 2) xd[d++] = ez;
+            xd[kWideCentre + 0] = ex;
+            xd[kWideCentre + 1] = ey;
+            if (k.vcd > 2) xd[kWideCentre + 2] = ez;
           }
           if (k.dist)
-            xd[d++] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)), __fmul_rn(r2, r2)));
+            xd[kWideDist] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)), __fmul_rn(r2, r2)));
         }
         uint32_t hi[16], lo[16];
 #pragma unroll
@@ -727,9 +731,11 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
 }
 
 // nn.Linear weights (U_l, K_l) -> hi / lo TF32 images in the UMMA K-major no-swizzle layout:
-// 16-byte unit (kchunk = kk/4, u) at ((kchunk * U + u) * 4 + kk%4) floats; K zero-padded to Kp.
+// 16-byte unit (kchunk = kk/4, u) at ((kchunk * U + u) * 4 + kk%4) floats; K zero-padded to Kp; layer 0 in the wide
+// column order (kWide*).
 struct PrepArgs {
   int L;
+  int map0[kK0Pad];  // wide layer-0 slot -> Linear.weight column of layer 0, -1 = unused slot (zero column)
   int K[MBEV_MAX_LAYERS], Kp[MBEV_MAX_LAYERS], U[MBEV_MAX_LAYERS];
   const float *w[MBEV_MAX_LAYERS];
   float *hi[MBEV_MAX_LAYERS], *lo[MBEV_MAX_LAYERS];
@@ -741,7 +747,8 @@ __global__ void k_prep_weights_tc(const PrepArgs a) {
   const int K = a.K[l], Kp = a.Kp[l], U = a.U[l];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < U * Kp; i += gridDim.x * blockDim.x) {
     const int u = i / Kp, kk = i - u * Kp;
-    const float v = kk < K ? __ldg(a.w[l] + static_cast<size_t>(u) * K + kk) : 0.f;
+    const int col = (l == 0) ? a.map0[kk] : (kk < K ? kk : -1);
+    const float v = col >= 0 ? __ldg(a.w[l] + static_cast<size_t>(u) * K + col) : 0.f;
     uint32_t hi, lo;
     split_tf32(v, hi, lo);
     const int idx = (((kk >> 2) * U + u) << 2) + (kk & 3);
@@ -781,7 +788,16 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capaci
   k.vcd = p->voxel_center_dims;
   if (k.vcenter && k.vcd != 2 && k.vcd != 3) return MBEV_ERR_BAD_ARG;
   k.D0 = C + (k.cluster ? 3 : 0) + (k.vcenter ? k.vcd : 0) + (k.dist ? 1 : 0);
-  if (k.D0 > kK0Pad) return MBEV_ERR_UNSUPPORTED;
+  static_assert(kWideExtra + MBEV_MAX_POINT_DIM - 3 <= kWideCluster && kWideDist < kK0Pad, "wide layer-0 layout");
+  for (int j = 0; j < kK0Pad; ++j) pa.map0[j] = -1;
+  {
+    int d = 0;
+    for (int j = 0; j < 3; ++j) pa.map0[j] = d++;
+    for (int j = 3; j < C; ++j) pa.map0[kWideExtra + j - 3] = d++;
+    if (k.cluster) for (int j = 0; j < 3; ++j) pa.map0[kWideCluster + j] = d++;
+    if (k.vcenter) for (int j = 0; j < k.vcd; ++j) pa.map0[kWideCentre + j] = d++;
+    if (k.dist) pa.map0[kWideDist] = d++;
+  }
   k.vx = p->vx; k.vy = p->vy; k.vz = p->vz;
   k.xo = p->x_offset; k.yo = p->y_offset; k.zo = p->z_offset;
   int um = 0;
@@ -812,7 +828,7 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capaci
   k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
   k.o_tab = o; o += (kPcap + (kPcap + 4) + kRows + kRows + kRows + kPcap * 4 + kPcap * 4 + 8) * 4;
   o = (o + 15u) & ~15u;
-  k.o_bar = o; o += 40 * 8 + 8;  // k_pfn_tc uses 20 barriers, k_pfn_tcw up to 36
+  k.o_bar = o; o += kNumBars * 8 + 8;
   k.smem_bytes = static_cast<int>(o);
   if (k.smem_bytes > kSmemLimit) return MBEV_ERR_UNSUPPORTED;
   // workspace: weight image, per-CTA statistic partials

@@ -16,7 +16,7 @@
 //   k_emit   : kept points write their slot; heads write coors / num_points and turn the cell table entry
 //              into the global pillar id (the scatter's inverse map / occupancy mask).
 // All ordering comes from row indices, never from atomic arrival order, so results are bit-reproducible.
-#include <cstdlib>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -362,6 +362,16 @@ int check_geo(const MbevGeometry *geo, int batch) {
 
 using namespace mbev;
 
+extern "C" int64_t mbev_pillar_capacity(const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo) {
+  if (!frame_offsets_host || !geo || batch < 1) return -1;
+  const int64_t cells = static_cast<int64_t>(geo->grid[0]) * geo->grid[1] * geo->grid[2];
+  const int64_t per_frame = std::min<int64_t>(geo->max_voxels, cells);
+  int64_t cap = 0;
+  for (int f = 0; f < batch; ++f)
+    cap += std::min<int64_t>(std::max<int64_t>(frame_offsets_host[f + 1] - frame_offsets_host[f], 0), per_frame);
+  return cap;
+}
+
 extern "C" int mbev_voxelize_workspace_bytes(const MbevGeometry *geo, int batch, int64_t total_points,
                                              size_t *bytes) {
   if (!bytes || total_points < 0) return MBEV_ERR_BAD_ARG;
@@ -392,9 +402,9 @@ extern "C" int mbev_voxelize(const float *points, const int64_t *frame_offsets_h
   const int total = fr.off[batch];
   if (total > 0 && !points) return MBEV_ERR_BAD_ARG;
   const GeoK g = make_geok(*geo);
-  // a frame cannot hold more pillars than points, than V, or than cells
-  const int64_t need_cap = std::min<int64_t>(total, static_cast<int64_t>(batch) * std::min(g.V, g.cells));
-  if (pillar_capacity < need_cap) return MBEV_ERR_BAD_ARG;
+  // a frame cannot hold more pillars than it has points, than V, or than cells: capacity = sum over frames
+  // (the bound the Python host side sizes its buffers with, functional.pillar_capacity)
+  if (pillar_capacity < mbev_pillar_capacity(frame_offsets_host, batch, geo)) return MBEV_ERR_BAD_ARG;
   const VoxWs w = carve(workspace, batch, total);
   if (workspace_bytes < w.bytes) return MBEV_ERR_WORKSPACE;
 

@@ -93,11 +93,37 @@ class FrontEndDataParallel:
         loss(canvas).backward()
         dp.reduce_gradients()
         optimizer.step()
+
+    overlap=True: the large gradients (the two LayerNorm tensors, `2*C*ny*nx` floats) are all-reduced from a
+    post-accumulate-grad hook, i.e. the moment the fused scatter+LayerNorm backward has produced them — NCCL then
+    moves them over NVLink while the PFN backward (K2', which does not depend on them) still computes;
+    `reduce_gradients` sends the small bucket and waits for everything. Same result as overlap=False.
     """
 
-    def __init__(self, encoder: torch.nn.Module, group=None):
+    def __init__(self, encoder: torch.nn.Module, group=None, overlap: bool = False,
+                 small_bucket_bytes: int = SMALL_BUCKET_BYTES):
         self.encoder = encoder
         self.group = group
+        self.overlap = overlap
+        self.small_bucket_bytes = small_bucket_bytes
+        self._pending = []   # (parameter, work handle) of hook-issued collectives
+        self._hooks = []
+        if overlap:
+            for p in encoder.parameters():
+                if p.requires_grad and p.numel() * p.element_size() >= small_bucket_bytes:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if self.world == 1 or p.grad is None:
+            return
+        if not p.grad.is_contiguous():
+            p.grad = p.grad.contiguous()
+        self._pending.append((p, dist.all_reduce(p.grad, group=self.group, async_op=True)))
+
+    def close(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
 
     @property
     def world(self) -> int:
@@ -117,7 +143,22 @@ class FrontEndDataParallel:
         return self.encoder([frames[i] for i in owned]), owned
 
     def reduce_gradients(self, average: bool = True) -> AllreduceReport:
-        return allreduce_gradients(self.encoder.parameters(), group=self.group, average=average)
+        if not self.overlap:
+            return allreduce_gradients(self.encoder.parameters(), group=self.group, average=average,
+                                       small_bucket_bytes=self.small_bucket_bytes)
+        done = {id(p) for p, _ in self._pending}
+        rest = [p for p in self.encoder.parameters() if p.requires_grad and id(p) not in done]
+        rep = allreduce_gradients(rest, group=self.group, average=average, small_bucket_bytes=self.small_bucket_bytes)
+        world = self.world
+        n_inplace = 0
+        for p, work in self._pending:
+            work.wait()
+            if average:
+                p.grad.mul_(1.0 / world)
+            n_inplace += p.grad.numel()
+        n_hooked = len(self._pending)
+        self._pending = []
+        return AllreduceReport(world, rep.collectives + n_hooked, rep.bucket_floats, rep.inplace_floats + n_inplace)
 
 
 def gradient_bytes(encoder: torch.nn.Module) -> int:

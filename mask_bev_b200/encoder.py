@@ -12,7 +12,6 @@ The reference file itself also imports unchanged against this package through th
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Union
 
@@ -92,16 +91,18 @@ class MaskBevEncoder(nn.Module):
         self._layer_norm = nn.LayerNorm([self._out_features, *out_shape], eps=1e-3)
         self.apply_layer_norm = True
         # with autograd on: scatter + LayerNorm as the fused forward / backward pair (False: K3, then torch's LayerNorm)
-        self.fuse_layer_norm_autograd = os.environ.get("MBEV_FUSED_LN_AUTOGRAD", "1") != "0"
+        self.fuse_layer_norm_autograd = True
         gs = self._voxel_layer.grid_size
         if int(gs[0]) != self._num_voxel_x or int(gs[1]) != self._num_voxel_y or int(gs[2]) != 1:
             raise MbevError(f"voxel grid {gs.tolist()} disagrees with the canvas {out_shape} (SURVEY.md a1)")
 
     # -- fused path -------------------------------------------------------------------------------------
     def encode_batch(self, point_clouds: List[torch.Tensor], return_aux: bool = False,
-                     canvas_dtype: torch.dtype = torch.float32):
+                     canvas_dtype: torch.dtype = torch.float32, channels_last: bool = False):
         """K1 -> K2 -> K3 for the whole batch: (B, C_out, ny, nx) canvas, before the LayerNorm.
-        canvas_dtype=torch.bfloat16 (inference only): the PFN still computes in fp32, the canvas is written in bf16."""
+        canvas_dtype=torch.bfloat16 (inference only): the PFN still computes in fp32, the canvas is written in bf16.
+        channels_last=True: the same tensor in torch.channels_last memory format (each pillar's features are one
+        contiguous row; north star item 3), forward and backward."""
         if len(point_clouds) == 0:
             raise MbevError("empty batch")
         if canvas_dtype != torch.float32:
@@ -110,21 +111,15 @@ class MaskBevEncoder(nn.Module):
         pts, sizes = _as_points(point_clouds)
         geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
         vb = F_.voxelize_batch(pts, sizes, geo)
-        fused = None
+        feats = self._voxel_encoder.apply_rows(pts, vb.kept_idx, vb.num_points, vb.coors, vb.num_pillars_dev,
+                                               vb.capacity, geo.max_points)
         if canvas_dtype == torch.float32:
-            fused = self._voxel_encoder.apply_rows_canvas(pts, vb.kept_idx, vb.num_points, vb.coors, vb.capacity,
-                                                          geo.max_points, vb.cell_table, len(sizes),
-                                                          self._num_voxel_y, self._num_voxel_x)
-        if fused is not None:  # inference: K2 + K3 in one kernel
-            feats, canvas = fused
+            canvas = scatter_with_table(feats, vb.cell_table, len(sizes), self._num_voxel_y, self._num_voxel_x,
+                                        channels_last=channels_last, coors=vb.coors,
+                                        num_pillars_dev=vb.num_pillars_dev)
         else:
-            feats = self._voxel_encoder.apply_rows(pts, vb.kept_idx, vb.num_points, vb.coors, vb.num_pillars_dev,
-                                                   vb.capacity, geo.max_points)
-            if canvas_dtype == torch.float32:
-                canvas = scatter_with_table(feats, vb.cell_table, len(sizes), self._num_voxel_y, self._num_voxel_x)
-            else:
-                canvas = F_.scatter_forward(feats.detach(), vb.cell_table, len(sizes), self._num_voxel_y,
-                                            self._num_voxel_x, dtype=canvas_dtype)
+            canvas = F_.scatter_forward(feats.detach(), vb.cell_table, len(sizes), self._num_voxel_y,
+                                        self._num_voxel_x, dtype=canvas_dtype)
         if return_aux:
             return canvas, EncodeAux(vb.coors, vb.num_points, vb.kept_idx, vb.pillar_base, vb.cell_table, feats, sizes)
         return canvas

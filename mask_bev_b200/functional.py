@@ -60,8 +60,13 @@ def _offsets(frame_sizes: Sequence[int]):
 
 
 def pillar_capacity(geo: MbevGeometry, frame_sizes: Sequence[int]) -> int:
-    cells = geo.grid[0] * geo.grid[1] * geo.grid[2]
-    return max(1, sum(min(int(s), geo.max_voxels, cells) for s in frame_sizes))
+    """Rows every per-pillar buffer of a batch needs: sum over frames of min(points, max_voxels, cells) — the one
+    bound the library checks (mbev_pillar_capacity), at least 1 so that empty batches still own valid pointers."""
+    off, _ = _offsets(frame_sizes)
+    cap = int(_lib.load().mbev_pillar_capacity(off, len(frame_sizes), ctypes.byref(geo)))
+    if cap < 0:
+        raise _lib.MbevError("pillar_capacity: bad geometry or frame sizes")
+    return max(1, cap)
 
 
 @dataclass
@@ -208,46 +213,6 @@ def pfn_forward_eval(rows, kept_idx, num_points, coors, num_pillars_dev, capacit
     return feats
 
 
-def pfn_scatter_default() -> bool:
-    """Does the library route the fused batch entry through the single K2+K3 kernel (MBEV_FUSED_CANVAS=1)?"""
-    return bool(_lib.load().mbev_pfn_scatter_default())
-
-
-def pfn_scatter_supported(cfg: PfnConfig, T: int, batch: int, ny: int, nx: int) -> bool:
-    """Can K2 and K3 run as the single fused kernel (mbev_pfn_scatter_forward) for this stack / canvas shape?"""
-    lib = _lib.load()
-    L = len(cfg.units)
-    params = _pfn_struct(cfg, [None] * L, None, None)
-    return bool(lib.mbev_pfn_scatter_supported(ctypes.byref(params), T, batch, ny, nx, ctypes.c_void_p(None)))
-
-
-def pfn_scatter_forward_eval(rows, kept_idx, num_points, coors, capacity, T, cfg: PfnConfig, weights, scales, shifts,
-                             cell_table, batch: int, ny: int, nx: int, canvas_out: Optional[torch.Tensor] = None):
-    """Eval-mode PFN forward + scatter in one kernel: returns (feats (capacity, C_out), canvas (B, C_out, ny, nx))."""
-    lib = _lib.load()
-    _need_cuda(rows, "features")
-    dev = rows.device
-    weights = [_f32c(w) for w in weights]
-    scales = [_f32c(s) for s in scales]
-    shifts = [_f32c(s) for s in shifts]
-    params = _pfn_struct(cfg, weights, scales, shifts)
-    nbytes = ctypes.c_size_t()
-    check(lib.mbev_pfn_scatter_workspace_bytes(ctypes.byref(params), T, capacity, batch, ny, nx, ctypes.byref(nbytes)),
-          "pfn_scatter_workspace_bytes")
-    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
-    feats = torch.empty((capacity, cfg.units[-1]), dtype=torch.float32, device=dev)
-    canvas = canvas_out if canvas_out is not None else torch.empty((batch, cfg.units[-1], ny, nx), dtype=torch.float32,
-                                                                   device=dev)
-    if canvas.shape != (batch, cfg.units[-1], ny, nx) or canvas.dtype != torch.float32 or not canvas.is_contiguous():
-        raise _lib.MbevError("canvas_out must be a contiguous float32 (B, C_out, ny, nx) tensor")
-    with torch.cuda.device(dev):
-        check(lib.mbev_pfn_scatter_forward(ptr(rows), cfg.in_channels, ptr(kept_idx), ptr(num_points), ptr(coors),
-                                           capacity, T, ctypes.byref(params), ptr(cell_table), batch, ny, nx,
-                                           ptr(feats), ptr(canvas), ptr(ws), ws.numel(), _stream()),
-              "pfn_scatter_forward")
-    return feats, canvas
-
-
 def pfn_forward_train(rows, kept_idx, num_points, coors, num_pillars_dev, capacity, T, cfg: PfnConfig,
                       weights, gammas, betas):
     """Returns (feats, scale_shift (L,2,MAX_UNITS), batch_stats (L,2,MAX_UNITS) = mean / biased var)."""
@@ -317,20 +282,33 @@ def build_cell_table(coors: torch.Tensor, num_pillars_dev: torch.Tensor, capacit
 
 
 def scatter_forward(feats: torch.Tensor, cell_table: torch.Tensor, batch: int, ny: int, nx: int,
-                    out: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """K3. dtype=torch.bfloat16 writes a bf16 canvas (= the fp32 canvas rounded to nearest-even; forward only)."""
+                    out: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.float32,
+                    stream_ctas_per_sm: int = 0, channels_last: bool = False) -> torch.Tensor:
+    """K3. dtype=torch.bfloat16 writes a bf16 canvas (= the fp32 canvas rounded to nearest-even; forward only).
+    stream_ctas_per_sm > 0: the TMA-engine form (mbev_scatter_forward_stream), same bits.
+    channels_last: the (B, C, ny, nx) result is laid out (B, ny, nx, C) in memory (torch.channels_last)."""
     lib = _lib.load()
     _need_cuda(feats, "voxel_features")
     C = feats.shape[1]
     if dtype not in (torch.float32, torch.bfloat16):
         raise _lib.MbevError(f"canvas dtype {dtype} is not supported (float32 or bfloat16)")
-    canvas = out if out is not None else torch.empty((batch, C, ny, nx), dtype=dtype, device=feats.device)
-    if canvas.dtype != dtype or tuple(canvas.shape) != (batch, C, ny, nx) or not canvas.is_contiguous():
-        raise _lib.MbevError("out must be a contiguous (B, C, ny, nx) tensor of the requested dtype")
+    mf = torch.channels_last if channels_last else torch.contiguous_format
+    canvas = out if out is not None else torch.empty((batch, C, ny, nx), dtype=dtype, device=feats.device,
+                                                     memory_format=mf)
+    if canvas.dtype != dtype or tuple(canvas.shape) != (batch, C, ny, nx) or not canvas.is_contiguous(memory_format=mf):
+        raise _lib.MbevError("out must be a (B, C, ny, nx) tensor of the requested dtype and memory format")
     with torch.cuda.device(feats.device):
-        if dtype == torch.bfloat16:
+        if channels_last:
+            if dtype != torch.float32:
+                raise _lib.MbevError("the channels-last canvas is float32 only")
+            check(lib.mbev_scatter_forward_nhwc(ptr(feats), ptr(cell_table), batch, C, ny, nx, ptr(canvas), _stream()),
+                  "scatter_forward_nhwc")
+        elif dtype == torch.bfloat16:
             check(lib.mbev_scatter_forward_bf16(ptr(feats), ptr(cell_table), batch, C, ny, nx, ptr(canvas), _stream()),
                   "scatter_forward_bf16")
+        elif stream_ctas_per_sm > 0:
+            check(lib.mbev_scatter_forward_stream(ptr(feats), ptr(cell_table), batch, C, ny, nx, ptr(canvas),
+                                                  int(stream_ctas_per_sm), _stream()), "scatter_forward_stream")
         else:
             check(lib.mbev_scatter_forward(ptr(feats), ptr(cell_table), batch, C, ny, nx, ptr(canvas), _stream()),
                   "scatter_forward")
@@ -339,9 +317,10 @@ def scatter_forward(feats: torch.Tensor, cell_table: torch.Tensor, batch: int, n
 
 def scatter_layernorm_forward(feats: torch.Tensor, cell_table: torch.Tensor, pillar_base: torch.Tensor, batch: int,
                               ny: int, nx: int, weight: torch.Tensor, bias: torch.Tensor, eps: float,
-                              out: Optional[torch.Tensor] = None):
+                              out: Optional[torch.Tensor] = None, walk: Optional[int] = None):
     """K3 + LayerNorm([C, ny, nx]) in one pass (forward only). Returns (out (B, C, ny, nx), stats (B, 2) = mean,
-    rstd), or None when the shapes / alignment do not fit the fused kernel (the caller then runs K3 + torch LN)."""
+    rstd), or None when the shapes / alignment do not fit the fused kernel (the caller then runs K3 + torch LN).
+    walk: _lib.LN_WALK_RUNS / LN_WALK_FRAMES (None: LN_WALK_DEFAULT where it applies)."""
     lib = _lib.load()
     _need_cuda(feats, "voxel_features")
     dev = feats.device
@@ -354,14 +333,22 @@ def scatter_layernorm_forward(feats: torch.Tensor, cell_table: torch.Tensor, pil
     if not lib.mbev_scatter_layernorm_supported(batch, C, ny, nx, ptr(out), ptr(weight), ptr(bias)):
         return None
     stats = torch.empty((batch, 2), dtype=torch.float32, device=dev)
+    if walk is None:
+        walk = LN_WALK_DEFAULT
+        if walk == _lib.LN_WALK_FRAMES and (C % 4 or feats.data_ptr() % 16):
+            walk = _lib.LN_WALK_RUNS
     nbytes = ctypes.c_size_t()
     check(lib.mbev_scatter_layernorm_workspace_bytes(batch, ctypes.byref(nbytes)), "scatter_layernorm_workspace_bytes")
     ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         check(lib.mbev_scatter_layernorm_forward(ptr(feats), ptr(cell_table), ptr(pillar_base), batch, C, ny, nx,
-                                                 ptr(weight), ptr(bias), float(eps), ptr(out), ptr(stats), ptr(ws),
-                                                 ws.numel(), _stream()), "scatter_layernorm_forward")
+                                                 ptr(weight), ptr(bias), float(eps), int(walk), ptr(out), ptr(stats),
+                                                 ptr(ws), ws.numel(), _stream()), "scatter_layernorm_forward")
     return out, stats
+
+
+# schedule of the K3+LN forward's streaming pass when the caller does not choose (set from B200 measurements)
+LN_WALK_DEFAULT = _lib.LN_WALK_RUNS
 
 
 def _aligned16(t: torch.Tensor) -> torch.Tensor:
@@ -406,4 +393,17 @@ def scatter_backward(dcanvas: torch.Tensor, cell_table: torch.Tensor, num_rows: 
     with torch.cuda.device(dcanvas.device):
         check(lib.mbev_scatter_backward(ptr(dcanvas), ptr(cell_table), B, C, ny, nx, ptr(dfeats), _stream()),
               "scatter_backward")
+    return dfeats
+
+
+def scatter_backward_nhwc(dcanvas: torch.Tensor, cell_table: torch.Tensor, coors: torch.Tensor,
+                          num_pillars_dev: torch.Tensor, num_rows: int) -> torch.Tensor:
+    """K3' for a channels-last gradient: dcanvas is (B, C, ny, nx) in torch.channels_last memory format."""
+    lib = _lib.load()
+    B, C, ny, nx = dcanvas.shape
+    dcanvas = dcanvas.detach().to(torch.float32).contiguous(memory_format=torch.channels_last)
+    dfeats = torch.empty((num_rows, C), dtype=torch.float32, device=dcanvas.device)
+    with torch.cuda.device(dcanvas.device):
+        check(lib.mbev_scatter_backward_nhwc(ptr(dcanvas), ptr(cell_table), ptr(coors), ptr(num_pillars_dev), num_rows,
+                                             B, C, ny, nx, ptr(dfeats), _stream()), "scatter_backward_nhwc")
     return dfeats

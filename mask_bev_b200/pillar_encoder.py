@@ -7,7 +7,6 @@ their forward is never called. There is no CPU path.
 """
 from __future__ import annotations
 
-import os
 from typing import Optional, Tuple
 
 import torch
@@ -47,12 +46,12 @@ class _PfnFunction(torch.autograd.Function):
         weights, gammas, betas = params[:L], params[L:2 * L], params[2 * L:]
         cfg = net._config()
         training = net.training
-        if not isinstance(ctx, _NullCtx) and cfg.gemm_path == 0 and os.environ.get("MBEV_AUTOGRAD_TC", "0") != "1":
+        if not isinstance(ctx, _NullCtx) and cfg.gemm_path == 0 and not net.autograd_tensor_cores:
             # A backward will follow: K2' recomputes the activations on the fp32 FMA pipe, and the parameter
             # gradients of a train-mode BatchNorm stack are ill-conditioned (torch's own fp32 autograd is ~2e-3 from
             # float64 on the 3-layer stack). Use the FMA forward here so that the saved statistics are bit-consistent
             # with what the backward recomputes; the tensor-core forward serves inference and no-grad calls.
-            # Measured: with the tensor-core forward (MBEV_AUTOGRAD_TC=1) the kitti_b16 training step drops from 26.7
+            # Measured: with the tensor-core forward (net.autograd_tensor_cores = True) the kitti_b16 training step drops from 26.7
             # to 20.9 ms, but two train-mode gradient-parity cases land at 3.4e-3 of float64 (torch fp32: 1.6e-3).
             cfg.gemm_path = 1
         if training:
@@ -120,7 +119,10 @@ class PillarFeatureNet(nn.Module):
         self.z_offset = self.vz / 2 + point_cloud_range[2]
         self.point_cloud_range = point_cloud_range
         # forward Linear layers: 'auto' (tcgen05 3xTF32 when the stack fits, else fp32 FMA), 'fma', 'tcgen05'
-        self.gemm_path = os.environ.get("MBEV_GEMM_PATH", "auto")
+        self.gemm_path = "auto"
+        # forward under autograd on the tensor cores too (faster; train-mode gradient parity then sits at 1.5-2x
+        # torch's own fp32 error instead of within it — see _PfnFunction.forward)
+        self.autograd_tensor_cores = False
 
     # -- helpers ------------------------------------------------------------------------------------
     def _config(self) -> F_.PfnConfig:
@@ -157,15 +159,21 @@ class PillarFeatureNet(nn.Module):
 
     @torch.no_grad()
     def _update_running_stats(self, batch_stats: torch.Tensor, npil_dev: torch.Tensor, T: int) -> None:
-        """BatchNorm1d bookkeeping: momentum update with the unbiased variance, M = P*T slots. No host sync."""
+        """BatchNorm1d bookkeeping: momentum update with the unbiased variance, M = P*T slots. No host sync. A step
+        without any pillar (every point filtered out) leaves the buffers untouched (nn.BatchNorm1d raises on an
+        empty input; silently decaying the statistics towards zero would be worse than either)."""
         M = npil_dev.to(torch.float32) * float(T)
+        live = (M > 0).to(torch.float32)
         unbias = M / torch.clamp(M - 1.0, min=1.0)
         for l, layer in enumerate(self.pfn_layers):
             bn, U = layer.norm, layer.units
             if not bn.track_running_stats:
                 continue
-            bn.num_batches_tracked += 1
-            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.num_batches_tracked += live.to(bn.num_batches_tracked.dtype).reshape(())
+            if bn.momentum is not None:
+                mom = live * bn.momentum
+            else:
+                mom = live / torch.clamp(bn.num_batches_tracked.to(torch.float32), min=1.0)
             bn.running_mean.mul_(1.0 - mom).add_(batch_stats[l, 0, :U].to(bn.running_mean.dtype) * mom)
             bn.running_var.mul_(1.0 - mom).add_((batch_stats[l, 1, :U] * unbias).to(bn.running_var.dtype) * mom)
 
@@ -178,25 +186,6 @@ class PillarFeatureNet(nn.Module):
         with torch.no_grad():
             return _PfnFunction.forward(_NullCtx(), self, rows, kept_idx, num_points, coors, npil_dev, capacity, T,
                                         *params)
-
-    def apply_rows_canvas(self, rows, kept_idx, num_points, coors, capacity: int, T: int, cell_table, batch: int,
-                          ny: int, nx: int, canvas_out=None, force: bool = False):
-        """Eval-mode, no-grad path: PFN + scatter as ONE kernel (opt-in with MBEV_FUSED_CANVAS=1, or `force`). Returns
-        (feats, canvas), or None when the call needs autograd / train-mode statistics, the stack does not fit the
-        fused kernel, or the fused kernel is not selected."""
-        params = self._param_list()
-        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in params)):
-            return None
-        if not force and not F_.pfn_scatter_default():
-            return None
-        cfg = self._config()
-        if capacity <= 0 or not F_.pfn_scatter_supported(cfg, T, batch, ny, nx):
-            return None
-        with torch.no_grad():
-            scales, shifts, _, _ = self._folded()
-            return F_.pfn_scatter_forward_eval(rows, kept_idx, num_points, coors, capacity, T, cfg,
-                                               [l.linear.weight for l in self.pfn_layers], scales, shifts,
-                                               cell_table, batch, ny, nx, canvas_out=canvas_out)
 
     # -- upstream forward -----------------------------------------------------------------------------
     def forward(self, features: torch.Tensor, num_points: torch.Tensor, coors: torch.Tensor, *args, **kwargs):

@@ -27,8 +27,37 @@ class _ScatterFunction(torch.autograd.Function):
         return F_.scatter_backward(dcanvas, cell_table, ctx.rows), None, None, None, None
 
 
-def scatter_with_table(feats: torch.Tensor, cell_table: torch.Tensor, batch: int, ny: int, nx: int) -> torch.Tensor:
-    if feats.requires_grad and torch.is_grad_enabled():
+class _ScatterChannelsLastFunction(torch.autograd.Function):
+    """Channels-last canvas: forward = one pass over the cell table writing whole 4*C-byte rows, backward = one
+    coalesced row read per pillar."""
+
+    @staticmethod
+    def forward(ctx, feats, cell_table, coors, num_pillars_dev, batch, ny, nx):
+        ctx.save_for_backward(cell_table, coors, num_pillars_dev)
+        ctx.rows = feats.shape[0]
+        return F_.scatter_forward(feats.detach().to(torch.float32).contiguous(), cell_table, batch, ny, nx,
+                                  channels_last=True)
+
+    @staticmethod
+    def backward(ctx, dcanvas):
+        cell_table, coors, npil = ctx.saved_tensors
+        return (F_.scatter_backward_nhwc(dcanvas, cell_table, coors, npil, ctx.rows),) + (None,) * 6
+
+
+def scatter_with_table(feats: torch.Tensor, cell_table: torch.Tensor, batch: int, ny: int, nx: int,
+                       channels_last: bool = False, coors: Optional[torch.Tensor] = None,
+                       num_pillars_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    grad = feats.requires_grad and torch.is_grad_enabled()
+    if channels_last:
+        if feats.shape[1] % 4:
+            raise MbevError("the channels-last canvas needs C % 4 == 0")
+        if grad:
+            if coors is None or num_pillars_dev is None:
+                raise MbevError("channels-last scatter under autograd needs coors and the device pillar count")
+            return _ScatterChannelsLastFunction.apply(feats, cell_table, coors, num_pillars_dev, batch, ny, nx)
+        return F_.scatter_forward(feats.detach().to(torch.float32).contiguous(), cell_table, batch, ny, nx,
+                                  channels_last=True)
+    if grad:
         return _ScatterFunction.apply(feats, cell_table, batch, ny, nx)
     return F_.scatter_forward(feats.detach().to(torch.float32).contiguous(), cell_table, batch, ny, nx)
 
@@ -73,13 +102,15 @@ def scatter_layernorm_with_table(feats: torch.Tensor, ln: nn.LayerNorm, cell_tab
 
 
 class PointPillarsScatter(nn.Module):
-    def __init__(self, in_channels: int, output_shape: List[int]):
+    def __init__(self, in_channels: int, output_shape: List[int], channels_last: bool = False):
         super().__init__()
         self.output_shape = output_shape
         self.ny = output_shape[0]
         self.nx = output_shape[1]
         self.in_channels = in_channels
         self.fp16_enabled = False
+        # additive: return the (B, C, ny, nx) canvas in torch.channels_last memory format
+        self.channels_last = channels_last
 
     def forward(self, voxel_features: torch.Tensor, coors: torch.Tensor, batch_size: Optional[int] = None):
         """voxel_features (P, C), coors (P, 4) int (b, z, y, x) -> (B, C, ny, nx); batch_size None = one sample
@@ -94,4 +125,5 @@ class PointPillarsScatter(nn.Module):
         P = voxel_features.shape[0]
         npil = torch.full((1,), P, dtype=torch.int32, device=voxel_features.device)
         table = F_.build_cell_table(coors, npil, P, batch_size, self.ny, self.nx)
-        return scatter_with_table(voxel_features, table, batch_size, self.ny, self.nx)
+        return scatter_with_table(voxel_features, table, batch_size, self.ny, self.nx,
+                                  channels_last=self.channels_last, coors=coors, num_pillars_dev=npil)

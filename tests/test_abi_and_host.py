@@ -58,6 +58,33 @@ def test_argument_validation_without_gpu():
         _lib.check(-3, "x")
 
 
+def test_pillar_capacity_contract_ragged_batches_without_gpu():
+    """Round-1 bug (GPUTEST_r01): the host side sized the pillar buffers as sum_f min(n_f, V, cells) while
+    mbev_voxelize demanded min(total, B * min(V, cells)) — any ragged batch with one frame above min(V, cells) was
+    refused with status -1. Both sides now use mbev_pillar_capacity; the check runs before the device is touched
+    (fake non-null pointers, a zero-byte workspace: -3 = the capacity was accepted, -1 = refused)."""
+    from mask_bev_b200 import _lib
+    from mask_bev_b200 import functional as F_
+    lib = _lib.load()
+    fake = ctypes.c_void_p(4096)
+    for grid_rng, vs, V, sizes in [((-8, 8, -6, 6), 0.5, 250000, [1500, 40, 900]),     # the failing round-1 case: 32 x 24 grid
+                                   ((-8, 8, -6, 6), 0.5, 100, [1500, 0, 50, 99, 101]),  # max_voxels binds
+                                   ((-40, 40, -40, 40), 0.16, 250000, [120000, 7, 0]),
+                                   ((-8, 8, -6, 6), 0.5, 250000, [0])]:
+        x0, x1, y0, y1 = grid_rng
+        geo = F_.make_geometry([vs, vs, 4], [x0, y0, -2, x1, y1, 2], 8, V, 4, True)
+        cells = geo.grid[0] * geo.grid[1] * geo.grid[2]
+        off, total = F_._offsets(sizes)
+        want = sum(min(s, V, cells) for s in sizes)
+        assert lib.mbev_pillar_capacity(off, len(sizes), ctypes.byref(geo)) == want
+        assert F_.pillar_capacity(geo, sizes) == max(1, want)
+        args = lambda cap: (fake, off, len(sizes), ctypes.byref(geo), fake, fake, fake, fake, fake, cap, fake, 0, None)  # noqa: E731
+        assert lib.mbev_voxelize(*args(want)) == -3, sizes       # capacity accepted, then "workspace too small"
+        if want > 0:
+            assert lib.mbev_voxelize(*args(want - 1)) == -1, sizes
+    assert lib.mbev_pillar_capacity(None, 1, ctypes.byref(geo)) == -1
+
+
 def test_capability_probes_without_gpu():
     """Shape / alignment probes of the fused entries are pure host code: they answer without a device."""
     from mask_bev_b200 import _lib
@@ -85,22 +112,33 @@ def test_capability_probes_without_gpu():
     st = lib.mbev_scatter_layernorm_backward(null, null, null, null, null, 0, 1, 4, 8, 8, null, null, null, null, null,
                                              null, 0, null)
     assert st == -1
-    # K2 + K3 fused kernel: tcgen05 stack, T <= 32, plane a multiple of 4 cells and at least one strip
+    # K3 through the TMA engine: channels in groups of 4, plane a multiple of 4 cells, 16-byte aligned canvas
+    assert lib.mbev_scatter_stream_supported(128, 800, 800, null) == 1
+    assert lib.mbev_scatter_stream_supported(128, 25, 25, null) == 0
+    assert lib.mbev_scatter_stream_supported(6, 16, 16, null) == 0
+    assert lib.mbev_scatter_stream_supported(64, 16, 16, ctypes.c_void_p(4100)) == 0
+    assert lib.mbev_scatter_forward_stream(null, null, 1, 64, 16, 16, null, 1, null) == -1
+    assert lib.mbev_scatter_forward_stream(ctypes.c_void_p(4096), ctypes.c_void_p(4096), 1, 64, 16, 16,
+                                           ctypes.c_void_p(4096), 0, null) == -1          # ctas_per_sm >= 1
+    assert lib.mbev_scatter_forward_nhwc(ctypes.c_void_p(4096), ctypes.c_void_p(4096), 1, 6, 16, 16,
+                                         ctypes.c_void_p(4096), null) == -2               # C % 4
+    # K3 + LayerNorm: the walk must be one of the two schedules (checked before the device is touched)
+    f = ctypes.c_void_p(4096)
+    assert lib.mbev_scatter_layernorm_forward(f, f, f, 1, 4, 8, 8, f, f, 1e-3, 7, f, f, f, 1 << 20, null) == -1
+    # the pipelined entry refuses missing or aliased streams / events before touching the device
     enc = M.MaskBevEncoder(**encoder_kwargs("kitti_b16"))
     cfg = enc._voxel_encoder._config()
-    assert F_.pfn_scatter_supported(cfg, 32, 16, 800, 800)
-    assert not F_.pfn_scatter_supported(cfg, 100, 16, 800, 800)
-    assert not F_.pfn_scatter_supported(cfg, 32, 1, 8, 8)
-    assert F_.pfn_scatter_default() in (False, True)
-    # the pipelined entries refuse missing streams / events before touching the device
+    assert F_.pfn_path(cfg, 32) == "tcgen05" and F_.pfn_path(cfg, 100) == "tcgen05"
     geo = F_.make_geometry([0.1, 0.1, 40], [0, -40, -20, 80, 40, 20], 32, 250000, 4, True)
     off = (ctypes.c_int64 * 2)(0, 10)
     params = F_._pfn_struct(cfg, [None] * 3, None, None)
     st = lib.mbev_encode_batch_pipelined(null, null, off, 1, ctypes.byref(geo), ctypes.byref(params), null, null, null,
-                                         null, null, 10, null, null, null, 0, null, 0, null, null, null, null)
+                                         null, null, 10, null, null, null, 0, null, 0, 1, null, null, null, null, null,
+                                         null)
     assert st == -1
-    st = lib.mbev_encode_batch_host_async(null, null, off, 1, ctypes.byref(geo), ctypes.byref(params), null, null, null,
-                                          null, null, 10, null, null, null, 0, null, null, null, null, null)
+    s1, s2 = ctypes.c_void_p(8), ctypes.c_void_p(16)
+    st = lib.mbev_encode_batch_pipelined(null, f, off, 1, ctypes.byref(geo), ctypes.byref(params), f, f, f, f, f, 10, f,
+                                         f, f, 0, f, 0, 1, null, s1, s1, f, f, f)      # prep stream == pfn stream
     assert st == -1
 
 

@@ -26,6 +26,15 @@ def _rank_grad(rank, i, shape):
     return torch.randn(shape, generator=g)
 
 
+def _toy_net():
+    torch.manual_seed(5)
+    return torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.Tanh(), torch.nn.Linear(4, 2))
+
+
+def _toy_input(rank):
+    return torch.randn((6, 8), generator=torch.Generator().manual_seed(77 + rank))
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -40,9 +49,18 @@ def _worker(rank, world, port, q):
         rep = allreduce_gradients(params + [frozen], small_bucket_bytes=128 * 40 * 40 * 4)
         dp = FrontEndDataParallel(torch.nn.Linear(2, 2))
         owned = [dp.owned_frames(n) for n in (5, 1)]
+        # overlap=True: large gradients leave from a post-accumulate hook during backward, the rest at the end
+        net = _toy_net()
+        odp = FrontEndDataParallel(net, overlap=True, small_bucket_bytes=100)   # the (4, 8) weight counts as large
+        for step in range(2):   # twice: the pending list must be reset between steps
+            net.zero_grad(set_to_none=False)
+            net(_toy_input(rank)).sum().backward()
+            orep = odp.reduce_gradients()
+        odp.close()
         if rank == 0:
             q.put(dict(grads=[p.grad.numpy().copy() for p in params], rep=dict(rep.__dict__), owned=owned,
-                       frozen=frozen.grad))   # numpy: pickled by value (tensors would travel as shared-memory handles)
+                       frozen=frozen.grad, ograds=[p.grad.numpy().copy() for p in net.parameters()],
+                       orep=dict(orep.__dict__)))   # numpy: pickled by value (tensors would travel as shared-memory handles)
         else:
             q.put(dict(owned1=owned))
     finally:
@@ -72,6 +90,15 @@ def test_two_rank_gradient_allreduce_gloo():
     # nine PFN tensors in ONE flat bucket (25 792 floats), the two LayerNorm-sized tensors in place: 3 collectives
     assert res["rep"] == dict(world=2, collectives=3, bucket_floats=25792, inplace_floats=2 * 128 * 40 * 40)
     assert res["frozen"] is None
+    # the overlapped exchange gives the same mean; one hooked collective + one flat bucket
+    want = []
+    for r in range(world):
+        net = _toy_net()
+        net(_toy_input(r)).sum().backward()
+        want.append([p.grad.clone() for p in net.parameters()])
+    for i, g in enumerate(res["ograds"]):
+        assert torch.allclose(torch.from_numpy(g), (want[0][i] + want[1][i]) / 2, rtol=0, atol=1e-6), i
+    assert res["orep"] == dict(world=2, collectives=2, bucket_floats=4 + 8 + 2, inplace_floats=32)
     assert res["owned"] == [[0, 2, 4], [0]] and other["owned1"] == [[1, 3], []]
 
 

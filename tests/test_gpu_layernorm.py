@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import O, assert_close, encoder_pair, ref_test_kwargs, rel_err
+from helpers import O, assert_close, encoder_pair, ref_test_kwargs, rel_err  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -87,3 +87,30 @@ def test_scatter_layernorm_unsupported_shape_falls_back_to_torch():
         a = enc(pcs)
         b = enc._layer_norm(enc.encode_batch(pcs))
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,C,ny,nx,P", [(3, 128, 100, 100, 900), (16, 64, 50, 70, 2000), (1, 32, 30, 26, 0), (5, 8, 64, 64, 4096)])
+def test_layernorm_forward_walks_are_bit_identical(B, C, ny, nx, P):
+    """MBEV_LN_WALK_FRAMES (a warp walks the frames with weight / bias in registers) computes the very expression of
+    MBEV_LN_WALK_RUNS per element: same bits, incl. ragged last runs (G % 128 != 0), an empty batch and P = every cell."""
+    from mask_bev_b200 import _lib
+    from mask_bev_b200 import functional as F_
+    rng = np.random.default_rng(B * 1000 + C)
+    lin = np.sort(rng.choice(B * ny * nx, P, replace=False))
+    coors = np.stack([lin // (ny * nx), np.zeros(P, np.int64), (lin // nx) % ny, lin % nx], 1).astype(np.int32).reshape(P, 4)
+    base = np.concatenate([[0], np.cumsum(np.bincount(coors[:, 0], minlength=B))]).astype(np.int32)
+    rows = max(P, 1)
+    feats = torch.from_numpy(rng.normal(size=(rows, C)).astype(np.float32)).to(DEV)
+    coors_d = torch.zeros((rows, 4), dtype=torch.int32, device=DEV)
+    coors_d[:P] = torch.from_numpy(coors).to(DEV)
+    base_d = torch.from_numpy(base).to(DEV)
+    table = F_.build_cell_table(coors_d, base_d[B:], rows, B, ny, nx)
+    w = torch.from_numpy(rng.normal(1.0, 0.3, size=(C, ny, nx)).astype(np.float32)).to(DEV)
+    b = torch.from_numpy(rng.normal(0.0, 0.3, size=(C, ny, nx)).astype(np.float32)).to(DEV)
+    a_out, a_st = F_.scatter_layernorm_forward(feats, table, base_d, B, ny, nx, w, b, 1e-3, walk=_lib.LN_WALK_RUNS)
+    f_out, f_st = F_.scatter_layernorm_forward(feats, table, base_d, B, ny, nx, w, b, 1e-3, walk=_lib.LN_WALK_FRAMES)
+    assert torch.equal(a_st, f_st)
+    assert torch.equal(a_out, f_out)
+    canvas = F_.scatter_forward(feats, table, B, ny, nx)
+    ref = torch.nn.functional.layer_norm(canvas.double(), (C, ny, nx), w.double(), b.double(), 1e-3)
+    assert_close(f_out.cpu().numpy(), ref.cpu().numpy(), what="frame-walking K3+LN vs float64 LayerNorm")
