@@ -390,7 +390,7 @@ def run_ours(args):
     enc, pfn_cpu = make_encoder(kwargs, dev)
     runner = FusedEncoderRunner(enc, [len(f) for f in frames], dev, scatter_ctas_per_sm=args.scatter_ctas)
     host = torch.from_numpy(np.concatenate(frames, 0)).pin_memory()
-    runner.points_dev.copy_(host)
+    runner.set_points(host)
     counts_host = torch.empty((B + 1,), dtype=torch.int32).pin_memory()
     sync = lambda: torch.cuda.synchronize(dev)  # noqa: E731
 

@@ -200,7 +200,7 @@ __device__ __forceinline__ void seg_max16(const Window &w, int lane, float (&a)[
   }
 }
 
-__global__ void __launch_bounds__(kW2Threads, 1)
+__global__ void __maxnreg__(88)
 k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, const int *__restrict__ num_points,
            const int *__restrict__ coors, const int *__restrict__ bounds8, float *__restrict__ feats,
            const __grid_constant__ Kargs k) {

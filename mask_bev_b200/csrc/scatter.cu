@@ -418,6 +418,10 @@ extern "C" int mbev_scatter_forward_stream(const float *feats, const int32_t *ce
   const int rpf = (G + kRunCells - 1) / kRunCells;
   const int nr = rpf * batch;
   const int blocks = std::min((nr + kBulkThreads / 32 - 1) / (kBulkThreads / 32), kNumSMs * ctas_per_sm);
+  // same shared-memory / L1 split as K2's 208 KB CTA: an SM cannot host two kernels that want different carve-outs
+  // (it would have to drain to reconfigure), and co-residency with K2 is the point of this kernel
+  MBEV_CUDA(cudaFuncSetAttribute(k_scatter_bulk, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
   k_scatter_bulk<<<blocks, kBulkThreads, kBulkSmem, static_cast<cudaStream_t>(stream_)>>>(feats, cell_table, c_out, G,
                                                                                          rpf, nr, canvas);
   MBEV_CHECK_LAUNCH();

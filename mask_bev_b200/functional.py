@@ -347,8 +347,9 @@ def scatter_layernorm_forward(feats: torch.Tensor, cell_table: torch.Tensor, pil
     return out, stats
 
 
-# schedule of the K3+LN forward's streaming pass when the caller does not choose (set from B200 measurements)
-LN_WALK_DEFAULT = _lib.LN_WALK_RUNS
+# schedule of the K3+LN forward's streaming pass when the caller does not choose. B200, kitti_b16: frames 1.43 ms,
+# runs 1.62 ms (profiles/r2a_bench.json) — the frame walk keeps weight / bias in registers instead of re-reading L2.
+LN_WALK_DEFAULT = _lib.LN_WALK_FRAMES
 
 
 def _aligned16(t: torch.Tensor) -> torch.Tensor:

@@ -52,6 +52,7 @@ class FusedEncoderRunner:
                   "encode_batch_workspace_bytes")
             self.ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
         self._sets = None
+        self._points_dirty = True
 
     def refresh_params(self) -> None:
         """Re-fold the eval-mode BatchNorm after a weight update."""
@@ -119,17 +120,22 @@ class FusedEncoderRunner:
     def run_pipelined(self, points_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Stream-of-batches form (mbev_encode_batch_pipelined): [H2D +] K1 of this batch on a prep stream, K2 on a
         PFN stream, K3 on the current stream, over two alternating buffer sets — K1 of batch i+2, K2 of batch i+1 and
-        K3 of batch i overlap. Without `points_host` the runner's resident `points_dev` is the input (it must not be
-        rewritten while batches are in flight: the prep stream is ordered after the current stream once per call).
+        K3 of batch i overlap. Without `points_host` the runner's resident `points_dev` is the input: write it with
+        `set_points` (or call `mark_points_updated` after writing it on the current stream) and not while batches are
+        in flight.
         `last_pillar_base` / `last_feats` belong to the batch just enqueued."""
         if self._sets is None:
             self._pipe_init()
         s = self._sets[self._i & 1]
         self._i += 1
         with torch.cuda.device(self.device):
-            if points_host is None:  # writes to points_dev enqueued on the current stream so far happen before K1 reads it
+            if points_host is None and self._points_dirty:
+                # writes to points_dev enqueued on the current stream so far happen before K1 reads it. Once per
+                # update only: the current stream also carries K3 of the previous batch, and ordering K1 after it on
+                # every call would serialise the pipeline.
                 self._resident.record(torch.cuda.current_stream(self.device))
                 self._prep.wait_event(self._resident)
+                self._points_dirty = False
             pts_dev = s["points"] if points_host is not None else self.points_dev
             check(self.lib.mbev_encode_batch_pipelined(
                 ptr(points_host), ptr(pts_dev), self.off, self.B, ctypes.byref(self.geo), ctypes.byref(self.params),
@@ -140,6 +146,14 @@ class FusedEncoderRunner:
                 s["ev"][0], s["ev"][1], s["ev"][2]), "encode_batch_pipelined")
         self._last = s
         return self.canvas
+
+    def set_points(self, points: torch.Tensor) -> None:
+        """Copy a (sum N_i, C) float32 batch (host or device) into the resident `points_dev` on the current stream."""
+        self.points_dev.copy_(points, non_blocking=True)
+        self._points_dirty = True
+
+    def mark_points_updated(self) -> None:
+        self._points_dirty = True
 
     @property
     def last_pillar_base(self) -> torch.Tensor:

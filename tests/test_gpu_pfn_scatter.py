@@ -381,7 +381,7 @@ def test_runner_three_stage_pipeline_matches_device_entry(ctas):
         assert torch.equal(o, refs[i & 1]), f"pipelined step {i} differs"
         assert torch.equal(b, bases[i & 1])
         assert torch.equal(f[:len(fts[i & 1])], fts[i & 1])
-    r.points_dev.copy_(ha.to(DEV))  # device-resident form: no copy, K1 still on the prep stream
+    r.set_points(ha)  # device-resident form: no copy per step, K1 still on the prep stream
     for i in range(4):
         r.run_pipelined()
         if i & 1:
