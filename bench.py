@@ -516,9 +516,23 @@ def run_ours(args):
         t_step16 = ev_time(runner.run_device_bf16, iters, sync)
         by_sc16 = P * Co * 4 + P * 16 + B * G * Co * 2
         bf16 = {"K3_scatter_bf16_ms": t_sc16, "alg_bytes": by_sc16, "gbs": by_sc16 / t_sc16 / 1e6,
-                "frac_hbm": by_sc16 / t_sc16 / 1e6 / peak, "ms_per_step": t_step16,
-                "frames_per_s": B / (t_step16 * 1e-3),
-                "note": "fp32 PFN (3xTF32), canvas rounded to bf16 on the way out (mbev_scatter_forward_bf16); one GPU"}
+                "frac_hbm": by_sc16 / t_sc16 / 1e6 / peak, "fp32_pfn_ms_per_step": t_step16,
+                "fp32_pfn_frames_per_s": B / (t_step16 * 1e-3),
+                "note": "K1 -> K2 -> K3 with a bf16 canvas on one stream; fp32_pfn_*: K2 in fp32 (3xTF32), the canvas "
+                        "rounded on the way out; bf16_pfn_*: K2 with gemm_path = MBEV_GEMM_TCGEN05_BF16 as well"}
+        net = enc._voxel_encoder
+        net.gemm_path = "tcgen05_bf16"
+        try:
+            runner.refresh_params()
+            if runner.lib.mbev_pfn_path(ctypes.byref(runner.params), T) == 3:
+                t_pfn16 = ev_time(runner.run_pfn, iters, sync)
+                t_all16 = ev_time(runner.run_device_bf16, iters, sync)
+                bf16.update({"K2_pfn_bf16_ms": t_pfn16, "bf16_pfn_ms_per_step": t_all16,
+                             "bf16_pfn_frames_per_s": B / (t_all16 * 1e-3)})
+        finally:
+            net.gemm_path = "auto"
+            runner.refresh_params()
+            runner.run_pfn(); sync()   # feats back to the fp32 path's for the timings below
         runner.canvas_bf16 = None
     # SURVEY §8 f1 ("next" row, not part of the headline metric): the LayerNorm that follows the scatter in
     # MaskBevEncoder.forward, fused into the scatter, next to torch's own LayerNorm on the finished canvas

@@ -74,10 +74,13 @@ typedef struct MbevPfnParams {
   int32_t voxel_center_dims;         /* 3 (mmdet3d 1.1.0) or 2 (mmdet3d 0.x fossil, mask_bev_encoders.py:165-166) */
   float vx, vy, vz, x_offset, y_offset, z_offset; /* float32(vx), float32(vx/2 + x0) ... */
   int32_t gemm_path; /* forward Linear layers: MBEV_GEMM_AUTO (tcgen05 3xTF32 when the stack fits it, else fp32 FMA),
-                        MBEV_GEMM_FMA, MBEV_GEMM_TCGEN05 (MBEV_ERR_UNSUPPORTED if the stack does not fit) */
+                        MBEV_GEMM_FMA, MBEV_GEMM_TCGEN05 (MBEV_ERR_UNSUPPORTED if the stack does not fit),
+                        MBEV_GEMM_TCGEN05_BF16 (layers >= 1 as single-pass bf16 tensor-core MMAs with fp32 accumulation,
+                        layer 0 — raw coordinates in — stays 3xTF32; eval mode, T <= 32, every units % 32 == 0 and
+                        <= 64 for non-last layers; 1e-2 tolerance class, BASELINE.json north star "1e-2 in bf16") */
 } MbevPfnParams;
 
-enum { MBEV_GEMM_AUTO = 0, MBEV_GEMM_FMA = 1, MBEV_GEMM_TCGEN05 = 2 };
+enum { MBEV_GEMM_AUTO = 0, MBEV_GEMM_FMA = 1, MBEV_GEMM_TCGEN05 = 2, MBEV_GEMM_TCGEN05_BF16 = 3 };
 
 /* Version / capability probes (host only, no GPU needed). */
 MBEV_API int mbev_abi_version(void);
@@ -132,7 +135,7 @@ MBEV_API int mbev_gather_voxels(const float *points, const int32_t *kept_idx, co
  * ---------------------------------------------------------------------------------------------- */
 MBEV_API int mbev_pfn_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity, int train,
                              size_t *bytes);
-MBEV_API int mbev_pfn_path(const MbevPfnParams *params, int T); /* MBEV_GEMM_FMA / MBEV_GEMM_TCGEN05, or < 0 */
+MBEV_API int mbev_pfn_path(const MbevPfnParams *params, int T); /* MBEV_GEMM_FMA / _TCGEN05 / _TCGEN05_BF16, or < 0 */
 MBEV_API int mbev_pfn_forward(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
                      const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity, int T,
                      const MbevPfnParams *params, float *feats, void *workspace, size_t workspace_bytes,

@@ -14,7 +14,7 @@ MAX_LAYERS = 4
 MAX_UNITS = 128
 MAX_POINT_DIM = 8
 ABI_VERSION = 8
-GEMM_AUTO, GEMM_FMA, GEMM_TCGEN05 = 0, 1, 2
+GEMM_AUTO, GEMM_FMA, GEMM_TCGEN05, GEMM_TCGEN05_BF16 = 0, 1, 2, 3
 LN_WALK_RUNS, LN_WALK_FRAMES = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

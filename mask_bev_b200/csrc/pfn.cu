@@ -531,12 +531,18 @@ int launch_pfn(const Plan &pl, const float *rows, const int32_t *kept_idx, const
   return MBEV_OK;
 }
 
-// Which implementation runs the Linear layers of this stack: MBEV_GEMM_TCGEN05 / MBEV_GEMM_FMA, or < 0.
+// Which implementation runs the Linear layers of this stack: MBEV_GEMM_TCGEN05[_BF16] / MBEV_GEMM_FMA, or < 0.
 int select_path(const MbevPfnParams *p, int C, int T) {  // capacity-independent
   if (!p) return MBEV_ERR_BAD_ARG;
+  if (p->gemm_path < MBEV_GEMM_AUTO || p->gemm_path > MBEV_GEMM_TCGEN05_BF16) return MBEV_ERR_BAD_ARG;
   if (p->gemm_path == MBEV_GEMM_FMA) return MBEV_GEMM_FMA;
   tc::Plan tp;
   const int st = tc::make_plan(p, C, T, 1, nullptr, &tp);
+  if (p->gemm_path == MBEV_GEMM_TCGEN05_BF16) {  // the warp-local two-pipeline kernel only
+    if (st) return st;
+    tc::Kargs k2 = tp.k;
+    return tc::tcw2_plan(k2) ? MBEV_GEMM_TCGEN05_BF16 : MBEV_ERR_UNSUPPORTED;
+  }
   if (st == MBEV_OK) return MBEV_GEMM_TCGEN05;
   if (st == MBEV_ERR_UNSUPPORTED && p->gemm_path == MBEV_GEMM_AUTO) return MBEV_GEMM_FMA;
   return st;
@@ -572,7 +578,7 @@ extern "C" int mbev_pfn_workspace_bytes(const MbevPfnParams *params, int T, int6
   const int C = raw_point_dim(params);
   const int path = select_path(params, C, T);
   if (path < 0) return path;
-  if (path == MBEV_GEMM_TCGEN05) {
+  if (path == MBEV_GEMM_TCGEN05 || path == MBEV_GEMM_TCGEN05_BF16) {
     tc::Plan tp;
     const int st = tc::make_plan(params, C, T, pillar_capacity, nullptr, &tp);
     if (st) return st;
@@ -596,7 +602,7 @@ extern "C" int mbev_pfn_forward(const float *rows, int C, const int32_t *kept_id
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int path = select_path(params, C, T);
   if (path < 0) return path;
-  if (path == MBEV_GEMM_TCGEN05) {
+  if (path == MBEV_GEMM_TCGEN05 || path == MBEV_GEMM_TCGEN05_BF16) {
     tc::Plan tp;
     int st = tc::make_plan(params, C, T, pillar_capacity, workspace, &tp);
     if (st) return st;
@@ -637,6 +643,7 @@ extern "C" int mbev_pfn_forward_train(const float *rows, int C, const int32_t *k
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int path = select_path(params, C, T);
   if (path < 0) return path;
+  if (path == MBEV_GEMM_TCGEN05_BF16) return MBEV_ERR_UNSUPPORTED;  // batch statistics need the fp32-accurate path
   if (path == MBEV_GEMM_TCGEN05) {
     tc::Plan tp;
     int st = tc::make_plan(params, C, T, pillar_capacity, workspace, &tp);

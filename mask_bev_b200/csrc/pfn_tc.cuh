@@ -69,6 +69,7 @@ struct Kargs {
   int smem_bytes;
   int stat_layer;    // -1: full forward; s: accumulate the statistics of layer s and stop
   double *partials;  // (gridDim.x, 2, um)
+  int bf16;          // 1: layers >= 1 run as single-pass bf16 MMAs (kind::f16), layer 0 stays 3xTF32 (k_pfn_tcw2 only)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -120,6 +121,19 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d, uint32_t a, uint64_t bde
       "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem] with bf16 operands (K = 16 per instruction, two bf16 per 32-bit TMEM column of A)
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+      "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same descriptor with a/b_format BF16 (= 1)
+__device__ __forceinline__ uint32_t make_idesc_bf16(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2,
 // a/b K-major (bits 15,16 = 0), n_dim [17,23) = N>>3, m_dim [24,29) = M>>4.
 __device__ __forceinline__ uint32_t make_idesc(int N) {
@@ -168,6 +182,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};" ::MBEV_I8(v, 0),
       MBEV_I8(v, 8), "r"(taddr)
       : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::MBEV_I8(v, 0), "r"(taddr)
+               : "memory");
+}
+// 16 consecutive K elements of a row -> 8 TMEM columns (element 2i in the low half of column i), round to nearest even
+__device__ __forceinline__ void pack_bf16x16(const float (&a)[16], uint32_t (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v[i]) : "f"(a[2 * i + 1]), "f"(a[2 * i]));
 }
 
 // x = hi + lo (+ <= 2^-22 |x|), both exactly representable in TF32 so the tensor core's own conversion is the identity
@@ -735,6 +759,7 @@ k_pfn_tc(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, c
 // column order (kWide*).
 struct PrepArgs {
   int L;
+  int bf16;          // layers >= 1: one bf16 image at hi[l] (16-byte unit = 8 K elements), no lo image
   int map0[kK0Pad];  // wide layer-0 slot -> Linear.weight column of layer 0, -1 = unused slot (zero column)
   int K[MBEV_MAX_LAYERS], Kp[MBEV_MAX_LAYERS], U[MBEV_MAX_LAYERS];
   const float *w[MBEV_MAX_LAYERS];
@@ -749,6 +774,13 @@ __global__ void k_prep_weights_tc(const PrepArgs a) {
     const int u = i / Kp, kk = i - u * Kp;
     const int col = (l == 0) ? a.map0[kk] : (kk < K ? kk : -1);
     const float v = col >= 0 ? __ldg(a.w[l] + static_cast<size_t>(u) * K + col) : 0.f;
+    if (a.bf16 && l > 0) {  // UMMA K-major no-swizzle core matrix: 8 rows x 16 bytes = 8 bf16 along K
+      uint16_t *img = reinterpret_cast<uint16_t *>(a.hi[l]);
+      uint32_t b;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b) : "f"(0.f), "f"(v));
+      img[(((kk >> 3) * U + u) << 3) + (kk & 7)] = static_cast<uint16_t>(b & 0xffffu);
+      continue;
+    }
     uint32_t hi, lo;
     split_tf32(v, hi, lo);
     const int idx = (((kk >> 2) * U + u) << 2) + (kk & 3);
@@ -772,6 +804,7 @@ struct Plan {
 // MBEV_OK when the stack fits the tensor-core kernel, MBEV_ERR_UNSUPPORTED when it must run on the FMA kernel.
 inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capacity, void *ws, Plan *out) {
   if (!p || p->num_layers < 1 || p->num_layers > MBEV_MAX_LAYERS) return MBEV_ERR_BAD_ARG;
+  const bool bf16 = p->gemm_path == MBEV_GEMM_TCGEN05_BF16;
   if (C < 3 || C > MBEV_MAX_POINT_DIM || T < 1) return MBEV_ERR_UNSUPPORTED;
   if (T + 1 > kRows) return MBEV_ERR_UNSUPPORTED;  // a pillar and its virtual row must fit one chunk
   Kargs &k = out->k;
@@ -779,6 +812,7 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capaci
   PrepArgs &pa = out->prep;
   pa = PrepArgs();
   k.L = pa.L = p->num_layers;
+  k.bf16 = pa.bf16 = bf16 ? 1 : 0;
   k.C = C;
   k.T = T;
   k.cluster = p->with_cluster_center != 0;
@@ -812,9 +846,15 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capaci
     k.U[l] = pa.U[l] = U;
     k.K[l] = pa.K[l] = K;
     k.Kp[l] = pa.Kp[l] = Kp;
-    for (int h = 0; h < 2; ++h) {
-      k.w_off[l][h] = off;
-      off += static_cast<uint32_t>(U) * Kp * 4u;
+    if (bf16 && l > 0) {  // one bf16 image
+      if (Kp & 15) return MBEV_ERR_UNSUPPORTED;
+      k.w_off[l][0] = k.w_off[l][1] = off;
+      off += static_cast<uint32_t>(U) * Kp * 2u;
+    } else {
+      for (int h = 0; h < 2; ++h) {
+        k.w_off[l][h] = off;
+        off += static_cast<uint32_t>(U) * Kp * 4u;
+      }
     }
     um = std::max(um, U);
   }

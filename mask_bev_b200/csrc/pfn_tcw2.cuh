@@ -182,6 +182,13 @@ __device__ __forceinline__ void split_store16(uint32_t t_hi, uint32_t t_lo, cons
   tmem_st16(t_lo, lo);
 }
 
+// bf16 form of split_store16: 16 K elements -> 8 packed columns
+__device__ __forceinline__ void pack_store16(uint32_t t_a, const float (&a)[16]) {
+  uint32_t v[8];
+  pack_bf16x16(a, v);
+  tmem_st8(t_a, v);
+}
+
 // per-pillar max over the lanes of the window: segmented inclusive max-scan, then read the pillar's last lane
 // (kBroadcast = false: only the pillar's LAST lane holds the result — enough for the last layer's store)
 template <bool kBroadcast = true>
@@ -200,6 +207,7 @@ __device__ __forceinline__ void seg_max16(const Window &w, int lane, float (&a)[
   }
 }
 
+template <bool kBf16>
 __global__ void __maxnreg__(88)
 k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, const int *__restrict__ num_points,
            const int *__restrict__ coors, const int *__restrict__ bounds8, float *__restrict__ feats,
@@ -262,12 +270,13 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
       tc_fence_after();
       for (int l = 0; l < L; ++l) {
         const int U = k.U[l];
-        const uint32_t idesc = make_idesc(U);
+        const bool half = kBf16 && l > 0;  // this layer's operands are bf16: one MMA per 16 K, no lo image
+        const uint32_t idesc = half ? make_idesc_bf16(U) : make_idesc(U);
         const uint32_t lbo = static_cast<uint32_t>(U) * 16u;
         const uint64_t dh0 = make_bdesc(smem_base + k.w_off[l][0], lbo, 128u);
         const uint64_t dl0 = make_bdesc(smem_base + k.w_off[l][1], lbo, 128u);
-        const uint64_t dstep = static_cast<uint64_t>(lbo >> 3);  // one K-step (8 K) in the descriptor address field
-        const int nks = (l == 0) ? (k.Kp[0] >> 3) : (k.U[l - 1] >> 3);
+        const uint64_t dstep = static_cast<uint64_t>(lbo >> 3);  // one K-step (two 16-byte K-chunks) in the descriptor address field
+        const int nks = (l == 0) ? (k.Kp[0] >> 3) : (k.U[l - 1] >> (half ? 4 : 3));
         const int nparts = (l == 0) ? 1 : 2;
         uint32_t acc = 0;
         for (int part = 0; part < nparts; ++part) {  // x K-half, then the replicated-max K-half through the same A columns
@@ -283,13 +292,21 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
           }
           if (leader) {
             const uint64_t koff = dstep * static_cast<uint64_t>(part * nks);
+            if (half) {
 #pragma unroll 1
-            for (int j = 0; j < nks; ++j) {  // al*wh, ah*wl, ah*wh : small terms first
-              const uint64_t dh = dh0 + koff + dstep * j, dl = dl0 + koff + dstep * j;
-              mma_tf32_ts(t_d, t_al + 8u * j, dh, idesc, acc);
-              mma_tf32_ts(t_d, t_ah + 8u * j, dl, idesc, 1u);
-              mma_tf32_ts(t_d, t_ah + 8u * j, dh, idesc, 1u);
-              acc = 1;
+              for (int j = 0; j < nks; ++j) {
+                mma_bf16_ts(t_d, t_ah + 8u * j, dh0 + koff + dstep * j, idesc, acc);
+                acc = 1;
+              }
+            } else {
+#pragma unroll 1
+              for (int j = 0; j < nks; ++j) {  // al*wh, ah*wl, ah*wh : small terms first
+                const uint64_t dh = dh0 + koff + dstep * j, dl = dl0 + koff + dstep * j;
+                mma_tf32_ts(t_d, t_al + 8u * j, dh, idesc, acc);
+                mma_tf32_ts(t_d, t_ah + 8u * j, dl, idesc, 1u);
+                mma_tf32_ts(t_d, t_ah + 8u * j, dh, idesc, 1u);
+                acc = 1;
+              }
             }
             tc_commit(bs + 8 * ((l > 0 && part == 0) ? kW2XC : kW2D));
           }
@@ -353,11 +370,12 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
           // "x consumed" wait
           float a0[16], a1[16];
           const uint32_t c0 = static_cast<uint32_t>(h * Uh);
+          const uint32_t ca = kBf16 ? (c0 >> 1) : c0;  // A column of K element c0 (bf16: two elements per column)
           load_bn_relu(t_d + c0, sc, sh, a0);
-          split_store16(t_ah + c0, t_al + c0, a0);  // x half: K index = unit index
+          if (kBf16) pack_store16(t_ah + ca, a0); else split_store16(t_ah + c0, t_al + c0, a0);  // x half: K index = unit index
           if (nbat > 1) {
             load_bn_relu(t_d + c0 + 16, sc + 16, sh + 16, a1);
-            split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
+            if (kBf16) pack_store16(t_ah + ca + 8, a1); else split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
           }
           tc_wait_st();
           tc_fence_before();
@@ -368,8 +386,11 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
           mbar_wait(bs + 8 * kW2XC, par_xc);  // the x-part MMAs have read A: its columns are free again
           par_xc ^= 1u;
           tc_fence_after();
-          split_store16(t_ah + c0, t_al + c0, a0);  // max half: K index = U + unit index, same A columns
-          if (nbat > 1) split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
+          // max half: K index = U + unit index, same A columns
+          if (kBf16) pack_store16(t_ah + ca, a0); else split_store16(t_ah + c0, t_al + c0, a0);
+          if (nbat > 1) {
+            if (kBf16) pack_store16(t_ah + ca + 8, a1); else split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
+          }
           tc_wait_st();
           tc_fence_before();
           __syncwarp();
@@ -409,9 +430,13 @@ inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, co
   Kargs k = pl.k;
   k.stat_layer = stat_layer;
   Kargs k2 = k;
-  if (stat_layer < 0 && tcw2_plan(k2)) {
-    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    k_pfn_tcw2<<<pl.grid, kW2Threads, k2.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k2);
+  if (k.bf16) {  // single-pass bf16 layers: k_pfn_tcw2 only, eval-mode only (the STATS launches are 3xTF32 images)
+    if (stat_layer >= 0 || !tcw2_plan(k2)) return MBEV_ERR_UNSUPPORTED;
+    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    k_pfn_tcw2<true><<<pl.grid, kW2Threads, k2.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k2);
+  } else if (stat_layer < 0 && tcw2_plan(k2)) {
+    MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    k_pfn_tcw2<false><<<pl.grid, kW2Threads, k2.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k2);
   } else {
     MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     k_pfn_tc<<<pl.grid, kThreads, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k);

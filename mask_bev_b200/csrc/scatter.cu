@@ -11,12 +11,12 @@
 // Three NCHW kernels:
 //   k_scatter_run   : a warp owns a run of 256 cells and streams all planes of it from registers with
 //                     st.global.cs.v4; one CTA per 8 runs, machine-filling grid. The stand-alone default.
-//   k_scatter_bulk  : the same walk with the stores handed to the TMA engine: a warp composes 4 planes of its run
-//                     in a 4 KB shared-memory slot and one lane per plane issues a 1 KB bulk copy
-//                     (cp.async.bulk.global.shared::cta); runs without pillars go out straight from a shared zero
-//                     tile (4 bulk copies per lane, no other work). 128 threads, <= 64 registers and 17 KB per CTA:
-//                     one such CTA fits on an SM NEXT TO K2's persistent 576-thread CTA, which is what lets the
-//                     canvas write of batch i run under the PFN of batch i+1 (mbev_encode_batch_pipelined).
+//   k_scatter_bulk  : small-footprint persistent form: runs without pillars go out through the TMA engine straight from
+//                     a shared zero tile (cp.async.bulk.global.shared::cta), runs with pillars are composed lane =
+//                     pillar with deep register prefetch and shuffled to the cell lanes. 128 threads, <= 64 registers
+//                     and 1.5 KB per CTA: one such CTA fits on an SM NEXT TO K2's persistent 576-thread CTA, which is
+//                     what lets the canvas write of batch i run under the PFN of batch i+1
+//                     (mbev_encode_batch_pipelined).
 //   k_scatter_scalar: any shape (G % 4 != 0 or an unaligned canvas).
 #include <algorithm>
 
@@ -96,11 +96,20 @@ k_scatter_run(const float *__restrict__ feats, const int *__restrict__ table, co
   }
 }
 
-// ---- TMA-engine form: small enough to share an SM with K2 ---------------------------------------------------------
+// ---- small-footprint form: 128 threads, <= 64 registers, 1.5 KB of shared memory — shares an SM with K2 ----------------
+// 4 warps per SM must keep the HBM write stream fed, so a warp may not spend its time waiting:
+//   * a run (256 cells) or half run without any pillar costs NO composing work: every plane goes out as one bulk copy
+//     of the TMA engine from a shared zero tile (cp.async.bulk.global.shared::cta, 1 KB / 512 B per plane, 4 copies per
+//     lane, nothing to wait for) — on LiDAR frames that is most of the canvas bytes;
+//   * a half run with pillars is composed LANE = PILLAR: the <= 32 pillars of a segment are ranked with ballots, lane L
+//     loads 16 channels of ITS pillar's feature row per batch (4 independent 16-byte loads, double buffered: the next
+//     batch is in flight while this one is emitted), and per plane four shuffles move the values to the lanes that own
+//     the cells (lane l = cells 4l .. 4l+3), which store 512 contiguous bytes with st.global.cs.v4. One L2 round trip
+//     per 16 planes and segment instead of one per plane; no shared-memory staging, no proxy fence, no bulk wait.
+//     Segments: the whole half (128 cells) when it holds <= 32 pillars, else its two 64-cell halves, else four 32-cell
+//     quarters (which cannot hold more than 32).
 constexpr int kBulkThreads = 128;  // 4 warps
-constexpr int kBulkPlanes = 4;     // planes composed per iteration: one 16-byte feature load per occupied cell
-constexpr int kBulkSlot = kBulkPlanes * kRunCells * 4;                  // 4 KB per warp
-constexpr int kBulkSmem = kRunCells * 4 + (kBulkThreads / 32) * kBulkSlot;  // zero tile + slots = 17 KB
+constexpr int kStrip = 128;        // cells per half run: lane l owns cells 4l .. 4l+3
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes, uint64_t policy) {
@@ -111,69 +120,126 @@ __device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kBulkThreads, 8)  // <= 64 registers: 8 K of the 10 K that K2 leaves on an SM
+// one segment: the lanes with `active` hold 4 consecutive cells each (p4 = their pillar ids), <= 32 pillars in all
+__device__ __forceinline__ void compose_segment(const float *__restrict__ feats, const int C, const size_t G,
+                                                const int4 p4, const bool active, int *s_list, float *out_lane,
+                                                const int lane) {
+  const int pj[4] = {p4.x, p4.y, p4.z, p4.w};
+  const unsigned lt = (1u << lane) - 1u;
+  bool occ[4];
+  int rank[4], np = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    occ[j] = active && pj[j] >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, occ[j]);
+    rank[j] = (np + __popc(m & lt)) & 31;
+    np += __popc(m);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (occ[j]) s_list[rank[j]] = pj[j];
+  __syncwarp();
+  const int mypid = lane < np ? s_list[lane] : -1;
+  __syncwarp();  // the list may be rewritten by the next segment
+  const float4 *row = reinterpret_cast<const float4 *>(feats + static_cast<size_t>(max(mypid, 0)) * C);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load = [&](float4 (&f)[4], const int p0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) f[r] = (mypid >= 0 && p0 + 4 * r < C) ? __ldg(row + (p0 >> 2) + r) : z;
+  };
+  auto plane = [&](const float fq, float *o) {
+    float4 v;
+    v.x = __shfl_sync(0xffffffffu, fq, rank[0]);
+    v.y = __shfl_sync(0xffffffffu, fq, rank[1]);
+    v.z = __shfl_sync(0xffffffffu, fq, rank[2]);
+    v.w = __shfl_sync(0xffffffffu, fq, rank[3]);
+    v.x = occ[0] ? v.x : 0.f;
+    v.y = occ[1] ? v.y : 0.f;
+    v.z = occ[2] ? v.z : 0.f;
+    v.w = occ[3] ? v.w : 0.f;
+    if (active) st_global_v4_stream_nc(o, v);
+  };
+  auto emit = [&](const float4 (&f)[4], const int p0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (p0 + 4 * r >= C) break;
+      float *o = out_lane + static_cast<size_t>(p0 + 4 * r) * G;
+      plane(f[r].x, o);
+      plane(f[r].y, o + G);
+      plane(f[r].z, o + 2 * G);
+      plane(f[r].w, o + 3 * G);
+    }
+  };
+  float4 fa[4], fb[4];
+  load(fa, 0);
+  for (int p0 = 0; p0 < C; p0 += 32) {
+    if (p0 + 16 < C) load(fb, p0 + 16);
+    emit(fa, p0);
+    if (p0 + 32 < C) load(fa, p0 + 32);
+    if (p0 + 16 < C) emit(fb, p0 + 16);
+  }
+}
+
+__global__ void __launch_bounds__(kBulkThreads, 8)  // <= 64 registers: 5 K2 warps at 88 leave 2304 on a sub-partition
 k_scatter_bulk(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
                const int runs_per_frame, const int num_runs, float *__restrict__ canvas) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(128) float s_zero[kRunCells];
+  __shared__ int s_lists[kBulkThreads / 32][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < kRunCells / 4; i += kBulkThreads) reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < kRunCells; i += kBulkThreads) s_zero[i] = 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros, read by the async proxy
   __syncthreads();
   uint64_t policy;  // the canvas is written once and not re-read here: keep the table and the feature rows in L2
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  const uint32_t zero = smem_addr(smem);
-  unsigned char *slot_p = smem + kRunCells * 4 + warp * kBulkSlot;
-  const uint32_t slot = smem_addr(slot_p);
+  const uint32_t zero = smem_addr(s_zero);
   const int nw = gridDim.x * (kBulkThreads / 32);
-  bool pending = false;  // lanes 0..3: a bulk copy that reads this warp's slot may still be in flight
   for (int task = blockIdx.x * (kBulkThreads / 32) + warp; task < num_runs; task += nw) {
-    const int run = num_runs - 1 - task;
+    const int run = num_runs - 1 - task;  // last frame first: its feature rows are the freshest in L2
     const int b = run / runs_per_frame;
     const int r0 = (run - b * runs_per_frame) * kRunCells;
-    const uint32_t bytes = static_cast<uint32_t>(min(kRunCells, G - r0)) * 4u;
     int4 pid[2];
     bool any;
     load_run_table(table, b, G, r0 + 4 * lane, pid, any);
     float *out = canvas + (static_cast<size_t>(b) * C) * G + r0;
     if (!__any_sync(0xffffffffu, any)) {  // a run without pillars: every plane straight from the zero tile
+      const uint32_t bytes = static_cast<uint32_t>(min(kRunCells, G - r0)) * 4u;
       for (int ch = lane; ch < C; ch += 32) bulk_s2g(out + static_cast<size_t>(ch) * G, zero, bytes, policy);
       bulk_commit();
       continue;
     }
-    for (int ch0 = 0; ch0 < C; ch0 += kBulkPlanes) {
-      float4 f[2][4];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int p4[4] = {pid[k].x, pid[k].y, pid[k].z, pid[k].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          f[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (any && p4[j] >= 0) f[k][j] = __ldg(reinterpret_cast<const float4 *>(feats + static_cast<size_t>(p4[j]) * C + ch0));
-        }
-      }
-      if (pending) {  // the previous iteration's copies have read the slot (the loads above are already in flight)
-        if (lane < kBulkPlanes) bulk_wait_read0();
-        __syncwarp();
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        float4 *dst = reinterpret_cast<float4 *>(slot_p + 512 * k + 16 * lane);
-        dst[0 * (kRunCells / 4)] = make_float4(f[k][0].x, f[k][1].x, f[k][2].x, f[k][3].x);
-        dst[1 * (kRunCells / 4)] = make_float4(f[k][0].y, f[k][1].y, f[k][2].y, f[k][3].y);
-        dst[2 * (kRunCells / 4)] = make_float4(f[k][0].z, f[k][1].z, f[k][2].z, f[k][3].z);
-        dst[3 * (kRunCells / 4)] = make_float4(f[k][0].w, f[k][1].w, f[k][2].w, f[k][3].w);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane < kBulkPlanes && ch0 + lane < C) {
-        bulk_s2g(out + static_cast<size_t>(ch0 + lane) * G, slot + lane * (kRunCells * 4), bytes, policy);
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+      const int cells = min(kStrip, G - (r0 + kStrip * k));
+      if (cells <= 0) break;
+      const int4 p4 = k ? pid[1] : pid[0];
+      const bool active = 4 * lane < cells;
+      const bool mine = active && (p4.x & p4.y & p4.z & p4.w) >= 0;
+      const unsigned lanes_occ = __ballot_sync(0xffffffffu, mine);
+      float *o = out + kStrip * k;
+      if (lanes_occ == 0u) {  // an empty half: bulk zeros
+        for (int ch = lane; ch < C; ch += 32)
+          bulk_s2g(o + static_cast<size_t>(ch) * G, zero, static_cast<uint32_t>(cells) * 4u, policy);
         bulk_commit();
+        continue;
       }
-      pending = true;
+      // pillars per 32-cell quarter (8 lanes each) -> segment length
+      const int cnt = (p4.x >= 0) + (p4.y >= 0) + (p4.z >= 0) + (p4.w >= 0);
+      int q = active ? cnt : 0;
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      q += __shfl_xor_sync(0xffffffffu, q, 4);   // every lane: pillars of its own quarter
+      const int h = q + __shfl_xor_sync(0xffffffffu, q, 8);    // ... of its 64-cell half
+      const int t = h + __shfl_xor_sync(0xffffffffu, h, 16);   // ... of the strip
+      // segment = 128 >> sh cells = 32 >> sh lanes: the whole half, its two halves, or its four quarters
+      const int sh = (t <= 32) ? 0 : (__all_sync(0xffffffffu, h <= 32) ? 1 : 2);
+      float *ol = o + 4 * lane;
+#pragma unroll 1
+      for (int s = 0; s < (1 << sh); ++s)
+        compose_segment(feats, C, static_cast<size_t>(G), p4, active && (lane >> (5 - sh)) == s, s_lists[warp], ol, lane);
     }
   }
   bulk_commit();
-  bulk_wait_read0();  // shared memory must outlive every copy that reads it
+  bulk_wait_read0();  // the zero tile must outlive every copy that reads it
 }
 
 // bf16 canvas (BASELINE config 4 / north star "1e-2 in bf16"): the register walk of k_scatter_run over 512-cell runs,
@@ -422,7 +488,7 @@ extern "C" int mbev_scatter_forward_stream(const float *feats, const int32_t *ce
   // (it would have to drain to reconfigure), and co-residency with K2 is the point of this kernel
   MBEV_CUDA(cudaFuncSetAttribute(k_scatter_bulk, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
-  k_scatter_bulk<<<blocks, kBulkThreads, kBulkSmem, static_cast<cudaStream_t>(stream_)>>>(feats, cell_table, c_out, G,
+  k_scatter_bulk<<<blocks, kBulkThreads, 0, static_cast<cudaStream_t>(stream_)>>>(feats, cell_table, c_out, G,
                                                                                          rpf, nr, canvas);
   MBEV_CHECK_LAUNCH();
   return MBEV_OK;

@@ -100,7 +100,8 @@ class MaskBevEncoder(nn.Module):
     def encode_batch(self, point_clouds: List[torch.Tensor], return_aux: bool = False,
                      canvas_dtype: torch.dtype = torch.float32, channels_last: bool = False):
         """K1 -> K2 -> K3 for the whole batch: (B, C_out, ny, nx) canvas, before the LayerNorm.
-        canvas_dtype=torch.bfloat16 (inference only): the PFN still computes in fp32, the canvas is written in bf16.
+        canvas_dtype=torch.bfloat16 (inference only): the canvas is written in bf16; the PFN computes in fp32 unless
+        `self._voxel_encoder.gemm_path = 'tcgen05_bf16'` selects the bf16 tensor-core layers as well (BASELINE config 4).
         channels_last=True: the same tensor in torch.channels_last memory format (each pillar's features are one
         contiguous row; north star item 3), forward and backward."""
         if len(point_clouds) == 0:

@@ -153,7 +153,7 @@ class PfnConfig:
     y_offset: float
     z_offset: float
     eps: float = 1e-3
-    gemm_path: int = 0        # _lib.GEMM_AUTO / GEMM_FMA / GEMM_TCGEN05 (forward Linear layers)
+    gemm_path: int = 0        # _lib.GEMM_AUTO / GEMM_FMA / GEMM_TCGEN05 / GEMM_TCGEN05_BF16 (forward Linear layers)
 
 
 def _pfn_struct(cfg: PfnConfig, weights, scales, shifts) -> MbevPfnParams:
@@ -180,13 +180,13 @@ def _pfn_struct(cfg: PfnConfig, weights, scales, shifts) -> MbevPfnParams:
 
 
 def pfn_path(cfg: PfnConfig, T: int) -> str:
-    """Which device implementation a forward with this stack takes: 'tcgen05' or 'fma'."""
+    """Which device implementation a forward with this stack takes: 'tcgen05', 'tcgen05_bf16' or 'fma'."""
     lib = _lib.load()
     params = _pfn_struct(cfg, [None] * len(cfg.units), None, None)
     r = lib.mbev_pfn_path(ctypes.byref(params), int(T))
     if r < 0:
         check(r, "pfn_path")
-    return {_lib.GEMM_FMA: "fma", _lib.GEMM_TCGEN05: "tcgen05"}[r]
+    return {_lib.GEMM_FMA: "fma", _lib.GEMM_TCGEN05: "tcgen05", _lib.GEMM_TCGEN05_BF16: "tcgen05_bf16"}[r]
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:

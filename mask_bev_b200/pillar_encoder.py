@@ -46,6 +46,9 @@ class _PfnFunction(torch.autograd.Function):
         weights, gammas, betas = params[:L], params[L:2 * L], params[2 * L:]
         cfg = net._config()
         training = net.training
+        if cfg.gemm_path == 3 and (training or not isinstance(ctx, _NullCtx)):
+            raise MbevError("gemm_path='tcgen05_bf16' is the inference path (eval mode, no autograd): batch statistics and "
+                            "the backward need the fp32-accurate kernels")
         if not isinstance(ctx, _NullCtx) and cfg.gemm_path == 0 and not net.autograd_tensor_cores:
             # A backward will follow: K2' recomputes the activations on the fp32 FMA pipe, and the parameter
             # gradients of a train-mode BatchNorm stack are ill-conditioned (torch's own fp32 autograd is ~2e-3 from
@@ -118,7 +121,8 @@ class PillarFeatureNet(nn.Module):
         self.y_offset = self.vy / 2 + point_cloud_range[1]
         self.z_offset = self.vz / 2 + point_cloud_range[2]
         self.point_cloud_range = point_cloud_range
-        # forward Linear layers: 'auto' (tcgen05 3xTF32 when the stack fits, else fp32 FMA), 'fma', 'tcgen05'
+        # forward Linear layers: 'auto' (tcgen05 3xTF32 when the stack fits, else fp32 FMA), 'fma', 'tcgen05',
+        # 'tcgen05_bf16' (inference only: layers >= 1 as single-pass bf16 MMAs, 1e-2 tolerance class)
         self.gemm_path = "auto"
         # forward under autograd on the tensor cores too (faster; train-mode gradient parity then sits at 1.5-2x
         # torch's own fp32 error instead of within it — see _PfnFunction.forward)
@@ -133,7 +137,7 @@ class PillarFeatureNet(nn.Module):
             with_distance=self._with_distance, legacy=self.legacy, voxel_center_dims=self._voxel_center_dims,
             vx=self.vx, vy=self.vy, vz=self.vz, x_offset=self.x_offset, y_offset=self.y_offset,
             z_offset=self.z_offset, eps=self.pfn_layers[0].norm.eps,
-            gemm_path={"auto": 0, "fma": 1, "tcgen05": 2}[self.gemm_path])
+            gemm_path={"auto": 0, "fma": 1, "tcgen05": 2, "tcgen05_bf16": 3}[self.gemm_path])
 
     def _param_list(self):
         ls = self.pfn_layers

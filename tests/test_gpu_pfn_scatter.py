@@ -413,3 +413,42 @@ def test_pfn_vcd2_on_the_reference_fossil_inputs(chans, gemm, legacy):
         out = net(vox.to(DEV), nump.to(DEV), coors.to(DEV))
     assert_close(out.cpu().numpy(), ref, what=f"vcd2 legacy={legacy} {chans} {gemm}")
 
+
+
+@pytest.mark.parametrize("chans,C", [((128, 128, 128), 4), ((128, 64, 128), 5), ((64,), 4)])
+def test_pfn_bf16_tensor_core_path_within_1e2(chans, C):
+    """gemm_path='tcgen05_bf16' (north star: 1e-2 in bf16): layers >= 1 as single-pass bf16 MMAs with fp32 accumulation,
+    layer 0 (raw coordinates) stays 3xTF32. Against the dense fp32 oracle, 1e-2 of max|ref| norm-wise AND element-wise;
+    the fp32 path on the same inputs stays at 1e-5. Inference only: train mode and autograd refuse loudly."""
+    import mask_bev_b200 as M
+    from mask_bev_b200 import functional as F_
+    kw = ref_test_kwargs(feat_channels=chans, T=32, C=C)
+    enc, orc = encoder_pair(kw, seed=23)
+    enc = enc.to(DEV).eval()
+    orc.pfn.eval()
+    frames = _frames(30000, C, seeds=(31, 32))
+    with torch.no_grad():
+        ref = orc.forward(frames).numpy()
+        c32 = enc.encode_batch([torch.from_numpy(f).to(DEV) for f in frames])
+    enc._voxel_encoder.gemm_path = "tcgen05_bf16"
+    assert F_.pfn_path(enc._voxel_encoder._config(), 32) == "tcgen05_bf16"
+    with torch.no_grad():
+        c16 = enc.encode_batch([torch.from_numpy(f).to(DEV) for f in frames])
+        cb = enc.encode_batch([torch.from_numpy(f).to(DEV) for f in frames], canvas_dtype=torch.bfloat16)
+    assert_close(c32.cpu().numpy(), ref, what=f"fp32 path {chans}")
+    e = assert_close(c16.cpu().numpy(), ref, tol=1e-2, what=f"bf16 tensor-core PFN {chans}")
+    assert torch.equal(cb, c16.to(torch.bfloat16)), "bf16 canvas = the bf16-PFN canvas rounded to bf16"
+    if len(chans) == 1:
+        assert torch.equal(c16, c32), "a single-layer stack has no bf16 layer: identical to the fp32 path"
+    else:
+        assert e > 1e-5, "the bf16 layers must actually have run"
+    with pytest.raises(M.MbevError):
+        enc([torch.from_numpy(f).to(DEV) for f in frames])          # autograd on
+    enc.train()
+    with torch.no_grad(), pytest.raises(M.MbevError):
+        enc.encode_batch([torch.from_numpy(f).to(DEV) for f in frames])   # train-mode statistics
+    # stacks outside the warp-local kernel report unsupported
+    enc2, _ = encoder_pair(ref_test_kwargs(feat_channels=(16, 32, 64), T=32), seed=1)
+    enc2._voxel_encoder.gemm_path = "tcgen05_bf16"
+    with pytest.raises(M.MbevError):
+        F_.pfn_path(enc2._voxel_encoder._config(), 32)
