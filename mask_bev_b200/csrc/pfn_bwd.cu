@@ -334,6 +334,77 @@ k_build_x(const float *__restrict__ Y, const int U, const float *__restrict__ sc
   }
 }
 
+// Train mode: the batch statistics of layer l, recomputed from the Y_l THIS pass computed (sum over all P*T slots =
+// sum over compact rows of row_w * y). The forward may have run on the tensor cores (3xTF32) while this recompute runs
+// on the FMA pipe: the two Y agree to ~1e-6, but BatchNorm's backward subtracts sums that cancel, so normalising the
+// FMA rows with the tensor-core pass's mean / variance put train-mode gradients at 2x torch's own fp32 error. With
+// the statistics taken from the same rows the backward differentiates is self-consistent again. Block = (U, NL): lane
+// y walks rows ra + y, ra + y + NL, ...; fp64, fixed order.
+constexpr int kStatBlocks = 512;
+
+__global__ void __launch_bounds__(1024)
+k_row_stats(const float *__restrict__ Y, const int U, const float *__restrict__ row_w, const int *__restrict__ num_rows,
+            double *__restrict__ partials) {
+  extern __shared__ double s_sum[];  // [NL][2][U]
+  const int u = threadIdx.x, yl = threadIdx.y, NL = blockDim.y;
+  const int R = *num_rows;
+  const int per = (R + gridDim.x - 1) / gridDim.x;
+  const int ra = min(R, blockIdx.x * per), rb = min(R, ra + per);
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = ra + yl; r < rb; r += NL) {
+    const double y = static_cast<double>(Y[static_cast<size_t>(r) * U + u]);
+    const double wy = static_cast<double>(row_w[r]) * y;
+    s1 += wy;
+    s2 += wy * y;
+  }
+  s_sum[(yl * 2 + 0) * U + u] = s1;
+  s_sum[(yl * 2 + 1) * U + u] = s2;
+  __syncthreads();
+  if (yl == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int j = 0; j < NL; ++j) {
+      t1 += s_sum[(j * 2 + 0) * U + u];
+      t2 += s_sum[(j * 2 + 1) * U + u];
+    }
+    partials[(static_cast<size_t>(blockIdx.x) * 2 + 0) * U + u] = t1;
+    partials[(static_cast<size_t>(blockIdx.x) * 2 + 1) * U + u] = t2;
+  }
+}
+
+// one warp per unit (fixed-order lane-strided sums + shuffle tree). gamma / beta are recovered from the folded
+// scale / shift and the statistics the forward used: gamma = scale * sqrt(var + eps), beta = shift + mean * scale.
+__global__ void __launch_bounds__(256)
+k_row_stats_finalize(const double *__restrict__ partials, const int nblocks, const int U,
+                     const int *__restrict__ num_pillars, const int T, const float eps,
+                     const float *__restrict__ scale_fwd, const float *__restrict__ shift_fwd,
+                     const float *__restrict__ mean_fwd, const float *__restrict__ var_fwd, float *__restrict__ scale,
+                     float *__restrict__ shift, float *__restrict__ mean, float *__restrict__ var) {
+  const int u = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (u >= U) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    s1 += partials[(static_cast<size_t>(b) * 2 + 0) * U + u];
+    s2 += partials[(static_cast<size_t>(b) * 2 + 1) * U + u];
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if (lane) return;
+  const double M = static_cast<double>(*num_pillars) * T;
+  const double mu = M > 0 ? s1 / M : 0.0;
+  double v = M > 0 ? s2 / M - mu * mu : 0.0;
+  if (v < 0) v = 0;
+  const double gamma = static_cast<double>(scale_fwd[u]) * sqrt(static_cast<double>(var_fwd[u]) + static_cast<double>(eps));
+  const double beta = static_cast<double>(shift_fwd[u]) + static_cast<double>(mean_fwd[u]) * static_cast<double>(scale_fwd[u]);
+  const double sc = gamma / sqrt(v + static_cast<double>(eps));
+  scale[u] = static_cast<float>(sc);
+  shift[u] = static_cast<float>(beta - mu * sc);
+  mean[u] = static_cast<float>(mu);
+  var[u] = static_cast<float>(v);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // backward pieces
 // ---------------------------------------------------------------------------------------------------
@@ -445,6 +516,7 @@ k_dy(const float *__restrict__ Y, const int U, const float *__restrict__ scale, 
 struct BwdWs {
   int *row_off, *row_pillar, *num_rows;
   float *row_w, *X, *DZ, *DX, *Mx[MBEV_MAX_LAYERS], *Y[MBEV_MAX_LAYERS], *c12, *wpart;
+  float *stats;  // (L, 4, MBEV_MAX_UNITS): scale, shift, mean, var recomputed by this pass (train mode)
   double *partials;
   size_t bytes;
 };
@@ -474,6 +546,7 @@ BwdWs carve_bwd(void *ws, const MbevPfnParams *p, int64_t cap, int64_t rows_cap)
   w.c12 = c.take<float>(2 * umax);
   w.wpart = c.take<float>(static_cast<size_t>(kSplitK) * umax * inmax);
   w.partials = c.take<double>(static_cast<size_t>(kDzBlocks) * 2 * umax);
+  w.stats = c.take<float>(static_cast<size_t>(MBEV_MAX_LAYERS) * 4 * MBEV_MAX_UNITS);
   w.bytes = c.off;
   return w;
 }
@@ -560,10 +633,17 @@ extern "C" int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_i
 
   const int ew_blocks = kNumSMs * 8;
   const int m_tiles_cap = static_cast<int>(std::min<int64_t>((rows_cap + 63) / 64, 1 << 30));
-  auto SC = [&](int l) { return scale_shift + (2 * l) * MBEV_MAX_UNITS; };
-  auto SH = [&](int l) { return scale_shift + (2 * l + 1) * MBEV_MAX_UNITS; };
-  auto MEAN = [&](int l) { return batch_stats + (2 * l) * MBEV_MAX_UNITS; };
-  auto VAR = [&](int l) { return batch_stats + (2 * l + 1) * MBEV_MAX_UNITS; };
+  // train mode: scale / shift / mean / var come from THIS pass's rows (k_row_stats); eval mode: the forward's (running
+  // statistics, constants of the graph)
+  auto FSC = [&](int l) { return scale_shift + (2 * l) * MBEV_MAX_UNITS; };
+  auto FSH = [&](int l) { return scale_shift + (2 * l + 1) * MBEV_MAX_UNITS; };
+  auto FMEAN = [&](int l) { return batch_stats + (2 * l) * MBEV_MAX_UNITS; };
+  auto FVAR = [&](int l) { return batch_stats + (2 * l + 1) * MBEV_MAX_UNITS; };
+  auto RST = [&](int l, int which) { return w.stats + (4 * l + which) * MBEV_MAX_UNITS; };
+  auto SC = [&](int l) -> const float * { return train ? RST(l, 0) : FSC(l); };
+  auto SH = [&](int l) -> const float * { return train ? RST(l, 1) : FSH(l); };
+  auto MEAN = [&](int l) -> const float * { return train ? RST(l, 2) : FMEAN(l); };
+  auto VAR = [&](int l) -> const float * { return train ? RST(l, 3) : FVAR(l); };
 
   // ---- row space + forward recompute (keeps Y_l and m_l of every layer) --------------------------------
   k_row_offsets<<<1, 1024, 0, stream>>>(num_points, num_pillars_dev, T, w.row_off, w.num_rows);
@@ -580,6 +660,16 @@ extern "C" int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_i
     g.M = 0; g.N = U; g.K = K; g.m_dev = w.num_rows; g.k_dev = nullptr; g.split_stride = 0;
     int st = launch_gemm(g, m_tiles_cap, U, 1, stream);
     if (st) return st;
+    if (train) {
+      const int nls = std::max(1, 1024 / U);
+      k_row_stats<<<kStatBlocks, dim3(U, nls), sizeof(double) * 2 * U * nls, stream>>>(w.Y[l], U, w.row_w, w.num_rows,
+                                                                                      w.partials);
+      MBEV_CHECK_LAUNCH();
+      k_row_stats_finalize<<<(U + 7) / 8, 256, 0, stream>>>(w.partials, kStatBlocks, U, num_pillars_dev, T, eps, FSC(l),
+                                                            FSH(l), FMEAN(l), FVAR(l), RST(l, 0), RST(l, 1), RST(l, 2),
+                                                            RST(l, 3));
+      MBEV_CHECK_LAUNCH();
+    }
     k_act_max<<<ew_blocks, kThreads, 0, stream>>>(w.Y[l], U, SC(l), SH(l), w.row_off, num_pillars_dev, w.Mx[l]);
     MBEV_CHECK_LAUNCH();
     if (l + 1 < L) {

@@ -182,11 +182,24 @@ __device__ __forceinline__ void split_store16(uint32_t t_hi, uint32_t t_lo, cons
   tmem_st16(t_lo, lo);
 }
 
-// bf16 form of split_store16: 16 K elements -> 8 packed columns
-__device__ __forceinline__ void pack_store16(uint32_t t_a, const float (&a)[16]) {
-  uint32_t v[8];
-  pack_bf16x16(a, v);
-  tmem_st8(t_a, v);
+// bf16 form of the segmented max: rounding to bf16 is monotonic, so max(bf16(a)) == bf16(max(a)) — the scan can run on
+// the 8 PACKED registers that go to tensor memory anyway: half the shuffles and half the max instructions.
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void seg_max8_bf16(const Window &w, int lane, uint32_t (&v)[8]) {
+  for (int d = 1; d < w.maxlen; d <<= 1) {
+    const bool take = lane - d >= w.s0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, v[j], d);
+      v[j] = take ? max_bf16x2(v[j], o) : v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __shfl_sync(0xffffffffu, v[j], w.s1);
 }
 
 // per-pillar max over the lanes of the window: segmented inclusive max-scan, then read the pillar's last lane
@@ -368,28 +381,50 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
         } else {
           // non-last layers have U <= 64: at most two 16-column batches per warp, kept in registers across the
           // "x consumed" wait
-          float a0[16], a1[16];
           const uint32_t c0 = static_cast<uint32_t>(h * Uh);
-          const uint32_t ca = kBf16 ? (c0 >> 1) : c0;  // A column of K element c0 (bf16: two elements per column)
-          load_bn_relu(t_d + c0, sc, sh, a0);
-          if (kBf16) pack_store16(t_ah + ca, a0); else split_store16(t_ah + c0, t_al + c0, a0);  // x half: K index = unit index
-          if (nbat > 1) {
-            load_bn_relu(t_d + c0 + 16, sc + 16, sh + 16, a1);
-            if (kBf16) pack_store16(t_ah + ca + 8, a1); else split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
-          }
-          tc_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bs + 8 * kW2EVX);
-          seg_max16(w, lane, a0);  // runs while the x-part MMAs do
-          if (nbat > 1) seg_max16(w, lane, a1);
-          mbar_wait(bs + 8 * kW2XC, par_xc);  // the x-part MMAs have read A: its columns are free again
-          par_xc ^= 1u;
-          tc_fence_after();
-          // max half: K index = U + unit index, same A columns
-          if (kBf16) pack_store16(t_ah + ca, a0); else split_store16(t_ah + c0, t_al + c0, a0);
-          if (nbat > 1) {
-            if (kBf16) pack_store16(t_ah + ca + 8, a1); else split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
+          if (kBf16) {
+            // next layer's operands are bf16: pack once, store the x half, scan the packed registers, store the max half
+            const uint32_t ca = c0 >> 1;  // A column of K element c0 (two bf16 per column)
+            float a[16];
+            uint32_t v0[8], v1[8];
+            load_bn_relu(t_d + c0, sc, sh, a);
+            pack_bf16x16(a, v0);
+            tmem_st8(t_ah + ca, v0);
+            if (nbat > 1) {
+              load_bn_relu(t_d + c0 + 16, sc + 16, sh + 16, a);
+              pack_bf16x16(a, v1);
+              tmem_st8(t_ah + ca + 8, v1);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bs + 8 * kW2EVX);
+            seg_max8_bf16(w, lane, v0);  // runs while the x-part MMAs do
+            if (nbat > 1) seg_max8_bf16(w, lane, v1);
+            mbar_wait(bs + 8 * kW2XC, par_xc);  // the x-part MMAs have read A: its columns are free again
+            par_xc ^= 1u;
+            tc_fence_after();
+            tmem_st8(t_ah + ca, v0);  // max half: K index = U + unit index, same A columns
+            if (nbat > 1) tmem_st8(t_ah + ca + 8, v1);
+          } else {
+            float a0[16], a1[16];
+            load_bn_relu(t_d + c0, sc, sh, a0);
+            split_store16(t_ah + c0, t_al + c0, a0);  // x half: K index = unit index
+            if (nbat > 1) {
+              load_bn_relu(t_d + c0 + 16, sc + 16, sh + 16, a1);
+              split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bs + 8 * kW2EVX);
+            seg_max16(w, lane, a0);  // runs while the x-part MMAs do
+            if (nbat > 1) seg_max16(w, lane, a1);
+            mbar_wait(bs + 8 * kW2XC, par_xc);  // the x-part MMAs have read A: its columns are free again
+            par_xc ^= 1u;
+            tc_fence_after();
+            split_store16(t_ah + c0, t_al + c0, a0);  // max half: K index = U + unit index, same A columns
+            if (nbat > 1) split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
           }
           tc_wait_st();
           tc_fence_before();

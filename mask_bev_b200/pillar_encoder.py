@@ -50,12 +50,7 @@ class _PfnFunction(torch.autograd.Function):
             raise MbevError("gemm_path='tcgen05_bf16' is the inference path (eval mode, no autograd): batch statistics and "
                             "the backward need the fp32-accurate kernels")
         if not isinstance(ctx, _NullCtx) and cfg.gemm_path == 0 and not net.autograd_tensor_cores:
-            # A backward will follow: K2' recomputes the activations on the fp32 FMA pipe, and the parameter
-            # gradients of a train-mode BatchNorm stack are ill-conditioned (torch's own fp32 autograd is ~2e-3 from
-            # float64 on the 3-layer stack). Use the FMA forward here so that the saved statistics are bit-consistent
-            # with what the backward recomputes; the tensor-core forward serves inference and no-grad calls.
-            # Measured: with the tensor-core forward (net.autograd_tensor_cores = True) the kitti_b16 training step drops from 26.7
-            # to 20.9 ms, but two train-mode gradient-parity cases land at 3.4e-3 of float64 (torch fp32: 1.6e-3).
+            # opt-out: forward on the fp32 FMA pipe, bit-consistent with what K2' recomputes (round 1's default).
             cfg.gemm_path = 1
         if training:
             feats, scale_shift, batch_stats = F_.pfn_forward_train(rows, kept_idx, num_points, coors, npil_dev,
@@ -124,9 +119,11 @@ class PillarFeatureNet(nn.Module):
         # forward Linear layers: 'auto' (tcgen05 3xTF32 when the stack fits, else fp32 FMA), 'fma', 'tcgen05',
         # 'tcgen05_bf16' (inference only: layers >= 1 as single-pass bf16 MMAs, 1e-2 tolerance class)
         self.gemm_path = "auto"
-        # forward under autograd on the tensor cores too (faster; train-mode gradient parity then sits at 1.5-2x
-        # torch's own fp32 error instead of within it — see _PfnFunction.forward)
-        self.autograd_tensor_cores = False
+        # forward under autograd on the tensor cores as well. K2' recomputes the activations on the fp32 FMA pipe and, in
+        # train mode, takes the BatchNorm batch statistics from ITS OWN rows (k_row_stats), so the backward stays
+        # self-consistent although the two passes differ by ~1e-6 (with the forward's statistics reused, round 1 measured
+        # train-mode gradients at 2x torch's own fp32 error). False: FMA forward, bit-consistent with the recompute.
+        self.autograd_tensor_cores = True
 
     # -- helpers ------------------------------------------------------------------------------------
     def _config(self) -> F_.PfnConfig:
