@@ -648,7 +648,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: ONE batch of the workload's size split over the ranks (BASELINE configs[2])")
     ap.add_argument("--serial", action="store_true", help="value / e2e on one stream (no three-stage pipeline)")
-    ap.add_argument("--scatter-ctas", type=int, default=1,
+    ap.add_argument("--scatter-ctas", type=int, default=0,
                     help="K3 of the pipelined step: CTAs per SM of the TMA-engine scatter (0: the register scatter)")
     ap.add_argument("--train", action="store_true", help="also time the encoder's training step (always on when N > 1)")
     ap.add_argument("--no-train", action="store_true")

@@ -221,7 +221,7 @@ __device__ __forceinline__ void seg_max16(const Window &w, int lane, float (&a)[
 }
 
 template <bool kBf16>
-__global__ void __maxnreg__(88)
+__global__ void __launch_bounds__(kW2Threads, 1)
 k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, const int *__restrict__ num_points,
            const int *__restrict__ coors, const int *__restrict__ bounds8, float *__restrict__ feats,
            const __grid_constant__ Kargs k) {

@@ -103,9 +103,10 @@ k_scatter_run(const float *__restrict__ feats, const int *__restrict__ table, co
 //     lane, nothing to wait for) — on LiDAR frames that is most of the canvas bytes;
 //   * a half run with pillars is composed LANE = PILLAR: the <= 32 pillars of a segment are ranked with ballots, lane L
 //     loads 16 channels of ITS pillar's feature row per batch (4 independent 16-byte loads, double buffered: the next
-//     batch is in flight while this one is emitted), and per plane four shuffles move the values to the lanes that own
-//     the cells (lane l = cells 4l .. 4l+3), which store 512 contiguous bytes with st.global.cs.v4. One L2 round trip
-//     per 16 planes and segment instead of one per plane; no shared-memory staging, no proxy fence, no bulk wait.
+//     batch is in flight while this one is emitted; with <= 16 / <= 8 pillars the idle lanes load 2 / 4 plane groups
+//     at once), and per plane four shuffles move the values to the lanes that own the cells (lane l = cells
+//     4l .. 4l+3), which store 512 contiguous bytes with st.global.cs.v4. One L2 round trip per 16-64 planes and
+//     segment instead of one per plane; no shared-memory staging, no proxy fence, no bulk wait.
 //     Segments: the whole half (128 cells) when it holds <= 32 pillars, else its two 64-cell halves, else four 32-cell
 //     quarters (which cannot hold more than 32).
 constexpr int kBulkThreads = 128;  // 4 warps
@@ -120,67 +121,82 @@ __device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// one segment: the lanes with `active` hold 4 consecutive cells each (p4 = their pillar ids), <= 32 pillars in all
+// One segment: lane l owns cells 4l .. 4l+3 of each of the run's two strips (p4[k] = their pillar ids); `act` bit k is
+// set when this lane's cells of strip k belong to the segment (<= 32 pillars in all active cells). `strips` (warp-uniform)
+// says which strips have any active lane. With np <= 16 (<= 8) pillars the idle lanes take further PLANE GROUPS of the same
+// pillars: lane = (pillar, group), 2 (4) groups of 16 planes per batch, so a 128-channel row needs 4 (2) dependent L2
+// round trips instead of 8. A whole run with <= 32 pillars (the usual LiDAR case) writes 1 KB contiguous per plane.
 __device__ __forceinline__ void compose_segment(const float *__restrict__ feats, const int C, const size_t G,
-                                                const int4 p4, const bool active, int *s_list, float *out_lane,
-                                                const int lane) {
-  const int pj[4] = {p4.x, p4.y, p4.z, p4.w};
+                                                const int4 (&p4)[2], const unsigned act, const unsigned strips,
+                                                int *s_list, float *out_lane, const int lane) {
   const unsigned lt = (1u << lane) - 1u;
-  bool occ[4];
-  int rank[4], np = 0;
+  // per cell slot (strip k, cell j): the pillar lane that holds its features (5 bits) and whether it is occupied —
+  // packed, 4 slots per register, so that the composing loop below lives in 64 registers
+  uint32_t rk[2] = {0u, 0u}, oc = 0;
+  int np = 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    occ[j] = active && pj[j] >= 0;
-    const unsigned m = __ballot_sync(0xffffffffu, occ[j]);
-    rank[j] = (np + __popc(m & lt)) & 31;
-    np += __popc(m);
+  for (int k = 0; k < 2; ++k) {
+    const int pj[4] = {p4[k].x, p4[k].y, p4[k].z, p4[k].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool o = ((act >> k) & 1u) && pj[j] >= 0;
+      const unsigned m = __ballot_sync(0xffffffffu, o);
+      const int r = (np + __popc(m & lt)) & 31;
+      rk[k] |= static_cast<uint32_t>(r) << (8 * j);
+      oc |= (o ? 1u : 0u) << (4 * k + j);
+      np += __popc(m);
+      if (o) s_list[r] = pj[j];
+    }
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (occ[j]) s_list[rank[j]] = pj[j];
   __syncwarp();
-  const int mypid = lane < np ? s_list[lane] : -1;
+  const int gsh = np <= 8 ? 2 : (np <= 16 ? 1 : 0);  // log2(plane groups)
+  const int npad = 32 >> gsh;                        // lanes per group
+  const int me = lane & (npad - 1), grp = lane >> (5 - gsh);
+  const int mypid = me < np ? s_list[me] : -1;
   __syncwarp();  // the list may be rewritten by the next segment
-  const float4 *row = reinterpret_cast<const float4 *>(feats + static_cast<size_t>(max(mypid, 0)) * C);
+  const int step = 16 << gsh;  // planes per batch
+  const float4 *row = reinterpret_cast<const float4 *>(feats + static_cast<size_t>(max(mypid, 0)) * C) + 4 * grp;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   auto load = [&](float4 (&f)[4], const int p0) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) f[r] = (mypid >= 0 && p0 + 4 * r < C) ? __ldg(row + (p0 >> 2) + r) : z;
-  };
-  auto plane = [&](const float fq, float *o) {
-    float4 v;
-    v.x = __shfl_sync(0xffffffffu, fq, rank[0]);
-    v.y = __shfl_sync(0xffffffffu, fq, rank[1]);
-    v.z = __shfl_sync(0xffffffffu, fq, rank[2]);
-    v.w = __shfl_sync(0xffffffffu, fq, rank[3]);
-    v.x = occ[0] ? v.x : 0.f;
-    v.y = occ[1] ? v.y : 0.f;
-    v.z = occ[2] ? v.z : 0.f;
-    v.w = occ[3] ? v.w : 0.f;
-    if (active) st_global_v4_stream_nc(o, v);
+    for (int r = 0; r < 4; ++r) f[r] = (mypid >= 0 && p0 + 16 * grp + 4 * r < C) ? __ldg(row + (p0 >> 2) + r) : z;
   };
   auto emit = [&](const float4 (&f)[4], const int p0) {
+    for (int g = 0; g < (1 << gsh); ++g) {
+      const unsigned src0 = static_cast<unsigned>(g * npad);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (p0 + 4 * r >= C) break;
-      float *o = out_lane + static_cast<size_t>(p0 + 4 * r) * G;
-      plane(f[r].x, o);
-      plane(f[r].y, o + G);
-      plane(f[r].z, o + 2 * G);
-      plane(f[r].w, o + 3 * G);
+      for (int r = 0; r < 4; ++r) {
+        if (p0 + 16 * g + 4 * r >= C) break;
+        float *o = out_lane + static_cast<size_t>(p0 + 16 * g + 4 * r) * G;
+        const float fq[4] = {f[r].x, f[r].y, f[r].z, f[r].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            if (!((strips >> k) & 1u)) continue;  // warp-uniform: every lane runs the same shuffles
+            float4 v;
+            v.x = __shfl_sync(0xffffffffu, fq[q], (rk[k] & 31u) + src0);
+            v.y = __shfl_sync(0xffffffffu, fq[q], ((rk[k] >> 8) & 31u) + src0);
+            v.z = __shfl_sync(0xffffffffu, fq[q], ((rk[k] >> 16) & 31u) + src0);
+            v.w = __shfl_sync(0xffffffffu, fq[q], ((rk[k] >> 24) & 31u) + src0);
+            v.x = (oc >> (4 * k + 0)) & 1u ? v.x : 0.f;
+            v.y = (oc >> (4 * k + 1)) & 1u ? v.y : 0.f;
+            v.z = (oc >> (4 * k + 2)) & 1u ? v.z : 0.f;
+            v.w = (oc >> (4 * k + 3)) & 1u ? v.w : 0.f;
+            if ((act >> k) & 1u) st_global_v4_stream_nc(o + static_cast<size_t>(q) * G + kStrip * k, v);
+          }
+        }
+      }
     }
   };
-  float4 fa[4], fb[4];
-  load(fa, 0);
-  for (int p0 = 0; p0 < C; p0 += 32) {
-    if (p0 + 16 < C) load(fb, p0 + 16);
-    emit(fa, p0);
-    if (p0 + 32 < C) load(fa, p0 + 32);
-    if (p0 + 16 < C) emit(fb, p0 + 16);
+  float4 f[4];
+  for (int p0 = 0; p0 < C; p0 += step) {
+    load(f, p0);
+    emit(f, p0);
   }
 }
 
-__global__ void __launch_bounds__(kBulkThreads, 8)  // <= 64 registers: 5 K2 warps at 88 leave 2304 on a sub-partition
+__global__ void __launch_bounds__(kBulkThreads, 7)  // <= 72 registers: what 5 K2 warps capped at 88 leave on an SM sub-partition
 k_scatter_bulk(const float *__restrict__ feats, const int *__restrict__ table, const int C, const int G,
                const int runs_per_frame, const int num_runs, float *__restrict__ canvas) {
   __shared__ __align__(128) float s_zero[kRunCells];
@@ -193,7 +209,34 @@ k_scatter_bulk(const float *__restrict__ feats, const int *__restrict__ table, c
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   const uint32_t zero = smem_addr(s_zero);
   const int nw = gridDim.x * (kBulkThreads / 32);
+  const int row_lines = (C * 4 + 127) >> 7;  // 128-byte lines per feature row
   for (int task = blockIdx.x * (kBulkThreads / 32) + warp; task < num_runs; task += nw) {
+    // Software pipeline over this warp's runs: the feature rows are read once, from L2 or (the 180 MB of a batch do not
+    // all stay there under a 5 GB write stream) from DRAM behind a saturated write queue — microseconds. Two runs
+    // ahead: the table lines go to L1; one run ahead: the table is read (an L1 hit by then) and every lane asks for the
+    // rows of the pillars in ITS cells to be brought to L2. Prefetches hold no registers and are never waited for.
+    if (task + 2 * nw < num_runs && lane < kRunCells / 32) {
+      const int run2 = num_runs - 1 - (task + 2 * nw);
+      const int b2 = run2 / runs_per_frame;
+      const int c2 = (run2 - b2 * runs_per_frame) * kRunCells + 32 * lane;
+      if (c2 < G) asm volatile("prefetch.global.L1 [%0];" ::"l"(table + static_cast<size_t>(b2) * G + c2));
+    }
+    if (task + nw < num_runs) {
+      const int run1 = num_runs - 1 - (task + nw);
+      const int b1 = run1 / runs_per_frame;
+      int4 pn[2];
+      bool any1;
+      load_run_table(table, b1, G, (run1 - b1 * runs_per_frame) * kRunCells + 4 * lane, pn, any1);
+      if (any1) {
+        const int q[8] = {pn[0].x, pn[0].y, pn[0].z, pn[0].w, pn[1].x, pn[1].y, pn[1].z, pn[1].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (q[j] < 0) continue;
+          const char *rowp = reinterpret_cast<const char *>(feats + static_cast<size_t>(q[j]) * C);
+          for (int l = 0; l < row_lines; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + 128 * l));
+        }
+      }
+    }
     const int run = num_runs - 1 - task;  // last frame first: its feature rows are the freshest in L2
     const int b = run / runs_per_frame;
     const int r0 = (run - b * runs_per_frame) * kRunCells;
@@ -207,23 +250,29 @@ k_scatter_bulk(const float *__restrict__ feats, const int *__restrict__ table, c
       bulk_commit();
       continue;
     }
+    const unsigned inr = (r0 + 4 * lane < G ? 1u : 0u) | (r0 + kStrip + 4 * lane < G ? 2u : 0u);  // my cells exist
+    const int c0 = (pid[0].x >= 0) + (pid[0].y >= 0) + (pid[0].z >= 0) + (pid[0].w >= 0);
+    const int c1 = (pid[1].x >= 0) + (pid[1].y >= 0) + (pid[1].z >= 0) + (pid[1].w >= 0);
+    if (__reduce_add_sync(0xffffffffu, c0 + c1) <= 32) {
+      // the whole run holds <= 32 pillars (the usual LiDAR case): one segment, 1 KB contiguous per plane
+      const unsigned strips = (__ballot_sync(0xffffffffu, inr & 1u) ? 1u : 0u) | (__ballot_sync(0xffffffffu, inr & 2u) ? 2u : 0u);
+      compose_segment(feats, C, static_cast<size_t>(G), pid, inr, strips, s_lists[warp], out + 4 * lane, lane);
+      continue;
+    }
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {
       const int cells = min(kStrip, G - (r0 + kStrip * k));
       if (cells <= 0) break;
-      const int4 p4 = k ? pid[1] : pid[0];
-      const bool active = 4 * lane < cells;
-      const bool mine = active && (p4.x & p4.y & p4.z & p4.w) >= 0;
-      const unsigned lanes_occ = __ballot_sync(0xffffffffu, mine);
-      float *o = out + kStrip * k;
-      if (lanes_occ == 0u) {  // an empty half: bulk zeros
+      const bool active = (inr >> k) & 1u;
+      const int cnt = k ? c1 : c0;
+      if (__ballot_sync(0xffffffffu, active && cnt > 0) == 0u) {  // an empty half: bulk zeros
+        float *o = out + kStrip * k;
         for (int ch = lane; ch < C; ch += 32)
           bulk_s2g(o + static_cast<size_t>(ch) * G, zero, static_cast<uint32_t>(cells) * 4u, policy);
         bulk_commit();
         continue;
       }
       // pillars per 32-cell quarter (8 lanes each) -> segment length
-      const int cnt = (p4.x >= 0) + (p4.y >= 0) + (p4.z >= 0) + (p4.w >= 0);
       int q = active ? cnt : 0;
       q += __shfl_xor_sync(0xffffffffu, q, 1);
       q += __shfl_xor_sync(0xffffffffu, q, 2);
@@ -232,10 +281,12 @@ k_scatter_bulk(const float *__restrict__ feats, const int *__restrict__ table, c
       const int t = h + __shfl_xor_sync(0xffffffffu, h, 16);   // ... of the strip
       // segment = 128 >> sh cells = 32 >> sh lanes: the whole half, its two halves, or its four quarters
       const int sh = (t <= 32) ? 0 : (__all_sync(0xffffffffu, h <= 32) ? 1 : 2);
-      float *ol = o + 4 * lane;
 #pragma unroll 1
-      for (int s = 0; s < (1 << sh); ++s)
-        compose_segment(feats, C, static_cast<size_t>(G), p4, active && (lane >> (5 - sh)) == s, s_lists[warp], ol, lane);
+      for (int sg = 0; sg < (1 << sh); ++sg) {
+        const unsigned act = (active && (lane >> (5 - sh)) == sg) ? (1u << k) : 0u;
+        if (__ballot_sync(0xffffffffu, act) == 0u) continue;  // beyond the ragged tail of the frame
+        compose_segment(feats, C, static_cast<size_t>(G), pid, act, 1u << k, s_lists[warp], out + 4 * lane, lane);
+      }
     }
   }
   bulk_commit();

@@ -16,10 +16,12 @@ from ._lib import check, ptr
 
 
 class FusedEncoderRunner:
-    """`scatter_ctas_per_sm`: K3 of the pipelined entry — 1 (default) = the TMA-engine scatter with one small CTA per
-    SM, which shares the SMs with K2 of the next batch; 0 = the stand-alone register scatter (does not co-run with K2)."""
+    """`scatter_ctas_per_sm`: K3 of the pipelined entry — 0 (default) = the register scatter on a machine-filling grid;
+    N >= 1 = the small-footprint scatter (k_scatter_bulk) with N CTAs per SM. Measured on B200 (kitti_b16,
+    profiles/r2_corun_probes.txt): 0 is the fastest — a co-resident K2 and K3 slow each other down by more than the
+    overlap gains."""
 
-    def __init__(self, encoder, frame_sizes: Sequence[int], device: torch.device, scatter_ctas_per_sm: int = 1):
+    def __init__(self, encoder, frame_sizes: Sequence[int], device: torch.device, scatter_ctas_per_sm: int = 0):
         self.enc = encoder
         self.device = torch.device(device)
         self.lib = _lib.load()

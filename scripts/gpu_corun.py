@@ -68,3 +68,29 @@ ta = timed(k3, s3); tb = timed(r.run_pfn, s2)
 report("concurrent, empty table:", (f"K3 stream x{ctas} zeros only", ta), ("K2", tb))
 report("alone, empty table     :", (f"K3 stream x{ctas} zeros only", timed(k3, s3)))
 r.cell_table.copy_(table)
+
+# ---- clocks / power during long loops: is the concurrent slowdown a power cap? ----
+def sampled(tag, fns, n=150):
+    samp = bench.NvmlSampler(0)
+    samp.start()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    ts = [timed(fn, st, n) for fn, st in fns]
+    for _, st in fns:
+        torch.cuda.current_stream().wait_stream(st)
+    b.record()
+    torch.cuda.synchronize()
+    c = samp.stop()
+    print(f"{tag}: wall {a.elapsed_time(b) / n:.3f} ms/iter  " + "  ".join(f"{x.elapsed_time(y) / m:.3f}" for x, y, m in ts) +
+          f"  sm_mhz median {c.get('sm_mhz')} min {c.get('sm_min_mhz')} power_max {c.get('power_w_max')} reasons {c.get('reasons')}")
+
+
+sampled("K2 alone        ", [(r.run_pfn, s2)])
+sampled("K3 stream alone ", [(k3, s3)])
+sampled("K3 register     ", [(r.run_scatter, s3)])
+sampled("K2 || K3 stream ", [(k3, s3), (r.run_pfn, s2)])
+r.cell_table.fill_(-1)
+sampled("K2 || K3 zeros  ", [(k3, s3), (r.run_pfn, s2)])
+sampled("K3 zeros alone  ", [(k3, s3)])
+r.cell_table.copy_(table)

@@ -248,7 +248,8 @@ def test_tcgen05_forced_on_unsupported_stack_fails_loudly():
 
 
 @pytest.mark.parametrize("rng,vs,chans", [((-40, 40), 0.16, (64,)), ((-31.25, 31.25), 0.25, (128, 128, 128)),
-                                          ((-20, 20), 0.32, (32, 64))])
+                                          ((-20, 20), 0.32, (32, 64)), ((-20.48, 20.48), 0.32, (64,)),
+                                          ((-20.48, 20.48), 0.16, (128, 128, 128))])
 def test_scatter_forms_bit_identical(rng, vs, chans):
     """The TMA-engine scatter (mbev_scatter_forward_stream, 1 and 4 CTAs per SM) and the channels-last scatter write
     the same values as the register scatter, bit for bit — on grids whose plane is a whole number of 256-cell runs
@@ -258,7 +259,11 @@ def test_scatter_forms_bit_identical(rng, vs, chans):
     kw = ref_test_kwargs(feat_channels=chans, T=32, vs=vs, x_range=rng, y_range=rng)
     enc, _ = encoder_pair(kw, seed=2)
     enc = enc.to(DEV).eval()
-    frames = _frames(30000, 4, seeds=(1, 2, 3)) + [np.zeros((0, 4), np.float32)]
+    from mask_bev_b200.synthetic import gen_dense_frame
+    # LiDAR-shaped frames (sparse runs), an empty frame, and a dense frame: runs with far more than 32 pillars take
+    # the stream form's 64- / 32-cell segments, half-occupied ones its whole-run and half-run segments
+    frames = _frames(30000, 4, seeds=(1, 2, 3)) + [np.zeros((0, 4), np.float32), gen_dense_frame(60000, 4, 5, half=rng[1]),
+                                                   gen_dense_frame(3000, 4, 6, half=rng[1])]
     with torch.no_grad():
         canvas, aux = enc.encode_batch([torch.from_numpy(f).to(DEV) for f in frames], return_aux=True)
     B, C, ny, nx = canvas.shape
