@@ -580,8 +580,8 @@ def run_ours(args):
     roof = {"kernel": f"{k3_key} ({k3['kernel']})", "bound": "hbm", "achieved": k3["gbs"], "peak": peak, "unit": "GB/s",
             "frac": k3["frac_hbm"], "traffic": None, "peak_source": peak_src, "launch_ms": k3["ms"],
             "dominant_by_time": dom, "share_of_serial_step": k3["ms"] / (t_vox + t_pfn + k3["ms"]),
-            "timed": "stand-alone launches (CUDA events on the launching stream, inputs resident); inside the "
-                     "pipelined step this kernel shares the SMs with K2 of the next batch",
+            "timed": "stand-alone launches (CUDA events on the launching stream, inputs resident)"
+                     + ("; inside the pipelined step this kernel shares the SMs with K2 of the next batch" if use_stream else ""),
             "step_floor_bytes": by_floor, "step_frac": by_floor / step_ms / 1e6 / peak,
             "step_frac_note": "fused-path HBM floor (points read once + canvas written once) / ms_per_step / peak",
             "serial_step_frac": by_floor / (ms_serial / args.steps) / 1e6 / peak}
