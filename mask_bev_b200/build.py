@@ -45,7 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH + ".tmp", *srcs]
+    extra = os.environ.get("MBEV_NVCC_EXTRA", "").split()  # developer builds (-DMBEV_K2_TRACE); never set by the product
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH + ".tmp", *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), flush=True)

@@ -692,3 +692,9 @@ extern "C" int mbev_pfn_forward_train(const float *rows, int C, const int32_t *k
   }
   return launch_pfn(pl, rows, kept_idx, num_points, coors, num_pillars_dev, pillar_capacity, feats, -1, stream);
 }
+
+#ifdef MBEV_K2_TRACE
+extern "C" __attribute__((visibility("default"))) int mbev_debug_k2_trace(long long *host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, mbev::tc::g_k2_trace, sizeof(long long) * 18 * 8 * 24));
+}
+#endif

@@ -33,6 +33,17 @@ constexpr int kW2SetCols = 256;                         // TMEM columns per set:
 constexpr int kW2BarW = 0, kW2BarSet = 1, kW2BarsPerSet = 5, kW2NumBars = kW2BarSet + kW2Sets * kW2BarsPerSet;
 enum { kW2X0 = 0, kW2D = 1, kW2XC = 2, kW2EVX = 3, kW2EVM = 4 };
 
+#ifdef MBEV_K2_TRACE
+// developer build only: cycle stamps of CTA 0 (18 warps x 8 chunks x 24 slots), read back by mbev_debug_k2_trace
+__device__ long long g_k2_trace[18 * 8 * 24];
+#define MBEV_TR(slot)                                                                                   \
+  do {                                                                                                  \
+    if (blockIdx.x == 0 && lane == 0 && c >= 6 && c < 14) g_k2_trace[(warp * 8 + (c - 6)) * 24 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define MBEV_TR(slot) do {} while (0)
+#endif
+
 struct Window {
   int cnt, nrows;  // pillars / rows packed into this window
   int pil;         // global pillar of this lane's row
@@ -174,6 +185,21 @@ __device__ __forceinline__ void load_bn_relu(uint32_t taddr, const float *sc, co
   }
 }
 
+__device__ __forceinline__ void load_bn_relu32(uint32_t taddr, const float *sc, const float *sh, float (&a)[32]) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+  tc_wait_ld();
+  const float4 *sc4 = reinterpret_cast<const float4 *>(sc), *sh4 = reinterpret_cast<const float4 *>(sh);
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 c = sc4[j4], s = sh4[j4];
+    a[4 * j4 + 0] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), c.x, s.x), 0.f);
+    a[4 * j4 + 1] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), c.y, s.y), 0.f);
+    a[4 * j4 + 2] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), c.z, s.z), 0.f);
+    a[4 * j4 + 3] = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), c.w, s.w), 0.f);
+  }
+}
+
 __device__ __forceinline__ void split_store16(uint32_t t_hi, uint32_t t_lo, const float (&a)[16]) {
   uint32_t hi[16], lo[16];
 #pragma unroll
@@ -182,41 +208,37 @@ __device__ __forceinline__ void split_store16(uint32_t t_hi, uint32_t t_lo, cons
   tmem_st16(t_lo, lo);
 }
 
-// bf16 form of the segmented max: rounding to bf16 is monotonic, so max(bf16(a)) == bf16(max(a)) — the scan can run on
-// the 8 PACKED registers that go to tensor memory anyway: half the shuffles and half the max instructions.
+// Per-pillar max over the lanes of the window as a CYCLIC DOUBLING all-reduce: in round d every lane takes the max with
+// the lane d rows further down its own pillar, wrapping to the pillar's first row — max is idempotent, so after
+// ceil(log2(len)) rounds every lane of the pillar holds the max over the whole pillar, for any mix of pillar lengths in
+// one warp (a lane whose pillar is not longer than d reads itself). No select, no broadcast round: one shuffle + one
+// max per register and round. N registers are scanned together so that N independent shuffles are in flight.
+__device__ __forceinline__ int cyc_src(const Window &w, int lane, int d) {
+  const int len = w.s1 - w.s0 + 1;
+  const int t2 = w.t + d;
+  return d < len ? (t2 < len ? lane + d : lane + d - len) : lane;
+}
+template <int N>
+__device__ __forceinline__ void seg_allmax(const Window &w, int lane, float (&a)[N]) {
+  for (int d = 1; d < w.maxlen; d <<= 1) {
+    const int src = cyc_src(w, lane, d);
+#pragma unroll
+    for (int j = 0; j < N; ++j) a[j] = fmaxf(a[j], __shfl_sync(0xffffffffu, a[j], src));
+  }
+}
+// bf16 form: rounding to bf16 is monotonic, so max(bf16(a)) == bf16(max(a)) — the all-reduce can run on the PACKED
+// registers that go to tensor memory anyway: half the shuffles and half the max instructions.
 __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
-__device__ __forceinline__ void seg_max8_bf16(const Window &w, int lane, uint32_t (&v)[8]) {
+template <int N>
+__device__ __forceinline__ void seg_allmax_bf16(const Window &w, int lane, uint32_t (&v)[N]) {
   for (int d = 1; d < w.maxlen; d <<= 1) {
-    const bool take = lane - d >= w.s0;
+    const int src = cyc_src(w, lane, d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, v[j], d);
-      v[j] = take ? max_bf16x2(v[j], o) : v[j];
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __shfl_sync(0xffffffffu, v[j], w.s1);
-}
-
-// per-pillar max over the lanes of the window: segmented inclusive max-scan, then read the pillar's last lane
-// (kBroadcast = false: only the pillar's LAST lane holds the result — enough for the last layer's store)
-template <bool kBroadcast = true>
-__device__ __forceinline__ void seg_max16(const Window &w, int lane, float (&a)[16]) {
-  for (int d = 1; d < w.maxlen; d <<= 1) {
-    const bool take = lane - d >= w.s0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float o = __shfl_up_sync(0xffffffffu, a[j], d);
-      a[j] = take ? fmaxf(a[j], o) : a[j];
-    }
-  }
-  if (kBroadcast) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = __shfl_sync(0xffffffffu, a[j], w.s1);
+    for (int j = 0; j < N; ++j) v[j] = max_bf16x2(v[j], __shfl_sync(0xffffffffu, v[j], src));
   }
 }
 
@@ -264,23 +286,31 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
 
   if (warp >= kW2EpiWarps) {
     // =========================================== MMA issuer of set `set` =====================================
-    const int set = warp - kW2EpiWarps;
-    const bool leader = lane == 0;
-    if (leader && set == 0) {
-      mbar_expect_tx(bar_w, k.w_bytes);  // weights: global image -> shared memory, resident, shared by both sets
-      for (uint32_t off = 0; off < k.w_bytes; off += 32768u)
-        bulk_g2s(smem_base + off, reinterpret_cast<const char *>(k.w_img) + off, min(32768u, k.w_bytes - off), bar_w);
+    // Every operand of tcgen05.mma below is WARP-UNIFORM and provably so for the compiler (kernel parameters, a
+    // constant-lane shuffle of the warp index and of the TMEM base, uniform loop counters), and the issuing thread is
+    // chosen by elect.sync: the descriptors then live in uniform registers. With `if (lane == 0)` and per-thread
+    // operands ptxas wraps every single MMA in an ELECT / 6 x R2UR / branch waterfall (~90 cycles per instruction —
+    // three times the tensor pipe's own 32 cycles for N = 64).
+    const int set = __shfl_sync(0xffffffffu, warp - kW2EpiWarps, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    if (set == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(bar_w, k.w_bytes);  // weights: global image -> shared memory, resident, shared by both sets
+        for (uint32_t off = 0; off < k.w_bytes; off += 32768u)
+          bulk_g2s(smem_base + off, reinterpret_cast<const char *>(k.w_img) + off, min(32768u, k.w_bytes - off), bar_w);
+      }
     }
     __syncwarp();
     mbar_wait(bar_w, 0);
     const uint32_t bs = bar0 + 8 * (kW2BarSet + kW2BarsPerSet * set);
-    const uint32_t t_ah = tmem + kW2SetCols * set, t_al = t_ah + 64, t_d = t_ah + 128;
+    const uint32_t t_ah = tmem_u + kW2SetCols * set, t_al = t_ah + 64, t_d = t_ah + 128;
     uint32_t par_x0 = 0, par_evx = 0, par_evm = 0;
     for (int c = 0;; ++c) {
       mbar_wait(bs + 8 * kW2X0, par_x0);
       par_x0 ^= 1u;
       if (*reinterpret_cast<volatile int *>(s_live + 4 * set + (c & 3)) == 0) break;
       tc_fence_after();
+      MBEV_TR(0);
       for (int l = 0; l < L; ++l) {
         const int U = k.U[l];
         const bool half = kBf16 && l > 0;  // this layer's operands are bf16: one MMA per 16 K, no lo image
@@ -288,7 +318,7 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
         const uint32_t lbo = static_cast<uint32_t>(U) * 16u;
         const uint64_t dh0 = make_bdesc(smem_base + k.w_off[l][0], lbo, 128u);
         const uint64_t dl0 = make_bdesc(smem_base + k.w_off[l][1], lbo, 128u);
-        const uint64_t dstep = static_cast<uint64_t>(lbo >> 3);  // one K-step (two 16-byte K-chunks) in the descriptor address field
+        const uint32_t dstep = lbo >> 3;  // one K-step (two 16-byte K-chunks) in the descriptor address field (low word)
         const int nks = (l == 0) ? (k.Kp[0] >> 3) : (k.U[l - 1] >> (half ? 4 : 3));
         const int nparts = (l == 0) ? 1 : 2;
         uint32_t acc = 0;
@@ -303,18 +333,19 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
             }
             tc_fence_after();
           }
-          if (leader) {
-            const uint64_t koff = dstep * static_cast<uint64_t>(part * nks);
+          MBEV_TR(1 + 4 * l + 2 * part);
+          if (elect_one()) {
+            const uint32_t koff = dstep * static_cast<uint32_t>(part * nks);
             if (half) {
-#pragma unroll 1
+#pragma unroll 2
               for (int j = 0; j < nks; ++j) {
-                mma_bf16_ts(t_d, t_ah + 8u * j, dh0 + koff + dstep * j, idesc, acc);
+                mma_bf16_ts(t_d, t_ah + 8u * j, dh0 + (koff + dstep * j), idesc, acc);
                 acc = 1;
               }
             } else {
-#pragma unroll 1
+#pragma unroll 2
               for (int j = 0; j < nks; ++j) {  // al*wh, ah*wl, ah*wh : small terms first
-                const uint64_t dh = dh0 + koff + dstep * j, dl = dl0 + koff + dstep * j;
+                const uint64_t dh = dh0 + (koff + dstep * j), dl = dl0 + (koff + dstep * j);
                 mma_tf32_ts(t_d, t_al + 8u * j, dh, idesc, acc);
                 mma_tf32_ts(t_d, t_ah + 8u * j, dl, idesc, 1u);
                 mma_tf32_ts(t_d, t_ah + 8u * j, dh, idesc, 1u);
@@ -324,6 +355,7 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
             tc_commit(bs + 8 * ((l > 0 && part == 0) ? kW2XC : kW2D));
           }
           __syncwarp();
+          MBEV_TR(1 + 4 * l + 2 * part + 1);
         }
       }
     }
@@ -340,8 +372,11 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
     int *live = s_live + 4 * set;
 
     for (int c = 0;; ++c) {
+      MBEV_TR(0);
       const Window w = pack_window(num_points, cursor, pend, k.T, lane);
+      MBEV_TR(1);
       if (h == 0) build_x0(k, w, rows_src, kept_idx, coors, t_ah, t_al);
+      MBEV_TR(2);
       // ---- set rendezvous: every window's layer-0 input is in TMEM, nobody reads the previous chunk's D ------
       tc_fence_before();
       __syncwarp();
@@ -353,6 +388,7 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
       mbar_wait(bs + 8 * kW2X0, par_x0);
       par_x0 ^= 1u;
       if (*reinterpret_cast<volatile int *>(live + (c & 3)) == 0) break;
+      MBEV_TR(3);
 
       for (int l = 0; l < L; ++l) {
         const int U = k.U[l];
@@ -360,22 +396,34 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
         mbar_wait(bs + 8 * kW2D, par_d);
         par_d ^= 1u;
         tc_fence_after();
+        MBEV_TR(4 + 5 * l);
         const int Uh = U >> 1;
         const int nbat = Uh >> 4;
         const float *sc = s_ss + (2 * l) * MBEV_MAX_UNITS + h * Uh, *sh = s_ss + (2 * l + 1) * MBEV_MAX_UNITS + h * Uh;
         if (last) {
+          // two 16-column batches per iteration: 32 independent registers through the all-reduce, 128 contiguous bytes
+          // per pillar and store
 #pragma unroll 1
-          for (int b = 0; b < nbat; ++b) {
+          for (int b = 0; b + 1 < nbat; b += 2) {
             const int col0 = h * Uh + 16 * b;
-            float a[16];
-            load_bn_relu(t_d + static_cast<uint32_t>(col0), sc + 16 * b, sh + 16 * b, a);
-            seg_max16<false>(w, lane, a);
-            if (w.inwin && lane == w.s1) {  // the last lane of each pillar holds its max: 16 columns, 64 contiguous bytes
+            float a[32];
+            load_bn_relu32(t_d + static_cast<uint32_t>(col0), sc + 16 * b, sh + 16 * b, a);
+            seg_allmax<32>(w, lane, a);
+            if (w.inwin && lane == w.s1) {
               float4 *out = reinterpret_cast<float4 *>(feats + static_cast<size_t>(w.pil) * U + col0);
-              out[0] = make_float4(a[0], a[1], a[2], a[3]);
-              out[1] = make_float4(a[4], a[5], a[6], a[7]);
-              out[2] = make_float4(a[8], a[9], a[10], a[11]);
-              out[3] = make_float4(a[12], a[13], a[14], a[15]);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) out[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+            }
+          }
+          if (nbat & 1) {
+            const int col0 = h * Uh + 16 * (nbat - 1);
+            float a[16];
+            load_bn_relu(t_d + static_cast<uint32_t>(col0), sc + 16 * (nbat - 1), sh + 16 * (nbat - 1), a);
+            seg_allmax<16>(w, lane, a);
+            if (w.inwin && lane == w.s1) {
+              float4 *out = reinterpret_cast<float4 *>(feats + static_cast<size_t>(w.pil) * U + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) out[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
             }
           }
         } else {
@@ -399,8 +447,16 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bs + 8 * kW2EVX);
-            seg_max8_bf16(w, lane, v0);  // runs while the x-part MMAs do
-            if (nbat > 1) seg_max8_bf16(w, lane, v1);
+            if (nbat > 1) {  // runs while the x-part MMAs do
+              uint32_t v[16];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] = v0[j]; v[8 + j] = v1[j]; }
+              seg_allmax_bf16<16>(w, lane, v);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v0[j] = v[j]; v1[j] = v[8 + j]; }
+            } else {
+              seg_allmax_bf16<8>(w, lane, v0);
+            }
             mbar_wait(bs + 8 * kW2XC, par_xc);  // the x-part MMAs have read A: its columns are free again
             par_xc ^= 1u;
             tc_fence_after();
@@ -418,11 +474,22 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bs + 8 * kW2EVX);
-            seg_max16(w, lane, a0);  // runs while the x-part MMAs do
-            if (nbat > 1) seg_max16(w, lane, a1);
+            MBEV_TR(4 + 5 * l + 1);
+            if (nbat > 1) {  // runs while the x-part MMAs do
+              float a[32];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { a[j] = a0[j]; a[16 + j] = a1[j]; }
+              seg_allmax<32>(w, lane, a);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { a0[j] = a[j]; a1[j] = a[16 + j]; }
+            } else {
+              seg_allmax<16>(w, lane, a0);
+            }
+            MBEV_TR(4 + 5 * l + 2);
             mbar_wait(bs + 8 * kW2XC, par_xc);  // the x-part MMAs have read A: its columns are free again
             par_xc ^= 1u;
             tc_fence_after();
+            MBEV_TR(4 + 5 * l + 3);
             split_store16(t_ah + c0, t_al + c0, a0);  // max half: K index = U + unit index, same A columns
             if (nbat > 1) split_store16(t_ah + c0 + 16, t_al + c0 + 16, a1);
           }
@@ -430,8 +497,10 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bs + 8 * kW2EVM);
+          MBEV_TR(4 + 5 * l + 4);
         }
       }
+      MBEV_TR(20);
       cursor += w.cnt;
     }
   }
