@@ -28,7 +28,7 @@ namespace tc {
 
 constexpr int kW2Sets = 2;
 constexpr int kW2EpiWarps = 8 * kW2Sets;               // per set: 4 quadrants x 2 column halves
-constexpr int kW2Threads = (kW2EpiWarps + kW2Sets) * 32;
+constexpr int kW2Threads = (kW2EpiWarps + 4) * 32;  // + one warpgroup: the two MMA issuers and two idle warps (setmaxnreg is warpgroup-wide)
 constexpr int kW2SetCols = 256;                         // TMEM columns per set: A_hi [0,64) A_lo [64,128) D [128,256)
 constexpr int kW2BarW = 0, kW2BarSet = 1, kW2BarsPerSet = 5, kW2NumBars = kW2BarSet + kW2Sets * kW2BarsPerSet;
 enum { kW2X0 = 0, kW2D = 1, kW2XC = 2, kW2EVX = 3, kW2EVM = 4 };
@@ -53,10 +53,14 @@ struct Window {
 
 // pack whole pillars cursor, cursor+1, ... into a 32-row window (lane r = row r); identical on every warp that
 // calls it with the same cursor
-__device__ __forceinline__ Window pack_window(const int *__restrict__ num_points, int cursor, int pend, int T, int lane) {
+// num_points of the 32 pillars a window starting at `cursor` may take (lane i: pillar cursor + i), requested a whole
+// chunk before pack_window consumes it
+__device__ __forceinline__ int load_np(const int *__restrict__ num_points, int cursor, int pend, int lane) {
+  return cursor + lane < pend ? __ldg(num_points + cursor + lane) : 0;
+}
+__device__ __forceinline__ Window pack_window(int np, int cursor, int pend, int T, int lane) {
   Window w;
   const bool cand = cursor + lane < pend;
-  const int np = cand ? __ldg(num_points + cursor + lane) : 0;
   const int need = cand ? np + (np < T ? 1 : 0) : 0;
   int incl = need;
 #pragma unroll
@@ -64,59 +68,93 @@ __device__ __forceinline__ Window pack_window(const int *__restrict__ num_points
     const int t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  w.cnt = __popc(__ballot_sync(0xffffffffu, cand && incl <= 32));  // prefix-closed
+  const bool taken = cand && incl <= 32;  // prefix-closed
+  w.cnt = __popc(__ballot_sync(0xffffffffu, taken));
   w.nrows = w.cnt ? __shfl_sync(0xffffffffu, incl, w.cnt - 1) : 0;
-  const int excl = incl - need;
-  int pi = 0;  // the pillar of row `lane` is the last i < cnt with excl_i <= lane
-#pragma unroll
-  for (int bit = 16; bit; bit >>= 1) {
-    const int j = pi + bit;
-    const int e = __shfl_sync(0xffffffffu, excl, j & 31);
-    if (j < w.cnt && e <= lane) pi = j;
-  }
+  // bit r of `starts` = a pillar starts at row r: the pillar / first row / last row of row `lane` are bit counts and bit
+  // positions of that mask (no shuffle search)
+  const unsigned starts = __reduce_or_sync(0xffffffffu, taken ? (1u << (incl - need)) : 0u);
+  const unsigned upto = starts & (0xffffffffu >> (31 - lane));  // starts at rows <= lane
+  const unsigned above = starts & ~(0xffffffffu >> (31 - lane));
+  const int pi = max(__popc(upto) - 1, 0);
   w.inwin = lane < w.nrows;
-  w.s0 = __shfl_sync(0xffffffffu, excl, pi);
-  int nd = __shfl_sync(0xffffffffu, need, pi);
   w.n = __shfl_sync(0xffffffffu, np, pi);
-  if (!w.inwin) {  // window padding: a segment of its own
-    w.s0 = lane;
-    nd = 1;
-  }
-  w.s1 = w.s0 + nd - 1;
+  w.s0 = w.inwin ? 31 - __clz(upto) : lane;  // window padding: a segment of its own
+  w.s1 = w.inwin ? (above ? __ffs(above) - 2 : w.nrows - 1) : lane;
   w.t = lane - w.s0;
   w.real = w.inwin && w.t < w.n;
   w.pil = cursor + pi;
-  int ml = w.inwin ? nd : 1;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, o));
-  w.maxlen = ml;
+  w.maxlen = __reduce_max_sync(0xffffffffu, w.s1 - w.s0 + 1);
   return w;
 }
 
-// gather this row's point, decorate (mmdet3d PillarFeatureNet.forward), split and store the layer-0 input row
-// (wide column order: every index below is a compile-time constant, so the row lives in registers)
-__device__ __forceinline__ void build_x0(const Kargs &k, const Window &w, const float *__restrict__ rows_src,
-                                         const int *__restrict__ kept_idx, const int *__restrict__ coors,
-                                         uint32_t t_hi, uint32_t t_lo) {
+// The gather of a chunk's points runs one chunk ahead of their use (software pipeline over the chunks of a quadrant):
+// kept_idx row of the NEXT window right after this chunk's rendezvous, the point and the pillar's coordinates under the
+// last layer's MMAs, decoration at the top of the next chunk — no global-memory latency on the chunk's critical chain.
+// The bytes in flight are staged in shared memory by cp.async (48 bytes per lane: 8 point features + the pillar's
+// (b, z, y, x)), not in registers: a prefetched REGISTER that ptxas spills turns the prefetch into a synchronous load.
+constexpr int kStageFloats = MBEV_MAX_POINT_DIM + 4;  // per lane
+struct Gathered {
   float pv[MBEV_MAX_POINT_DIM];
-#pragma unroll
-  for (int j = 0; j < MBEV_MAX_POINT_DIM; ++j) pv[j] = 0.f;
-  if (w.real) {
-    const size_t slot = static_cast<size_t>(w.pil) * k.T + w.t;
-    const int src = kept_idx ? __ldg(kept_idx + slot) : static_cast<int>(slot);
+  int4 cc;
+};
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ int gather_index(const Kargs &k, const Window &w, const int *__restrict__ kept_idx) {
+  if (!w.real) return -1;
+  const size_t slot = static_cast<size_t>(w.pil) * k.T + w.t;
+  return kept_idx ? __ldg(kept_idx + slot) : static_cast<int>(slot);
+}
+// request the point of this lane's row and its pillar's coordinates into the lane's staging slot
+__device__ __forceinline__ void gather_issue(const Kargs &k, int src, int pil, bool inwin, const float *__restrict__ rows_src,
+                                             const int *__restrict__ coors, uint32_t slot) {
+  if (src >= 0) {
     const float *pp = rows_src + static_cast<size_t>(src) * k.C;
     if (k.C == 4) {
-      const float4 v = __ldg(reinterpret_cast<const float4 *>(pp));
-      pv[0] = v.x; pv[1] = v.y; pv[2] = v.z; pv[3] = v.w;
+      cp_async16(slot, pp);
     } else {
 #pragma unroll
       for (int j = 0; j < MBEV_MAX_POINT_DIM; ++j)
-        if (j < k.C) pv[j] = __ldg(pp + j);
+        if (j < k.C) cp_async4(slot + 4u * j, pp + j);
     }
   }
+  if (inwin) cp_async16(slot + 4u * MBEV_MAX_POINT_DIM, reinterpret_cast<const int4 *>(coors) + pil);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void gather_take(const Kargs &k, const Window &w, const float *stage, Gathered &g) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < MBEV_MAX_POINT_DIM; ++j) g.pv[j] = 0.f;
+  if (w.real) {
+    const float4 v = *reinterpret_cast<const float4 *>(stage);
+    g.pv[0] = v.x; g.pv[1] = v.y; g.pv[2] = v.z; g.pv[3] = v.w;
+    if (k.C > 4) {
+      const float4 u = *reinterpret_cast<const float4 *>(stage + 4);
+      g.pv[4] = u.x; g.pv[5] = u.y; g.pv[6] = u.z; g.pv[7] = u.w;
+#pragma unroll
+      for (int j = 4; j < MBEV_MAX_POINT_DIM; ++j)
+        if (j >= k.C) g.pv[j] = 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j >= k.C) g.pv[j] = 0.f;
+    }
+  }
+  g.cc = make_int4(0, 0, 0, 0);
+  if (w.inwin) g.cc = *reinterpret_cast<const int4 *>(stage + MBEV_MAX_POINT_DIM);
+}
+
+// decorate the gathered point (mmdet3d PillarFeatureNet.forward), split and store the layer-0 input row
+// (wide column order: every index below is a compile-time constant, so the row lives in registers)
+__device__ __forceinline__ void build_x0(const Kargs &k, const Window &w, const Gathered &g, uint32_t t_hi, uint32_t t_lo) {
+  const float (&pv)[MBEV_MAX_POINT_DIM] = g.pv;
   float cx = 0.f, cy = 0.f, cz = 0.f;
   if (w.inwin) {
-    const int4 cc = __ldg(reinterpret_cast<const int4 *>(coors) + w.pil);  // (b, z, y, x)
+    const int4 cc = g.cc;
     // upstream: coors.type_as(features) * vx + x_offset — float32 multiply THEN add (no FMA contraction)
     cx = __fadd_rn(__fmul_rn(static_cast<float>(cc.w), k.vx), k.xo);
     cy = __fadd_rn(__fmul_rn(static_cast<float>(cc.z), k.vy), k.yo);
@@ -242,8 +280,12 @@ __device__ __forceinline__ void seg_allmax_bf16(const Window &w, int lane, uint3
   }
 }
 
+// Register budget: 20 warps = 5 on each of the four SM sub-partitions (16 384 registers each), so the kernel starts
+// with 96 registers per thread; the last warpgroup (MMA issuers: uniform-register work only) then hands its registers
+// back and the epilogue warpgroups grow to 112 (setmaxnreg): 4 x 32 x 112 + 32 x 24 per sub-partition; the grow must fit into what the shrink released: 128 x 72 >= 512 x 16.
+constexpr int kW2RegsLaunch = 96, kW2RegsEpi = 112, kW2RegsIssuer = 24;
 template <bool kBf16>
-__global__ void __launch_bounds__(kW2Threads, 1)
+__global__ void __maxnreg__(kW2RegsLaunch)
 k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, const int *__restrict__ num_points,
            const int *__restrict__ coors, const int *__restrict__ bounds8, float *__restrict__ feats,
            const __grid_constant__ Kargs k) {
@@ -285,6 +327,11 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
   const uint32_t tmem = *s_tmem;
 
   if (warp >= kW2EpiWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kW2RegsIssuer));
+  }
+  if (warp >= kW2EpiWarps + kW2Sets) {
+    // idle warps of the issuer warpgroup
+  } else if (warp >= kW2EpiWarps) {
     // =========================================== MMA issuer of set `set` =====================================
     // Every operand of tcgen05.mma below is WARP-UNIFORM and provably so for the compiler (kernel parameters, a
     // constant-lane shuffle of the warp index and of the TMEM base, uniform loop counters), and the issuing thread is
@@ -361,6 +408,7 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
     }
   } else {
     // =========================================== epilogue warps ===============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kW2RegsEpi));
     const int set = warp >> 3, quad = warp & 3, h = (warp >> 2) & 1;
     const uint32_t tl = tmem + (static_cast<uint32_t>(quad * 32) << 16) + kW2SetCols * set;  // lane quadrant, set columns
     const uint32_t t_ah = tl, t_al = tl + 64, t_d = tl + 128;
@@ -371,11 +419,22 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
     uint32_t par_d = 0, par_x0 = 0, par_xc = 0;
     int *live = s_live + 4 * set;
 
+    // prologue of the gather pipeline: window 0 and its points, num_points of window 1
+    Window w = pack_window(load_np(num_points, cursor, pend, lane), cursor, pend, k.T, lane);
+    int cnext = cursor + w.cnt;
+    int np_next = load_np(num_points, cnext, pend, lane);
+    float *stage = reinterpret_cast<float *>(smem_raw + k.o_scr) + ((4 * set + quad) * 32 + lane) * kStageFloats;
+    const uint32_t stage_u = smem_u32(stage);
+    if (h == 0) gather_issue(k, gather_index(k, w, kept_idx), w.pil, w.inwin, rows_src, coors, stage_u);
+
     for (int c = 0;; ++c) {
       MBEV_TR(0);
-      const Window w = pack_window(num_points, cursor, pend, k.T, lane);
       MBEV_TR(1);
-      if (h == 0) build_x0(k, w, rows_src, kept_idx, coors, t_ah, t_al);
+      if (h == 0) {
+        Gathered g;
+        gather_take(k, w, stage, g);
+        build_x0(k, w, g, t_ah, t_al);
+      }
       MBEV_TR(2);
       // ---- set rendezvous: every window's layer-0 input is in TMEM, nobody reads the previous chunk's D ------
       tc_fence_before();
@@ -389,10 +448,21 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
       par_x0 ^= 1u;
       if (*reinterpret_cast<volatile int *>(live + (c & 3)) == 0) break;
       MBEV_TR(3);
+      Window wn;
+      int cnn = cnext, src_n = -1;
 
       for (int l = 0; l < L; ++l) {
         const int U = k.U[l];
         const bool last = (l == L - 1);
+        if (l == max(L - 2, 0)) {
+          // next window (its num_points were requested a chunk ago), the kept_idx entries of its rows, num_points of the
+          // window after it — placed where this warp would otherwise only wait for the layer's MMAs
+          wn = pack_window(np_next, cnext, pend, k.T, lane);
+          cnn = cnext + wn.cnt;
+          np_next = load_np(num_points, cnn, pend, lane);
+          if (h == 0) src_n = gather_index(k, wn, kept_idx);
+        }
+        if (last && h == 0) gather_issue(k, src_n, wn.pil, wn.inwin, rows_src, coors, stage_u);  // lands under the last layer
         mbar_wait(bs + 8 * kW2D, par_d);
         par_d ^= 1u;
         tc_fence_after();
@@ -501,7 +571,8 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
         }
       }
       MBEV_TR(20);
-      cursor += w.cnt;
+      w = wn;
+      cnext = cnn;
     }
   }
   tc_fence_before();
@@ -510,7 +581,7 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
 }
 
 // does the stack fit k_pfn_tcw2 (T <= 32, every U a multiple of 32, non-last layers <= 64 units), and its
-// shared-memory plan: [weight image][scale / shift][live ring][barriers + TMEM slot]
+// shared-memory plan: [weight image][scale / shift][live ring][gather staging][barriers + TMEM slot]
 inline bool tcw2_plan(Kargs &k) {
   if (k.T > 32) return false;
   for (int l = 0; l < k.L; ++l)
@@ -521,6 +592,7 @@ inline bool tcw2_plan(Kargs &k) {
   k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
   k.o_tab = o; o += 4 * kW2Sets * 4;
   o = (o + 15u) & ~15u;
+  k.o_scr = o; o += 4 * kW2Sets * 32 * kStageFloats * 4;  // gather staging: one 48-byte slot per row of every window
   k.o_bar = o; o += 8 * kW2NumBars + 16;
   k.smem_bytes = static_cast<int>(o);
   return k.smem_bytes <= kSmemLimit;

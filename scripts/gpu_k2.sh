@@ -2,10 +2,10 @@
 # K2 iteration loop: PFN parity tests + K2 timing on kitti_b16 / waymo_b32 / dense_1024. usage (under gpurun): bash scripts/gpu_k2.sh <tag>
 tag=${1:-k2}
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_pfn_scatter.py tests/test_gpu_reference_run.py -m gpu -q -x -p no:cacheprovider --timeout 600 2>&1 | tail -15 > gpurun_out/${tag}_pytest.log
+timeout 400 python -m pytest tests/test_gpu_pfn_scatter.py tests/test_gpu_reference_run.py -m gpu -q -x -p no:cacheprovider --timeout 600 2>&1 | tail -15 > gpurun_out/${tag}_pytest.log
 tail -3 gpurun_out/${tag}_pytest.log
 for wl in kitti_b16 waymo_b32 dense_1024 semkitti_b1; do
-python bench.py --workload $wl --steps 30 --warmup 5 --no-cpu-baseline --no-layernorm --no-train > gpurun_out/${tag}_bench_$wl.json 2> gpurun_out/${tag}_bench_$wl.err || tail -5 gpurun_out/${tag}_bench_$wl.err
+timeout 120 python bench.py --workload $wl --steps 30 --warmup 5 --no-cpu-baseline --no-layernorm --no-train > gpurun_out/${tag}_bench_$wl.json 2> gpurun_out/${tag}_bench_$wl.err || tail -5 gpurun_out/${tag}_bench_$wl.err
 python - <<PY
 import json
 d = json.load(open("gpurun_out/${tag}_bench_$wl.json"))
