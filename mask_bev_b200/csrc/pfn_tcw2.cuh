@@ -93,7 +93,7 @@ __device__ __forceinline__ Window pack_window(int np, int cursor, int pend, int 
 // last layer's MMAs, decoration at the top of the next chunk — no global-memory latency on the chunk's critical chain.
 // The bytes in flight are staged in shared memory by cp.async (48 bytes per lane: 8 point features + the pillar's
 // (b, z, y, x)), not in registers: a prefetched REGISTER that ptxas spills turns the prefetch into a synchronous load.
-constexpr int kStageFloats = MBEV_MAX_POINT_DIM + 4;  // per lane
+constexpr int kStageFloats = 16;  // per lane: the raw point (8) + coordinates (4) in flight, then the decorated row (16)
 struct Gathered {
   float pv[MBEV_MAX_POINT_DIM];
   int4 cc;
@@ -148,9 +148,9 @@ __device__ __forceinline__ void gather_take(const Kargs &k, const Window &w, con
   if (w.inwin) g.cc = *reinterpret_cast<const int4 *>(stage + MBEV_MAX_POINT_DIM);
 }
 
-// decorate the gathered point (mmdet3d PillarFeatureNet.forward), split and store the layer-0 input row
-// (wide column order: every index below is a compile-time constant, so the row lives in registers)
-__device__ __forceinline__ void build_x0(const Kargs &k, const Window &w, const Gathered &g, uint32_t t_hi, uint32_t t_lo) {
+// decorate the gathered point (mmdet3d PillarFeatureNet.forward) into the layer-0 input row (wide column order: every
+// index below is a compile-time constant, so the row lives in registers) and park it in the lane's staging slot
+__device__ __forceinline__ void decorate_x0(const Kargs &k, const Window &w, const Gathered &g, float *stage) {
   const float (&pv)[MBEV_MAX_POINT_DIM] = g.pv;
   float cx = 0.f, cy = 0.f, cz = 0.f;
   if (w.inwin) {
@@ -199,9 +199,22 @@ __device__ __forceinline__ void build_x0(const Kargs &k, const Window &w, const 
     }
     if (k.dist) xd[kWideDist] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)), __fmul_rn(r2, r2)));
   }
+  float4 *st4 = reinterpret_cast<float4 *>(stage);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) st4[q] = make_float4(xd[4 * q], xd[4 * q + 1], xd[4 * q + 2], xd[4 * q + 3]);
+}
+// the parked layer-0 input row -> split -> tensor memory
+__device__ __forceinline__ void store_x0(const float *stage, uint32_t t_hi, uint32_t t_lo) {
+  const float4 *st4 = reinterpret_cast<const float4 *>(stage);
   uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) split_tf32_alu(xd[j], hi[j], lo[j]);
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = st4[q];
+    split_tf32_alu(v.x, hi[4 * q + 0], lo[4 * q + 0]);
+    split_tf32_alu(v.y, hi[4 * q + 1], lo[4 * q + 1]);
+    split_tf32_alu(v.z, hi[4 * q + 2], lo[4 * q + 2]);
+    split_tf32_alu(v.w, hi[4 * q + 3], lo[4 * q + 3]);
+  }
   tmem_st16(t_hi, hi);
   tmem_st16(t_lo, lo);
   tc_wait_st();
@@ -425,16 +438,17 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
     int np_next = load_np(num_points, cnext, pend, lane);
     float *stage = reinterpret_cast<float *>(smem_raw + k.o_scr) + ((4 * set + quad) * 32 + lane) * kStageFloats;
     const uint32_t stage_u = smem_u32(stage);
-    if (h == 0) gather_issue(k, gather_index(k, w, kept_idx), w.pil, w.inwin, rows_src, coors, stage_u);
+    if (h == 0) {
+      gather_issue(k, gather_index(k, w, kept_idx), w.pil, w.inwin, rows_src, coors, stage_u);
+      Gathered g;
+      gather_take(k, w, stage, g);
+      decorate_x0(k, w, g, stage);
+    }
 
     for (int c = 0;; ++c) {
       MBEV_TR(0);
       MBEV_TR(1);
-      if (h == 0) {
-        Gathered g;
-        gather_take(k, w, stage, g);
-        build_x0(k, w, g, t_ah, t_al);
-      }
+      if (h == 0) store_x0(stage, t_ah, t_al);
       MBEV_TR(2);
       // ---- set rendezvous: every window's layer-0 input is in TMEM, nobody reads the previous chunk's D ------
       tc_fence_before();
@@ -454,15 +468,24 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
       for (int l = 0; l < L; ++l) {
         const int U = k.U[l];
         const bool last = (l == L - 1);
-        if (l == max(L - 2, 0)) {
+        // The next chunk's input is prepared in the three places where this warp would otherwise only wait for MMAs:
+        // (A) window + kept_idx entries, (B) point / coordinate requests, (C) decoration into the staging slot
+        if (l == max(L - 3, 0)) {
           // next window (its num_points were requested a chunk ago), the kept_idx entries of its rows, num_points of the
-          // window after it — placed where this warp would otherwise only wait for the layer's MMAs
+          // window after it
           wn = pack_window(np_next, cnext, pend, k.T, lane);
           cnn = cnext + wn.cnt;
           np_next = load_np(num_points, cnn, pend, lane);
           if (h == 0) src_n = gather_index(k, wn, kept_idx);
         }
-        if (last && h == 0) gather_issue(k, src_n, wn.pil, wn.inwin, rows_src, coors, stage_u);  // lands under the last layer
+        if (h == 0) {
+          if (l == max(L - 2, 0)) gather_issue(k, src_n, wn.pil, wn.inwin, rows_src, coors, stage_u);
+          if (last) {
+            Gathered g;
+            gather_take(k, wn, stage, g);
+            decorate_x0(k, wn, g, stage);
+          }
+        }
         mbar_wait(bs + 8 * kW2D, par_d);
         par_d ^= 1u;
         tc_fence_after();
@@ -592,7 +615,7 @@ inline bool tcw2_plan(Kargs &k) {
   k.o_ss = o; o += k.L * 2 * MBEV_MAX_UNITS * 4;
   k.o_tab = o; o += 4 * kW2Sets * 4;
   o = (o + 15u) & ~15u;
-  k.o_scr = o; o += 4 * kW2Sets * 32 * kStageFloats * 4;  // gather staging: one 48-byte slot per row of every window
+  k.o_scr = o; o += 4 * kW2Sets * 32 * kStageFloats * 4;  // gather staging: one 64-byte slot per row of every window
   k.o_bar = o; o += 8 * kW2NumBars + 16;
   k.smem_bytes = static_cast<int>(o);
   return k.smem_bytes <= kSmemLimit;
