@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 8
+#define MBEV_ABI_VERSION 9
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -244,6 +244,32 @@ MBEV_API int mbev_scatter_layernorm_backward(const float *dout, const float *fea
                                              const float *ln_weight, const float *stats, float *dfeats,
                                              float *dweight, float *dbias, void *workspace, size_t workspace_bytes,
                                              void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * F2 — Swin patch embedding on pillars. Replaces, for the first consumer of the pseudo image
+ * (/root/reference/mask_bev/models/networks/swin/swin.py:578-586 construction, :745-746 call; mmdet PatchEmbed,
+ * swin.py:13), the chain  nn.LayerNorm([C,ny,nx], eps) (mask_bev_encoders.py:75, 92)  ->  corner padding ->
+ * Conv2d(C, E, kernel = stride = patch, bias) -> flatten(2).transpose(1, 2) [-> nn.LayerNorm(E)]
+ * WITHOUT materialising the canvas: tokens (batch, Hp*Wp, E), Hp = ceil(ny / patch), Wp = ceil(nx / patch).
+ *   feats (pillar_capacity, C), coors (pillar_capacity, 4) (b,z,y,x), cell_table (batch, ny*nx), pillar_base
+ *   (batch + 1) as K1 / K2 produce them;
+ *   ln_weight_cl (ny*nx, C): the LayerNorm weight in channels-last order;
+ *   w_img: mbev_patch_embed_prepare_weights(conv weight (E, C, patch, patch)) -> patch*patch*2*E*C floats;
+ *   p0, p1 (Hp*Wp, E): parameter-only images conv(pad(ln_bias)) + conv bias and conv(pad(ln_weight)), channels-last;
+ *   norm_weight / norm_bias (E) or both NULL (patch_norm = False); stats_out (batch, 2) = mean, rstd of the canvas.
+ * Supported (probe): C in {32, 64, 128}, E a multiple of 32 <= 256 with 2*E*C*4 bytes of weights fitting shared
+ * memory, patch <= 8. fp32 parity through 3xTF32 tcgen05 MMAs; results are run-to-run identical. */
+MBEV_API int mbev_patch_embed_supported(int batch, int C, int ny, int nx, int patch, int embed_dims);
+MBEV_API int mbev_patch_embed_workspace_bytes(int batch, int64_t pillar_capacity, int patch, int embed_dims,
+                                              size_t *bytes);
+MBEV_API int mbev_patch_embed_prepare_weights(const float *conv_weight, int embed_dims, int C, int patch, float *w_img,
+                                              void *stream);
+MBEV_API int mbev_patch_embed_forward(const float *feats, const int32_t *coors, const int32_t *cell_table,
+                                      const int32_t *pillar_base, int64_t pillar_capacity, int batch, int C, int ny,
+                                      int nx, int patch, int embed_dims, const float *ln_weight_cl, float ln_eps,
+                                      const float *w_img, const float *p0, const float *p1, const float *norm_weight,
+                                      const float *norm_bias, float norm_eps, float *tokens, float *stats_out,
+                                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused batch entry (additive): K1 -> K2(eval) -> K3 on one stream, no host sync.

@@ -10,6 +10,7 @@ from .voxelize import Voxelization  # noqa: F401
 from .pillar_encoder import PFNLayer, PillarFeatureNet  # noqa: F401
 from .scatter import PointPillarsScatter  # noqa: F401
 from .encoder import EncodingType, MaskBevEncoder  # noqa: F401
+from .patch_embed import PillarPatchEmbed  # noqa: F401
 
 __all__ = ["Voxelization", "PFNLayer", "PillarFeatureNet", "PointPillarsScatter", "MaskBevEncoder",
-           "EncodingType", "MbevError", "launch_count"]
+           "EncodingType", "PillarPatchEmbed", "MbevError", "launch_count"]

@@ -13,7 +13,7 @@ MAX_BATCH = 128
 MAX_LAYERS = 4
 MAX_UNITS = 128
 MAX_POINT_DIM = 8
-ABI_VERSION = 8
+ABI_VERSION = 9
 GEMM_AUTO, GEMM_FMA, GEMM_TCGEN05, GEMM_TCGEN05_BF16 = 0, 1, 2, 3
 LN_WALK_RUNS, LN_WALK_FRAMES = 0, 1
 
@@ -76,6 +76,11 @@ SIGNATURES = {
     "mbev_scatter_layernorm_backward_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "mbev_scatter_layernorm_backward": (c_int, [_v, _v, _v, _v, _v, c_int64, c_int, c_int, c_int, c_int, _v, _v, _v,
                                                 _v, _v, _v, c_size_t, _v]),
+    "mbev_patch_embed_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mbev_patch_embed_workspace_bytes": (c_int, [c_int, c_int64, c_int, c_int, POINTER(c_size_t)]),
+    "mbev_patch_embed_prepare_weights": (c_int, [_v, c_int, c_int, c_int, _v, _v]),
+    "mbev_patch_embed_forward": (c_int, [_v, _v, _v, _v, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _v, c_float,
+                                         _v, _v, _v, _v, _v, c_float, _v, _v, _v, c_size_t, _v]),
     "mbev_encode_batch_workspace_bytes": (c_int, [_G, _P, c_int, c_int64, c_int64, POINTER(c_size_t)]),
     "mbev_encode_batch": (c_int, [_v, POINTER(c_int64), c_int, _G, _P, _v, _v, _v, _v, _v, c_int64, _v, _v, _v,
                                   c_size_t, _v]),

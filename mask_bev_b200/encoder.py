@@ -171,6 +171,21 @@ class MaskBevEncoder(nn.Module):
             return ln(canvas)
         return res[0]
 
+    def forward_patch_tokens(self, point_clouds, patch_embed):
+        """K1 -> K2 -> pillar patch embedding: the (B, Hp*Wp, E) tokens that swin.py:745-746 would
+        compute from ``self.forward(point_clouds)``, without writing the pseudo image. Inference only.
+        Returns (tokens, (Hp, Wp))."""
+        if len(point_clouds) == 0:
+            raise MbevError("empty batch")
+        pts, sizes = _as_points(point_clouds)
+        geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
+        vb = F_.voxelize_batch(pts, sizes, geo)
+        with torch.no_grad():
+            feats = self._voxel_encoder.apply_rows(pts, vb.kept_idx, vb.num_points, vb.coors, vb.num_pillars_dev,
+                                                   vb.capacity, geo.max_points)
+            return patch_embed.forward_pillars(feats, vb.coors, vb.cell_table, vb.pillar_base, len(sizes),
+                                               self._num_voxel_y, self._num_voxel_x, self._layer_norm)
+
     # -- module-level methods with the reference's semantics ---------------------------------------------
     def voxelize(self, point_clouds):
         """mask_bev_encoders.py:95-111: voxels (P,T,C), num_points (P,), coors_batch (P,4) = (b,z,y,x)."""

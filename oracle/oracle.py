@@ -447,6 +447,68 @@ def occupancy_np(coors4: np.ndarray, batch_size: int, ny: int, nx: int) -> np.nd
 
 
 # --------------------------------------------------------------------------------------------------
+# F2 — the first consumer of the pseudo image: mmdet PatchEmbed as the reference's Swin builds and calls it
+# (/root/reference/mask_bev/models/networks/swin/swin.py:13 import, :578-586 construction, :745-746 call).
+# mmdet==3.x is not on disk (Dockerfile pins it next to mmcv / mmdet3d): PARITY UNPINNED — this restates the published
+# mmdet.models.layers.PatchEmbed.forward with padding='corner' (AdaptivePadding: zeros at the bottom / right so that
+# H, W become multiples of the stride), Conv2d(kernel = stride = patch, bias), flatten(2).transpose(1, 2), then the
+# optional LayerNorm(E). Dense torch CPU ops, exactly the sequence upstream executes.
+# --------------------------------------------------------------------------------------------------
+def patch_embed_dense(x, conv_weight, conv_bias, patch: int, norm_weight=None, norm_bias=None, norm_eps: float = 1e-5):
+    """x (B, C, H, W) torch CPU tensor (the LayerNorm-ed pseudo image) -> (tokens (B, Hp*Wp, E), (Hp, Wp))."""
+    torch = _torch()
+    import math
+    import torch.nn.functional as F
+    H, W = x.shape[-2:]
+    pad_h = max((math.ceil(H / patch) - 1) * patch + (patch - 1) + 1 - H, 0)
+    pad_w = max((math.ceil(W / patch) - 1) * patch + (patch - 1) + 1 - W, 0)
+    if pad_h > 0 or pad_w > 0:
+        x = F.pad(x, [0, pad_w, 0, pad_h])
+    y = F.conv2d(x, conv_weight, conv_bias, stride=patch)
+    out_size = (y.shape[2], y.shape[3])
+    y = y.flatten(2).transpose(1, 2)
+    if norm_weight is not None:
+        y = F.layer_norm(y, (y.shape[-1],), norm_weight, norm_bias, norm_eps)
+    return y, out_size
+
+
+def patch_embed_on_pillars_np(feat, coors4, batch_size, ny, nx, ln_weight, ln_bias, ln_eps, conv_weight, conv_bias, patch,
+                              norm_weight=None, norm_bias=None, norm_eps: float = 1e-5):
+    """The same tokens from the pillars alone, in float64 numpy — the algebra csrc/patch_embed.cu implements (LayerNorm
+    pushed through the convolution), used to check the identity against ``patch_embed_dense`` on CPU."""
+    import math
+    f = np.asarray(feat, dtype=np.float64)
+    C = f.shape[1]
+    lw, lb = np.asarray(ln_weight, np.float64), np.asarray(ln_bias, np.float64)
+    W = np.asarray(conv_weight, np.float64)
+    E = W.shape[0]
+    Hp, Wp = math.ceil(ny / patch), math.ceil(nx / patch)
+    pad = lambda a: np.pad(a, ((0, 0), (0, Hp * patch - ny), (0, Wp * patch - nx)))  # noqa: E731
+    conv = lambda a: np.einsum('cyixj,ecij->yxe', pad(a).reshape(C, Hp, patch, Wp, patch), W)  # noqa: E731
+    p0 = conv(lb) + (0.0 if conv_bias is None else np.asarray(conv_bias, np.float64))
+    p1 = conv(lw)
+    out = np.zeros((batch_size, Hp, Wp, E))
+    M = C * ny * nx
+    for b in range(batch_size):
+        sel = coors4[:, 0] == b
+        fb, yb, xb = f[sel], coors4[sel, 2].astype(np.int64), coors4[sel, 3].astype(np.int64)
+        mu = fb.sum() / M
+        var = max((fb * fb).sum() / M - mu * mu, 0.0)
+        rstd = 1.0 / np.sqrt(var + ln_eps)
+        sparse = np.zeros((Hp, Wp, E))
+        g = fb * lw[:, yb, xb].T
+        z = np.einsum('pc,pec->pe', g, W[:, :, yb % patch, xb % patch].transpose(2, 0, 1))
+        np.add.at(sparse, (yb // patch, xb // patch), z)
+        out[b] = p0 - mu * rstd * p1 + rstd * sparse
+    y = out.reshape(batch_size, Hp * Wp, E)
+    if norm_weight is not None:
+        m = y.mean(-1, keepdims=True)
+        v = ((y - m) ** 2).mean(-1, keepdims=True)
+        y = (y - m) / np.sqrt(v + norm_eps) * np.asarray(norm_weight, np.float64) + np.asarray(norm_bias, np.float64)
+    return y, (Hp, Wp)
+
+
+# --------------------------------------------------------------------------------------------------
 # The whole path — mirrors MaskBevEncoder (mask_bev_encoders.py:21-123) on CPU
 # --------------------------------------------------------------------------------------------------
 class MaskBevEncoderOracle:
