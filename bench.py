@@ -571,6 +571,47 @@ def run_ours(args):
                                   "backward_note": "mbev_scatter_layernorm_backward: dy read once, dweight / dbias "
                                                    "written once, dfeats in pillar space"})
         del out_ln
+    # SURVEY §8 f2 ("next" row): the first consumer of the pseudo image, Swin's patch embedding (swin.py:578-586,
+    # 745-746; patch 4, embed_dims 192 as in configs/training), fed from the pillars — next to the canvas route
+    # (fused K3 + LayerNorm, then torch's Conv2d + LayerNorm on the 5 GB image)
+    patch_embed = None
+    if not args.no_layernorm and not args.no_patch_embed:
+        import mask_bev_b200 as M
+        if _lib.load().mbev_patch_embed_supported(B, Co, runner.ny, runner.nx, 4, 192):
+            pe = M.PillarPatchEmbed(in_channels=Co, embed_dims=192, kernel_size=4, stride=4, norm_cfg=dict(type="LN")).to(dev)
+            ln = enc._layer_norm
+
+            def f2():
+                return pe.forward_pillars(runner.feats, runner.coors, runner.cell_table, runner.pillar_base, B, runner.ny,
+                                          runner.nx, ln)
+            with torch.no_grad():
+                tok, (Hp, Wp) = f2()
+                t_f2 = ev_time(f2, iters, sync)
+                by_f2 = P * Co * 4 * 2 + P * 16 + B * G * 4 + B * Hp * Wp * 192 * 4  # feats + ln weight rows, coors, table, tokens
+                patch_embed = {"f2_tokens_ms": t_f2, "alg_bytes": by_f2, "gbs": by_f2 / t_f2 / 1e6,
+                               "frac_hbm": by_f2 / t_f2 / 1e6 / peak, "tokens_shape": [B, Hp * Wp, 192],
+                               "front_end_to_tokens_ms": t_vox + t_pfn + t_f2,
+                               "note": "K1 + K2 + mbev_patch_embed_forward: LayerNorm([C,ny,nx]) + Conv2d(k=s=4) + LayerNorm(E) "
+                                       "from the pillars, the pseudo image is never written"}
+                try:  # the canvas route on the same GPU: our fused K3+LN, then torch / cuDNN for the convolution
+                    from mask_bev_b200 import functional as F_
+                    x = torch.empty_like(runner.canvas)
+                    F_.scatter_layernorm_forward(runner.feats, runner.cell_table, runner.pillar_base, B, runner.ny, runner.nx,
+                                                 ln.weight, ln.bias, ln.eps, out=x)
+
+                    def dense():
+                        return pe.norm(pe.projection(x).flatten(2).transpose(1, 2))
+                    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                        ref = dense()
+                        t_dense = ev_time(dense, 3, sync)
+                    err = float((tok - ref).abs().max() / ref.abs().max())
+                    patch_embed.update({"canvas_route_conv_ms": t_dense, "rel_err_vs_canvas_route": err,
+                                        "canvas_route_note": "torch Conv2d (fp32, no TF32) + LayerNorm on the LayerNorm-ed canvas; "
+                                                             "add K3+LN_fused_ms for the whole canvas route"})
+                    del x, ref
+                except Exception as ex:  # noqa: BLE001
+                    patch_embed["canvas_route_error"] = str(ex)[:200]
+            del tok
     # the K3 form the timed step used: its stand-alone launch time is the roofline line; step_frac is the whole step
     use_stream = (not args.serial) and stream_ok and args.scatter_ctas > 0
     k3_key = f"K3_scatter_stream_{args.scatter_ctas}cta" if use_stream and args.scatter_ctas in t_st else "K3_scatter"
@@ -625,7 +666,7 @@ def run_ours(args):
                             "batches in flight) -> canvas in HBM, where the reference's consumer (LayerNorm / Swin) "
                             "reads it + D2H of the per-frame pillar counts (the canvas itself, 5.2 GB per step, is NOT "
                             "copied back); serial_value = same through mbev_encode_batch_host on one stream"},
-            "roofline": roof, "kernels": kernels, "layernorm_f1": layernorm, "bf16_canvas": bf16, "cpu_baseline": cpu,
+            "roofline": roof, "kernels": kernels, "layernorm_f1": layernorm, "patch_embed_f2": patch_embed, "bf16_canvas": bf16, "cpu_baseline": cpu,
             "train": train, "pillars_per_step": P, "kept_points_per_step": nk, "points_per_step": N}
     if saved_stdout is not None:
         sys.stdout.flush()
@@ -655,6 +696,7 @@ def main():
     ap.add_argument("--train-batch", type=int, default=4, help="frames per GPU of the training step (semantic_kitti/01:28)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layernorm", action="store_true", help="skip the K3+LayerNorm (SURVEY f1) timing")
+    ap.add_argument("--no-patch-embed", action="store_true", help="skip the pillar patch embedding (SURVEY f2) timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

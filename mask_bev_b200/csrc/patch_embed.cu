@@ -11,7 +11,7 @@
 // pillar's position inside its patch (ps * ps classes, one E x C weight slice each):
 //   k_pe_hist / k_pe_bases / k_pe_place : counting sort of the pillars by class into 128-row aligned slabs
 //   k_pe_gemm   : tcgen05 3xTF32 (fp32 parity as in K2): A = f * lnw built in registers -> TMEM, B = the class's weight
-//                 slice (UMMA K-major image, resident in shared memory while the CTA stays in the class), D -> Z rows
+//                 slice (UMMA K-major image, resident in shared memory while the CTA stays in the class), D -> Z[pillar]
 //   k_pe_tokens : a warp per token sums the Z rows of its patch in cell order (fixed order: run-to-run identical),
 //                 adds the parameter images, applies the patch LayerNorm and writes (B, Hp*Wp, E).
 #include <algorithm>
@@ -63,7 +63,7 @@ __global__ void k_pe_bases(const int *__restrict__ count, const int ncls, int *_
 // the places inside by shared-memory atomics. The order inside a class is arbitrary — nothing downstream depends on it.
 __global__ void __launch_bounds__(kPlaceThreads)
 k_pe_place(const int *__restrict__ coors, const int *__restrict__ num_pillars, const int ps, const int *__restrict__ base,
-           int *__restrict__ cursor, int *__restrict__ perm, int *__restrict__ pos) {
+           int *__restrict__ cursor, int *__restrict__ perm) {
   __shared__ int s_c[kPeMaxClasses], s_b[kPeMaxClasses];
   if (threadIdx.x < kPeMaxClasses) s_c[threadIdx.x] = 0;
   __syncthreads();
@@ -88,7 +88,6 @@ k_pe_place(const int *__restrict__ coors, const int *__restrict__ num_pillars, c
     const int p = p0 + i * kPlaceThreads + threadIdx.x;
     const int slot = s_b[cls[i]] + rk[i];
     perm[slot] = p;
-    pos[p] = slot;
   }
 }
 
@@ -114,7 +113,7 @@ struct PeArgs {
   const int *coors, *perm, *base;
   const float *lnw_cl;  // (ny * nx, C)
   const float *w_img;
-  float *Z;             // (slots, E)
+  float *Z;             // (pillar capacity, E): row = pillar id
   int C, E, nx, ncls;
   uint32_t img_bytes;   // E * C * 4: one hi or lo image
   uint32_t o_bar;
@@ -203,10 +202,10 @@ k_pe_gemm(const __grid_constant__ PeArgs a) {
     const int row = quad * 32 + lane;
     const uint32_t tl = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     uint32_t par_d = 0;
-    for (int c = c_lo; c < c_hi; ++c) {
-      const int slot = c * kPeRows + row;
-      const int p = __ldg(a.perm + slot);
-      float4 f[kHalf / 4], w[kHalf / 4];
+    float4 f[kHalf / 4], w[kHalf / 4];
+    // the row's 2 x 16 float4 loads are requested a whole chunk ahead: under the previous chunk's MMAs and drain
+    auto request = [&](int c) -> int {
+      const int p = (c < c_hi) ? __ldg(a.perm + c * kPeRows + row) : -1;
       if (p >= 0) {
         const int4 cc = __ldg(reinterpret_cast<const int4 *>(a.coors) + p);
         const float4 *fp = reinterpret_cast<const float4 *>(a.feats + static_cast<size_t>(p) * kC + hh * kHalf);
@@ -219,6 +218,11 @@ k_pe_gemm(const __grid_constant__ PeArgs a) {
 #pragma unroll
         for (int q = 0; q < kHalf / 4; ++q) f[q] = w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      return p;
+    };
+    int p_next = request(c_lo);
+    for (int c = c_lo; c < c_hi; ++c) {
+      const int p = p_next;
 #pragma unroll
       for (int jb = 0; jb < kHalf / 16; ++jb) {
         uint32_t hi[16], lo[16];
@@ -238,11 +242,12 @@ k_pe_gemm(const __grid_constant__ PeArgs a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a);
+      p_next = request(c + 1);
       mbar_wait(bar_d, par_d);
       par_d ^= 1u;
       tc_fence_after();
       const int Eh = E >> 1;
-      float *zrow = a.Z + static_cast<size_t>(slot) * E + hh * Eh;
+      float *zrow = a.Z + static_cast<size_t>(p >= 0 ? p : 0) * E + hh * Eh;
       for (int jb = 0; jb < Eh / 16; ++jb) {
         uint32_t v[16];
         tmem_ld16(tl + kColD + static_cast<uint32_t>(hh * Eh + 16 * jb), v);
@@ -263,86 +268,109 @@ k_pe_gemm(const __grid_constant__ PeArgs a) {
   if (warp == kPeWorkers / 32) tmem_dealloc(tmem, 512);
 }
 
-// A warp per token. Lane e + 32 j holds embedding channel e + 32 j.
+// A warp per kTok consecutive tokens; lane e + 32 j holds embedding channel e + 32 j. The cell-table lookups of all
+// the warp's tokens are requested together, then the Z rows (row = pillar id): the kernel is a chain of dependent
+// gathers and would otherwise wait out one memory round trip per token and stage.
+constexpr int kTok = 4;
 template <int kJ>
 __global__ void __launch_bounds__(256)
-k_pe_tokens(const float *__restrict__ Z, const int *__restrict__ table, const int *__restrict__ pos,
-            const float2 *__restrict__ stats, const float *__restrict__ P0, const float *__restrict__ P1,
-            const float *__restrict__ norm_w, const float *__restrict__ norm_b, const float norm_eps, const int batch,
-            const int ny, const int nx, const int ps, const int Hp, const int Wp, const int E, float *__restrict__ tokens) {
+k_pe_tokens(const float *__restrict__ Z, const int *__restrict__ table, const float2 *__restrict__ stats,
+            const float *__restrict__ P0, const float *__restrict__ P1, const float *__restrict__ norm_w,
+            const float *__restrict__ norm_b, const float norm_eps, const int batch, const int ny, const int nx,
+            const int ps, const int Hp, const int Wp, const int E, float *__restrict__ tokens) {
   const int lane = threadIdx.x & 31;
-  const long long t = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // token position major, frame group minor: the parameter images P0 / P1 (61 MB at 200 x 200 x 192) are read once per
+  // position and kTok frames, and the warps that share a position run next to each other (L2 hits) — frame-major order
+  // re-streams both images from HBM for every frame
+  const long long g = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int HW = Hp * Wp;
-  if (t >= static_cast<long long>(batch) * HW) return;
-  const int b = static_cast<int>(t / HW), tt = static_cast<int>(t - static_cast<long long>(b) * HW);
-  const int py = tt / Wp, px = tt - py * Wp;
-  float acc[kJ];
+  const int nfg = (batch + kTok - 1) / kTok;
+  if (g >= static_cast<long long>(HW) * nfg) return;
+  const int tt = static_cast<int>(g / nfg), b0 = static_cast<int>(g - static_cast<long long>(tt) * nfg) * kTok;
+  int bq[kTok], ttq[kTok];
 #pragma unroll
-  for (int j = 0; j < kJ; ++j) acc[j] = 0.f;
+  for (int i = 0; i < kTok; ++i) {
+    bq[i] = min(b0 + i, batch - 1);
+    ttq[i] = tt;
+  }
+  float acc[kTok][kJ];
+#pragma unroll
+  for (int i = 0; i < kTok; ++i)
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) acc[i][j] = 0.f;
   const int ncell = ps * ps;
   for (int c0 = 0; c0 < ncell; c0 += 32) {  // cells of the patch in (dy, dx) order
     const int ci = c0 + lane;
-    int slot = -1;
-    if (ci < ncell) {
-      const int y = py * ps + ci / ps, x = px * ps + ci % ps;
-      if (y < ny && x < nx) {
-        const int pid = __ldg(table + static_cast<size_t>(b) * ny * nx + static_cast<size_t>(y) * nx + x);
-        if (pid >= 0) slot = __ldg(pos + pid);
+    int pid[kTok];
+#pragma unroll
+    for (int i = 0; i < kTok; ++i) {
+      pid[i] = -1;
+      if (ci < ncell) {
+        const int py = ttq[i] / Wp, px = ttq[i] - py * Wp;
+        const int y = py * ps + ci / ps, x = px * ps + ci % ps;
+        if (y < ny && x < nx) pid[i] = __ldg(table + static_cast<size_t>(bq[i]) * ny * nx + static_cast<size_t>(y) * nx + x);
       }
     }
-    unsigned m = __ballot_sync(0xffffffffu, slot >= 0);
-    while (m) {
-      const int l = __ffs(m) - 1;
-      m &= m - 1;
-      const int s = __shfl_sync(0xffffffffu, slot, l);
-      const float *z = Z + static_cast<size_t>(s) * E + lane;
 #pragma unroll
-      for (int j = 0; j < kJ; ++j)
-        if (lane + 32 * j < E) acc[j] = __fadd_rn(acc[j], __ldg(z + 32 * j));
-    }
-  }
-  const float2 st = stats[b];
-  const float nmr = -st.x * st.y;  // -mean * rstd
-  float y[kJ];
-  float sum = 0.f;
+    for (int i = 0; i < kTok; ++i) {
+      unsigned m = __ballot_sync(0xffffffffu, pid[i] >= 0);
+      while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const int s = __shfl_sync(0xffffffffu, pid[i], l);
+        const float *z = Z + static_cast<size_t>(s) * E + lane;
 #pragma unroll
-  for (int j = 0; j < kJ; ++j) {
-    const int e = lane + 32 * j;
-    y[j] = 0.f;
-    if (e < E) {
-      const size_t o = static_cast<size_t>(tt) * E + e;
-      y[j] = fmaf(st.y, acc[j], fmaf(nmr, __ldg(P1 + o), __ldg(P0 + o)));
-      sum += y[j];
-    }
-  }
-  if (norm_w) {  // nn.LayerNorm(E): biased variance, two passes
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / static_cast<float>(E);
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < kJ; ++j)
-      if (lane + 32 * j < E) {
-        const float d = y[j] - mean;
-        sq = fmaf(d, d, sq);
+        for (int j = 0; j < kJ; ++j)
+          if (lane + 32 * j < E) acc[i][j] = __fadd_rn(acc[i][j], __ldg(z + 32 * j));
       }
+    }
+  }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq / static_cast<float>(E) + norm_eps);
+  for (int i = 0; i < kTok; ++i) {
+    if (b0 + i >= batch) break;
+    const float2 st = stats[bq[i]];
+    const float nmr = -st.x * st.y;  // -mean * rstd
+    float y[kJ];
+    float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kJ; ++j) {
       const int e = lane + 32 * j;
-      if (e < E) y[j] = fmaf((y[j] - mean) * rstd, __ldg(norm_w + e), __ldg(norm_b + e));
+      y[j] = 0.f;
+      if (e < E) {
+        const size_t o = static_cast<size_t>(ttq[i]) * E + e;
+        y[j] = fmaf(st.y, acc[i][j], fmaf(nmr, __ldg(P1 + o), __ldg(P0 + o)));
+        sum += y[j];
+      }
     }
-  }
-  float *out = tokens + static_cast<size_t>(t) * E + lane;
+    if (norm_w) {  // nn.LayerNorm(E): biased variance, two passes
 #pragma unroll
-  for (int j = 0; j < kJ; ++j)
-    if (lane + 32 * j < E) out[32 * j] = y[j];
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum / static_cast<float>(E);
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < kJ; ++j)
+        if (lane + 32 * j < E) {
+          const float d = y[j] - mean;
+          sq = fmaf(d, d, sq);
+        }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq / static_cast<float>(E) + norm_eps);
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        const int e = lane + 32 * j;
+        if (e < E) y[j] = fmaf((y[j] - mean) * rstd, __ldg(norm_w + e), __ldg(norm_b + e));
+      }
+    }
+    float *out = tokens + (static_cast<size_t>(bq[i]) * HW + tt) * E + lane;
+#pragma unroll
+    for (int j = 0; j < kJ; ++j)
+      if (lane + 32 * j < E) out[32 * j] = y[j];
+  }
 }
 
 struct PeWs {
-  int *count, *base, *cursor, *perm, *pos;
+  int *count, *base, *cursor, *perm;
   float *Z;
   double2 *partial;
   size_t slots, bytes;
@@ -357,8 +385,7 @@ PeWs carve_pe(void *ws, int batch, int64_t cap, int ncls, int E) {
   w.base = c.take<int>(kPeMaxClasses + 1);
   w.cursor = c.take<int>(kPeMaxClasses);
   w.perm = c.take<int>(w.slots);
-  w.pos = c.take<int>(P);
-  w.Z = c.take<float>(w.slots * static_cast<size_t>(E));
+  w.Z = c.take<float>(P * static_cast<size_t>(E));
   w.partial = c.take<double2>(static_cast<size_t>(batch) * kStatBlocks);
   w.bytes = c.off;
   return w;
@@ -437,7 +464,7 @@ extern "C" int mbev_patch_embed_forward(const float *feats, const int32_t *coors
   k_pe_bases<<<1, kPeMaxClasses, 0, stream>>>(w.count, ncls, w.base, w.cursor);
   MBEV_CHECK_LAUNCH();
   k_pe_place<<<(cap + kPlaceThreads * kPlaceItems - 1) / (kPlaceThreads * kPlaceItems), kPlaceThreads, 0, stream>>>(
-      coors, num_pillars, patch, w.base, w.cursor, w.perm, w.pos);
+      coors, num_pillars, patch, w.base, w.cursor, w.perm);
   MBEV_CHECK_LAUNCH();
 
   PeArgs a;
@@ -468,11 +495,11 @@ extern "C" int mbev_patch_embed_forward(const float *feats, const int32_t *coors
   }
   MBEV_CHECK_LAUNCH();
 
-  const long long ntok = static_cast<long long>(batch) * Hp * Wp;
-  const int blocks = static_cast<int>((ntok + 7) / 8);
+  const long long nwarps = static_cast<long long>(Hp) * Wp * ((batch + kTok - 1) / kTok);
+  const int blocks = static_cast<int>((nwarps + 7) / 8);
   const int J = (E + 31) / 32;
 #define MBEV_PE_TOK(JJ)                                                                                                  \
-  k_pe_tokens<JJ><<<blocks, 256, 0, stream>>>(w.Z, cell_table, w.pos, stats, p0, p1, norm_weight, norm_bias, norm_eps, batch, \
+  k_pe_tokens<JJ><<<blocks, 256, 0, stream>>>(w.Z, cell_table, stats, p0, p1, norm_weight, norm_bias, norm_eps, batch, \
                                              ny, nx, patch, Hp, Wp, E, tokens)
   switch (J) {
     case 1: MBEV_PE_TOK(1); break;
