@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 9
+#define MBEV_ABI_VERSION 10
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -110,6 +110,36 @@ MBEV_API int mbev_voxelize(const float *points, const int64_t *frame_offsets_hos
                   int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
                   int32_t *pillar_base, int64_t pillar_capacity, void *workspace, size_t workspace_bytes,
                   void *stream);
+
+/* F4: the point side of the reference's augmentations applied in K1's load stage, in the order the
+ * training configs list them (configs/training/semantic_kitti/01*.yml:34-49; classes in
+ * mask_bev/augmentations/semantic_kitti_mask_augmentations.py): RandomDropPoints (:152-162) -> Flip (:44-56) ->
+ * RandomRotate (:73-101, float64 like numpy's R @ p) -> JitterPoints (:116-149, intensity clipped to [0, 1]).
+ * Per-frame decisions are drawn by the host (one MbevFrameAugment per frame, DEVICE array); per-point randomness is
+ * replayed from drop_u / noise when given (bit-exact against a numpy stream) or generated in the kernel from
+ * (seed, point row). points_out (total_points, C) receives the augmented cloud: kept_idx indexes IT, so the PFN must
+ * gather from points_out. A dropped point keeps its row (and is simply not voxelised). */
+typedef struct MbevFrameAugment {
+  double cos_t, sin_t;     /* rotation about z; used when rotate != 0 */
+  float drop_prob;         /* per-point drop probability of this frame, 0 = keep all */
+  float jitter_std[4];     /* generator mode: std of the x, y, z, intensity noise */
+  float jitter_max[4];     /* generator mode: clip of the noise, <= 0 = none */
+  int32_t flip_x, flip_y;  /* x -> -x, y -> -y */
+  int32_t rotate;
+  int32_t jitter;          /* add noise (given or generated), then clip intensity */
+} MbevFrameAugment;
+typedef struct MbevAugment {
+  const MbevFrameAugment *frames; /* DEVICE, batch entries */
+  const float *drop_u;            /* DEVICE (total_points) uniforms in [0, 1): dropped iff u < drop_prob; NULL = generated */
+  const double *noise;            /* DEVICE (total_points, C) additive noise, scaled and clipped; NULL = generated */
+  uint64_t seed;
+  float *points_out;              /* DEVICE (total_points, C) */
+} MbevAugment;
+MBEV_API int mbev_voxelize_augmented(const float *points, const int64_t *frame_offsets_host, int batch,
+                                     const MbevGeometry *geo, const MbevAugment *aug, int32_t *cell_table,
+                                     int32_t *coors, int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
+                                     int64_t pillar_capacity, void *workspace, size_t workspace_bytes, void *stream);
+
 
 /* Materialise the zero-padded (P, T, C) voxel tensor that mmcv's op returns (voxels_out) and, optionally,
  * the -1 padded kept-index matrix rebased to frame-local rows. num_pillars_dev: device int32 (total P). */

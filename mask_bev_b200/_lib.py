@@ -7,13 +7,13 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 MAX_BATCH = 128
 MAX_LAYERS = 4
 MAX_UNITS = 128
 MAX_POINT_DIM = 8
-ABI_VERSION = 9
+ABI_VERSION = 10
 GEMM_AUTO, GEMM_FMA, GEMM_TCGEN05, GEMM_TCGEN05_BF16 = 0, 1, 2, 3
 LN_WALK_RUNS, LN_WALK_FRAMES = 0, 1
 
@@ -38,6 +38,17 @@ class MbevPfnParams(ctypes.Structure):
                 ("gemm_path", c_int32)]
 
 
+class MbevFrameAugment(ctypes.Structure):
+    _fields_ = [("cos_t", c_double), ("sin_t", c_double), ("drop_prob", c_float), ("jitter_std", c_float * 4),
+                ("jitter_max", c_float * 4), ("flip_x", c_int32), ("flip_y", c_int32), ("rotate", c_int32),
+                ("jitter", c_int32)]
+
+
+class MbevAugment(ctypes.Structure):
+    _fields_ = [("frames", c_void_p), ("drop_u", c_void_p), ("noise", c_void_p), ("seed", c_uint64),
+                ("points_out", c_void_p)]
+
+
 _PTRS = c_void_p * MAX_LAYERS
 _G = POINTER(MbevGeometry)
 _P = POINTER(MbevPfnParams)
@@ -51,6 +62,7 @@ SIGNATURES = {
     "mbev_pillar_capacity": (c_int64, [POINTER(c_int64), c_int, _G]),
     "mbev_voxelize_workspace_bytes": (c_int, [_G, c_int, c_int64, POINTER(c_size_t)]),
     "mbev_voxelize": (c_int, [_v, POINTER(c_int64), c_int, _G, _v, _v, _v, _v, _v, c_int64, _v, c_size_t, _v]),
+    "mbev_voxelize_augmented": (c_int, [_v, POINTER(c_int64), c_int, _G, _v, _v, _v, _v, _v, _v, c_int64, _v, c_size_t, _v]),
     "mbev_gather_voxels": (c_int, [_v, _v, _v, _v, c_int64, c_int, c_int, _v, _v]),
     "mbev_pfn_workspace_bytes": (c_int, [_P, c_int, c_int64, c_int, POINTER(c_size_t)]),
     "mbev_pfn_path": (c_int, [_P, c_int]),

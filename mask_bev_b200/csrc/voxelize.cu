@@ -71,6 +71,95 @@ k_assign(const float *__restrict__ pts, const int total, const __grid_constant__
   next[i] = atomicExch(head + gc, i);
 }
 
+// ---- F4: augmentations in K1's load stage -------------------------------------------------------
+// The point side of /root/reference/mask_bev/augmentations/semantic_kitti_mask_augmentations.py in the order the
+// training configs list them (configs/training/semantic_kitti/01*.yml:34-49): RandomDropPoints (:152-162) -> Flip
+// (:44-56) -> RandomRotate (:73-101) -> JitterPoints (:116-149). Per-frame decisions and angles are drawn on the host
+// (MbevFrameAugment); the per-point randomness is either given (drop_u / noise: bit-exact replay of a numpy stream)
+// or generated here from (seed, point row) with Philox4x32-10. A dropped point is simply not voxelised: input order
+// of the others is what the rank walk uses, exactly as if the row had been removed.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0, 1)
+
+__global__ void __launch_bounds__(kThreads)
+k_assign_aug(const float *__restrict__ pts, const int total, const __grid_constant__ Frames fr,
+             const __grid_constant__ GeoK g, const MbevFrameAugment *__restrict__ fa, const float *__restrict__ drop_u,
+             const double *__restrict__ noise, const unsigned long long seed, float *__restrict__ pts_out,
+             int *__restrict__ head, int *__restrict__ next, int *__restrict__ cellid) {
+  __shared__ int s_off[MBEV_MAX_BATCH + 1];
+  for (int t = threadIdx.x; t <= fr.batch; t += kThreads) s_off[t] = fr.off[t];
+  __syncthreads();
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  if (t >= total) return;
+  const int i = total - 1 - t;  // reverse visit order, as k_assign
+  const int f = frame_of(s_off, fr.batch, i);
+  const MbevFrameAugment a = fa[f];
+  float v[MBEV_MAX_POINT_DIM];
+  const float *p = pts + static_cast<size_t>(i) * g.C;
+#pragma unroll
+  for (int j = 0; j < MBEV_MAX_POINT_DIM; ++j) v[j] = j < g.C ? __ldg(p + j) : 0.f;
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  bool dropped = false;
+  if (a.drop_prob > 0.f) {  // keep = u >= p  (:158)
+    const float u = drop_u ? __ldg(drop_u + i) : u01(philox4x32_10(make_uint4(static_cast<uint32_t>(i), 0u, 0u, 0u), key).x);
+    dropped = u < a.drop_prob;
+  }
+  if (a.flip_x) v[0] = -v[0];  // (:51, :54)
+  if (a.flip_y) v[1] = -v[1];
+  if (a.rotate) {  // float64 R @ (x, y, z, 1), stored back into the float32 cloud (:88-97)
+    const double x = static_cast<double>(v[0]), y = static_cast<double>(v[1]);
+    // (+ 0.0: the matrix rows' 0 * z + 0 * 1 terms turn a -0 result into +0, as numpy's product does)
+    v[0] = static_cast<float>(__dadd_rn(__dadd_rn(__dmul_rn(a.cos_t, x), __dmul_rn(-a.sin_t, y)), 0.0));
+    v[1] = static_cast<float>(__dadd_rn(__dadd_rn(__dmul_rn(a.sin_t, x), __dmul_rn(a.cos_t, y)), 0.0));
+    v[2] = static_cast<float>(__dadd_rn(static_cast<double>(v[2]), 0.0));
+  }
+  if (a.jitter) {  // cloud += noise (float64 sum rounded to float32), intensity clipped to [0, 1] (:134-148)
+    if (noise) {
+      const double *n = noise + static_cast<size_t>(i) * g.C;
+#pragma unroll
+      for (int j = 0; j < MBEV_MAX_POINT_DIM; ++j)
+        if (j < g.C) v[j] = static_cast<float>(__dadd_rn(static_cast<double>(v[j]), __ldg(n + j)));
+    } else {
+      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(i), 1u, 0u, 0u), key);
+      const float m0 = sqrtf(-2.f * logf(u01(r.x))), m1 = sqrtf(-2.f * logf(u01(r.z)));
+      float z4[4];
+      sincospif(2.f * u01(r.y), &z4[1], &z4[0]);
+      sincospif(2.f * u01(r.w), &z4[3], &z4[2]);
+      z4[0] *= m0; z4[1] *= m0; z4[2] *= m1; z4[3] *= m1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= g.C) break;
+        float n = z4[j] * a.jitter_std[j];
+        if (a.jitter_max[j] > 0.f) n = fminf(fmaxf(n, -a.jitter_max[j]), a.jitter_max[j]);
+        v[j] += n;
+      }
+    }
+    if (g.C > 3) v[3] = fminf(fmaxf(v[3], 0.f), 1.f);
+  }
+  float *o = pts_out + static_cast<size_t>(i) * g.C;
+#pragma unroll
+  for (int j = 0; j < MBEV_MAX_POINT_DIM; ++j)
+    if (j < g.C) o[j] = v[j];
+  int cell;
+  if (dropped || !point_cell(v[0], v[1], v[2], g, cell)) {
+    cellid[i] = -1;
+    return;
+  }
+  const int gc = f * g.cells + cell;
+  cellid[i] = gc;
+  next[i] = atomicExch(head + gc, i);
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_rank(const int total, const int T, const int *__restrict__ head, const int *__restrict__ next,
        const int *__restrict__ cellid, int *__restrict__ rank, int *__restrict__ aux,
@@ -382,10 +471,10 @@ extern "C" int mbev_voxelize_workspace_bytes(const MbevGeometry *geo, int batch,
   return MBEV_OK;
 }
 
-extern "C" int mbev_voxelize(const float *points, const int64_t *frame_offsets_host, int batch,
-                             const MbevGeometry *geo, int32_t *cell_table, int32_t *coors, int32_t *num_points,
-                             int32_t *kept_idx, int32_t *pillar_base, int64_t pillar_capacity, void *workspace,
-                             size_t workspace_bytes, void *stream_) {
+static int voxelize_impl(const float *points, const int64_t *frame_offsets_host, int batch, const MbevGeometry *geo,
+                         int32_t *cell_table, int32_t *coors, int32_t *num_points, int32_t *kept_idx,
+                         int32_t *pillar_base, int64_t pillar_capacity, void *workspace, size_t workspace_bytes,
+                         void *stream_, const MbevAugment *aug) {
   const int st = check_geo(geo, batch);
   if (st) return st;
   if (!frame_offsets_host || !cell_table || !coors || !num_points || !kept_idx || !pillar_base || !workspace)
@@ -412,7 +501,10 @@ extern "C" int mbev_voxelize(const float *points, const int64_t *frame_offsets_h
   const int words = (total + 31) / 32;
   if (total > 0) {
     const int blocks = (total + kThreads - 1) / kThreads;
-    if (g.C == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0)
+    if (aug)
+      k_assign_aug<<<blocks, kThreads, 0, stream>>>(points, total, fr, g, aug->frames, aug->drop_u, aug->noise, aug->seed,
+                                                   aug->points_out, cell_table, w.next, w.cellid);
+    else if (g.C == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0)
       k_assign<4><<<blocks, kThreads, 0, stream>>>(points, total, fr, g, cell_table, w.next, w.cellid);
     else
       k_assign<0><<<blocks, kThreads, 0, stream>>>(points, total, fr, g, cell_table, w.next, w.cellid);
@@ -439,6 +531,23 @@ extern "C" int mbev_voxelize(const float *points, const int64_t *frame_offsets_h
     MBEV_CHECK_LAUNCH();
   }
   return MBEV_OK;
+}
+
+extern "C" int mbev_voxelize(const float *points, const int64_t *frame_offsets_host, int batch,
+                             const MbevGeometry *geo, int32_t *cell_table, int32_t *coors, int32_t *num_points,
+                             int32_t *kept_idx, int32_t *pillar_base, int64_t pillar_capacity, void *workspace,
+                             size_t workspace_bytes, void *stream_) {
+  return voxelize_impl(points, frame_offsets_host, batch, geo, cell_table, coors, num_points, kept_idx, pillar_base,
+                       pillar_capacity, workspace, workspace_bytes, stream_, nullptr);
+}
+
+extern "C" int mbev_voxelize_augmented(const float *points, const int64_t *frame_offsets_host, int batch,
+                                       const MbevGeometry *geo, const MbevAugment *aug, int32_t *cell_table,
+                                       int32_t *coors, int32_t *num_points, int32_t *kept_idx, int32_t *pillar_base,
+                                       int64_t pillar_capacity, void *workspace, size_t workspace_bytes, void *stream_) {
+  if (!aug || !aug->frames || !aug->points_out) return MBEV_ERR_BAD_ARG;
+  return voxelize_impl(points, frame_offsets_host, batch, geo, cell_table, coors, num_points, kept_idx, pillar_base,
+                       pillar_capacity, workspace, workspace_bytes, stream_, aug);
 }
 
 extern "C" int mbev_gather_voxels(const float *points, const int32_t *kept_idx, const int32_t *num_points,

@@ -98,12 +98,13 @@ class MaskBevEncoder(nn.Module):
 
     # -- fused path -------------------------------------------------------------------------------------
     def encode_batch(self, point_clouds: List[torch.Tensor], return_aux: bool = False,
-                     canvas_dtype: torch.dtype = torch.float32, channels_last: bool = False):
+                     canvas_dtype: torch.dtype = torch.float32, channels_last: bool = False, augment=None):
         """K1 -> K2 -> K3 for the whole batch: (B, C_out, ny, nx) canvas, before the LayerNorm.
         canvas_dtype=torch.bfloat16 (inference only): the canvas is written in bf16; the PFN computes in fp32 unless
         `self._voxel_encoder.gemm_path = 'tcgen05_bf16'` selects the bf16 tensor-core layers as well (BASELINE config 4).
         channels_last=True: the same tensor in torch.channels_last memory format (each pillar's features are one
-        contiguous row; north star item 3), forward and backward."""
+        contiguous row; north star item 3), forward and backward.
+        augment: an ``augment.BatchAugment`` — the reference's point augmentations applied in K1's load stage (f4)."""
         if len(point_clouds) == 0:
             raise MbevError("empty batch")
         if canvas_dtype != torch.float32:
@@ -111,7 +112,9 @@ class MaskBevEncoder(nn.Module):
                 raise MbevError("a bfloat16 canvas is forward-only: call under torch.no_grad()")
         pts, sizes = _as_points(point_clouds)
         geo = self._voxel_layer._geometry(pts.shape[1], strict_filter=True)
-        vb = F_.voxelize_batch(pts, sizes, geo)
+        vb = F_.voxelize_batch(pts, sizes, geo, augment=augment)
+        if vb.points is not None:
+            pts = vb.points  # the augmented cloud: what kept_idx indexes
         feats = self._voxel_encoder.apply_rows(pts, vb.kept_idx, vb.num_points, vb.coors, vb.num_pillars_dev,
                                                vb.capacity, geo.max_points)
         if canvas_dtype == torch.float32:

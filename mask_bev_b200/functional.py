@@ -79,6 +79,7 @@ class VoxelBatch:
     pillar_base: torch.Tensor  # (B+1,) int32
     capacity: int
     batch: int
+    points: Optional[torch.Tensor] = None  # the augmented cloud when K1 ran with augmentations (kept_idx indexes it)
 
     @property
     def num_pillars_dev(self) -> torch.Tensor:
@@ -89,8 +90,10 @@ class VoxelBatch:
 
 
 def voxelize_batch(points: torch.Tensor, frame_sizes: Sequence[int], geo: MbevGeometry,
-                   capacity: Optional[int] = None) -> VoxelBatch:
-    """K1 over a batch of concatenated frames. No host synchronisation."""
+                   capacity: Optional[int] = None, augment=None) -> VoxelBatch:
+    """K1 over a batch of concatenated frames. No host synchronisation.
+    augment: an ``augment.BatchAugment`` — the augmentations run in K1's load stage and the returned
+    batch carries ``points`` = the augmented cloud, which is what ``kept_idx`` indexes (the PFN must gather from it)."""
     _need_cuda(points, "points")
     lib = _lib.load()
     if points.dtype != torch.float32:
@@ -114,9 +117,19 @@ def voxelize_batch(points: torch.Tensor, frame_sizes: Sequence[int], geo: MbevGe
         pillar_base=torch.empty((B + 1,), dtype=torch.int32, device=dev),
         capacity=cap, batch=B)
     with torch.cuda.device(dev):
-        check(lib.mbev_voxelize(ptr(points), off, B, ctypes.byref(geo), ptr(out.cell_table), ptr(out.coors),
-                                ptr(out.num_points), ptr(out.kept_idx), ptr(out.pillar_base), cap, ptr(ws),
-                                ws.numel(), _stream()), "voxelize")
+        if augment is None:
+            check(lib.mbev_voxelize(ptr(points), off, B, ctypes.byref(geo), ptr(out.cell_table), ptr(out.coors),
+                                    ptr(out.num_points), ptr(out.kept_idx), ptr(out.pillar_base), cap, ptr(ws),
+                                    ws.numel(), _stream()), "voxelize")
+        else:
+            aug, keep_alive = augment.to_struct(dev, B, total, points.shape[1])
+            out.points = torch.empty_like(points)
+            aug.points_out = out.points.data_ptr()
+            check(lib.mbev_voxelize_augmented(ptr(points), off, B, ctypes.byref(geo), ctypes.byref(aug),
+                                              ptr(out.cell_table), ptr(out.coors), ptr(out.num_points),
+                                              ptr(out.kept_idx), ptr(out.pillar_base), cap, ptr(ws), ws.numel(),
+                                              _stream()), "voxelize_augmented")
+            out._keep_alive = keep_alive
     return out
 
 

@@ -509,6 +509,37 @@ def patch_embed_on_pillars_np(feat, coors4, batch_size, ny, nx, ln_weight, ln_bi
 
 
 # --------------------------------------------------------------------------------------------------
+# F4 — point side of the reference's augmentations (mask_bev/augmentations/semantic_kitti_mask_augmentations.py),
+# in the order train_mask_bev.py:71 composes the configured list: RandomDropPoints (:152-162), Flip (:44-56),
+# RandomRotate (:73-101), JitterPoints (:116-149). PINNED to executed reference code: tests/golden/augment_reference.npz
+# holds outputs of the reference's own classes (make_golden_augment.py); this restatement, driven by the decisions the
+# product's sampler replays from the same numpy seed, reproduces them bit for bit (tests/test_augment.py).
+# --------------------------------------------------------------------------------------------------
+def augment_points_np(points: np.ndarray, keep=None, flip_x=False, flip_y=False, theta_deg=None, noise=None):
+    """points (N, 4) float32; keep: bool (N,) or None; noise: (N, 4) float64 in ORIGINAL row indexing or None.
+    Returns the augmented cloud with the dropped rows removed, as the reference leaves it."""
+    pc = np.array(points, dtype=np.float32, copy=True)
+    if keep is not None:
+        pc = pc[keep]                                           # :160
+        if noise is not None:
+            noise = noise[keep]
+    if flip_x:
+        pc[:, 0] = -pc[:, 0]                                    # :51
+    if flip_y:
+        pc[:, 1] = -pc[:, 1]                                    # :54
+    if theta_deg is not None:                                   # :88-97: float64 R @ (x, y, z, 1), stored into float32
+        c, s = np.cos(np.deg2rad(theta_deg)), np.sin(np.deg2rad(theta_deg))
+        x, y = pc[:, 0].astype(np.float64), pc[:, 1].astype(np.float64)
+        pc[:, 0] = (c * x + (-s) * y) + 0.0                     # the matrix row's 0 * z + 0 * 1 terms: -0 becomes +0
+        pc[:, 1] = (s * x + c * y) + 0.0
+        pc[:, 2] = pc[:, 2].astype(np.float64) + 0.0
+    if noise is not None:
+        pc += noise                                             # :145 (float64 sum, stored into float32)
+        np.clip(pc[:, 3], 0, 1, pc[:, 3])                       # :146
+    return pc
+
+
+# --------------------------------------------------------------------------------------------------
 # The whole path — mirrors MaskBevEncoder (mask_bev_encoders.py:21-123) on CPU
 # --------------------------------------------------------------------------------------------------
 class MaskBevEncoderOracle:
