@@ -661,6 +661,10 @@ struct Plan {
   int *blocksum;  // (nb)
   int *ctot;      // (nbA)
   int *bounds;    // (8 * grid + 1) first pillar of each sub-range (k_pfn_tcw2: one per set and TMEM lane quadrant)
+  // k_pfn_tcw2 walks every sub-range sorted by row count (pfn_tcw2.cuh): order[i] = pillar at sorted position i of
+  // its sub-range, np_sorted[i] = its num_points (scratch the kernel fills itself)
+  int *order, *np_sorted;
+  int64_t cap;
 };
 
 // MBEV_OK when the stack fits the tensor-core kernel, MBEV_ERR_UNSUPPORTED when it must run on the FMA kernel.
@@ -750,11 +754,13 @@ inline int make_plan(const MbevPfnParams *p, int C, int T, int64_t pillar_capaci
   out->nbA = (out->nb + kRbBlocks - 1) / kRbBlocks;
   out->ctot = cw.take<int>(out->nbA);
   out->bounds = cw.take<int>(8 * out->grid + 1);
+  out->cap = std::max<int64_t>(pillar_capacity, 1);
+  out->order = cw.take<int>(static_cast<size_t>(out->cap));
+  out->np_sorted = cw.take<int>(static_cast<size_t>(out->cap));
   out->ws_bytes = cw.off;
   return MBEV_OK;
 }
 
-// weight images + the row-balanced CTA partition (once per forward call; shared by the STATS and FULL launches)
 inline int launch_prep(const MbevPfnParams *p, Plan &pl, const int32_t *num_points, const int32_t *num_pillars_dev,
                        cudaStream_t stream) {
   for (int l = 0; l < pl.k.L; ++l) {

@@ -55,10 +55,69 @@ struct Window {
 // calls it with the same cursor
 // num_points of the 32 pillars a window starting at `cursor` may take (lane i: pillar cursor + i), requested a whole
 // chunk before pack_window consumes it
-__device__ __forceinline__ int load_np(const int *__restrict__ num_points, int cursor, int pend, int lane) {
-  return cursor + lane < pend ? __ldg(num_points + cursor + lane) : 0;
+__device__ __forceinline__ int load_np(const int *num_points, int cursor, int pend, int lane) {
+  return cursor + lane < pend ? num_points[cursor + lane] : 0;  // plain load: np_sorted is written by this kernel
 }
-__device__ __forceinline__ Window pack_window(int np, int cursor, int pend, int T, int lane) {
+__device__ __forceinline__ int load_ord(const int *order, int cursor, int pend, int lane) {
+  return cursor + lane < pend ? order[cursor + lane] : 0;
+}
+
+// Local counting sort of a sub-range's pillars by row count, longest first (stable, no atomics: ranks inside a group of
+// 32 come from __match_any_sync, so the two warps that share a quadrant build the SAME order independently and write
+// identical values). The per-pillar max is a log2(longest pillar of the window)-round shuffle all-reduce, a third of
+// K2's time; pillars come numbered by first appearance, i.e. lengths are mixed at random and nearly every 32-row window
+// holds a long pillar: 3-4 rounds everywhere. Sorted, the windows are uniform — on LiDAR frames a third of all rows sit
+// in 2-row pillars (one point + the virtual row) and need ONE round. Sorting inside the sub-range keeps the row-balanced
+// partition and the locality of the kept_idx / coors / feats rows. Results do not depend on the order at all.
+constexpr int kSortClasses = 64;
+__device__ __forceinline__ int sort_class(int n, int T) { return min(kSortClasses - 1, max(0, 33 - (n + (n < T ? 1 : 0)))); }
+__device__ __forceinline__ void sort_subrange(const int *__restrict__ num_points, int p0, int pend, int T, int lane,
+                                              int *s_cls, int *order, int *np_sorted) {
+  s_cls[lane] = 0;
+  s_cls[lane + 32] = 0;
+  __syncwarp();
+#pragma unroll 4
+  for (int b = p0; b < pend; b += 32) {
+    const int p = b + lane;
+    const bool valid = p < pend;
+    const int cls = valid ? sort_class(__ldg(num_points + p), T) : kSortClasses + lane;
+    const unsigned m = __match_any_sync(0xffffffffu, cls);
+    if (valid && lane == __ffs(m) - 1) s_cls[cls] += __popc(m);
+    __syncwarp();
+  }
+  {  // exclusive prefix over the 64 classes
+    const int a = s_cls[2 * lane], c = s_cls[2 * lane + 1];
+    int inc = a + c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __syncwarp();
+    s_cls[2 * lane] = inc - a - c;
+    s_cls[2 * lane + 1] = inc - c;
+    __syncwarp();
+  }
+#pragma unroll 2
+  for (int b = p0; b < pend; b += 32) {
+    const int p = b + lane;
+    const bool valid = p < pend;
+    const int n = valid ? __ldg(num_points + p) : 0;
+    const int cls = valid ? sort_class(n, T) : kSortClasses + lane;
+    const unsigned m = __match_any_sync(0xffffffffu, cls);
+    if (valid) {
+      const int slot = p0 + s_cls[cls] + __popc(m & ((1u << lane) - 1u));
+      order[slot] = p;
+      np_sorted[slot] = n;
+    }
+    __syncwarp();
+    if (valid && lane == __ffs(m) - 1) s_cls[cls] += __popc(m);
+    __syncwarp();
+  }
+  __syncwarp();
+}
+// np / ord: num_points and pillar id of the candidate at sorted position cursor + lane
+__device__ __forceinline__ Window pack_window(int np, int ord, int cursor, int pend, int T, int lane) {
   Window w;
   const bool cand = cursor + lane < pend;
   const int need = cand ? np + (np < T ? 1 : 0) : 0;
@@ -83,7 +142,7 @@ __device__ __forceinline__ Window pack_window(int np, int cursor, int pend, int 
   w.s1 = w.inwin ? (above ? __ffs(above) - 2 : w.nrows - 1) : lane;
   w.t = lane - w.s0;
   w.real = w.inwin && w.t < w.n;
-  w.pil = cursor + pi;
+  w.pil = __shfl_sync(0xffffffffu, ord, pi);
   w.maxlen = __reduce_max_sync(0xffffffffu, w.s1 - w.s0 + 1);
   return w;
 }
@@ -296,12 +355,16 @@ __device__ __forceinline__ void seg_allmax_bf16(const Window &w, int lane, uint3
 // Register budget: 20 warps = 5 on each of the four SM sub-partitions (16 384 registers each), so the kernel starts
 // with 96 registers per thread; the last warpgroup (MMA issuers: uniform-register work only) then hands its registers
 // back and the epilogue warpgroups grow to 112 (setmaxnreg): 4 x 32 x 112 + 32 x 24 per sub-partition; the grow must fit into what the shrink released: 128 x 72 >= 512 x 16.
-constexpr int kW2RegsLaunch = 96, kW2RegsEpi = 112, kW2RegsIssuer = 24;
+#ifndef MBEV_W2_REGS_LAUNCH
+#define MBEV_W2_REGS_LAUNCH 96
+#define MBEV_W2_REGS_EPI 112
+#endif
+constexpr int kW2RegsLaunch = MBEV_W2_REGS_LAUNCH, kW2RegsEpi = MBEV_W2_REGS_EPI, kW2RegsIssuer = 24;
 template <bool kBf16>
 __global__ void __maxnreg__(kW2RegsLaunch)
-k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, const int *__restrict__ num_points,
-           const int *__restrict__ coors, const int *__restrict__ bounds8, float *__restrict__ feats,
-           const __grid_constant__ Kargs k) {
+k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx, const int *__restrict__ num_points_nat,
+           int *np_sorted, int *order, const int *__restrict__ coors, const int *__restrict__ bounds8,
+           float *__restrict__ feats, const __grid_constant__ Kargs k) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float *s_ss = reinterpret_cast<float *>(smem_raw + k.o_ss);     // [L][2][128]
@@ -433,9 +496,12 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
     int *live = s_live + 4 * set;
 
     // prologue of the gather pipeline: window 0 and its points, num_points of window 1
-    Window w = pack_window(load_np(num_points, cursor, pend, lane), cursor, pend, k.T, lane);
+    sort_subrange(num_points_nat, cursor, pend, k.T, lane, reinterpret_cast<int *>(smem_raw + k.o_scr) + 4 * kW2Sets * 32 * kStageFloats + warp * kSortClasses,
+                  order, np_sorted);
+    const int *num_points = np_sorted;
+    Window w = pack_window(load_np(num_points, cursor, pend, lane), load_ord(order, cursor, pend, lane), cursor, pend, k.T, lane);
     int cnext = cursor + w.cnt;
-    int np_next = load_np(num_points, cnext, pend, lane);
+    int np_next = load_np(num_points, cnext, pend, lane), ord_next = load_ord(order, cnext, pend, lane);
     float *stage = reinterpret_cast<float *>(smem_raw + k.o_scr) + ((4 * set + quad) * 32 + lane) * kStageFloats;
     const uint32_t stage_u = smem_u32(stage);
     if (h == 0) {
@@ -473,9 +539,10 @@ k_pfn_tcw2(const float *__restrict__ rows_src, const int *__restrict__ kept_idx,
         if (l == max(L - 3, 0)) {
           // next window (its num_points were requested a chunk ago), the kept_idx entries of its rows, num_points of the
           // window after it
-          wn = pack_window(np_next, cnext, pend, k.T, lane);
+          wn = pack_window(np_next, ord_next, cnext, pend, k.T, lane);
           cnn = cnext + wn.cnt;
           np_next = load_np(num_points, cnn, pend, lane);
+          ord_next = load_ord(order, cnn, pend, lane);
           if (h == 0) src_n = gather_index(k, wn, kept_idx);
         }
         if (h == 0) {
@@ -616,6 +683,7 @@ inline bool tcw2_plan(Kargs &k) {
   k.o_tab = o; o += 4 * kW2Sets * 4;
   o = (o + 15u) & ~15u;
   k.o_scr = o; o += 4 * kW2Sets * 32 * kStageFloats * 4;  // gather staging: one 64-byte slot per row of every window
+  o += kW2EpiWarps * kSortClasses * 4;                  // class counters of the sub-range sort, one set per epilogue warp
   k.o_bar = o; o += 8 * kW2NumBars + 16;
   k.smem_bytes = static_cast<int>(o);
   return k.smem_bytes <= kSmemLimit;
@@ -632,10 +700,10 @@ inline int launch(const Plan &pl, const float *rows, const int32_t *kept_idx, co
   if (k.bf16) {  // single-pass bf16 layers: k_pfn_tcw2 only, eval-mode only (the STATS launches are 3xTF32 images)
     if (stat_layer >= 0 || !tcw2_plan(k2)) return MBEV_ERR_UNSUPPORTED;
     MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    k_pfn_tcw2<true><<<pl.grid, kW2Threads, k2.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k2);
+    k_pfn_tcw2<true><<<pl.grid, kW2Threads, k2.smem_bytes, stream>>>(rows, kept_idx, num_points, pl.np_sorted, pl.order, coors, pl.bounds, feats, k2);
   } else if (stat_layer < 0 && tcw2_plan(k2)) {
     MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tcw2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    k_pfn_tcw2<false><<<pl.grid, kW2Threads, k2.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k2);
+    k_pfn_tcw2<false><<<pl.grid, kW2Threads, k2.smem_bytes, stream>>>(rows, kept_idx, num_points, pl.np_sorted, pl.order, coors, pl.bounds, feats, k2);
   } else {
     MBEV_CUDA(cudaFuncSetAttribute(k_pfn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     k_pfn_tc<<<pl.grid, kThreads, k.smem_bytes, stream>>>(rows, kept_idx, num_points, coors, pl.bounds, feats, k);
