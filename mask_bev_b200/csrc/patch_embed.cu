@@ -116,12 +116,12 @@ struct PeArgs {
   float *Z;             // (pillar capacity, E): row = pillar id
   int C, E, nx, ncls;
   uint32_t img_bytes;   // E * C * 4: one hi or lo image
-  uint32_t o_bar;
+  uint32_t o_stage, o_bar;  // byte offsets in dynamic shared memory: per-warp staging tiles, barriers
   int smem_bytes;
 };
 
-// One chunk = 128 consecutive slots of one class. Worker thread (row r = TMEM lane, channel half hh): g = f * lnw for
-// its 64 channels, all 32 float4 loads of the row half in flight at once; split to TF32 hi / lo -> TMEM. The issuer
+// One chunk = 128 consecutive slots of one class. Worker warps build A = f * lnw (split to TF32 hi / lo) in tensor
+// memory and drain D to Z, both through a swizzled staging tile so that global accesses are whole lines. The issuer
 // warp keeps the class's weight slice in shared memory (reloaded by bulk copies when the CTA crosses a class border,
 // 16 times per launch in total) and issues 3 MMAs per K-step with uniform operands. Phases of a chunk are serial
 // (A and D fill the 512 TMEM columns); the kernel is bound by the gather / store bytes, not by the tensor pipe.
@@ -198,25 +198,48 @@ k_pe_gemm(const __grid_constant__ PeArgs a) {
     }
   } else {
     // =========================================== workers =======================================================
+    // Warp (quad, hh) owns rows [32 quad, 32 quad + 32) x channels [hh kHalf, (hh + 1) kHalf). Tensor memory wants one row
+    // per lane, global memory wants a warp instruction to cover whole 128-byte lines: a thread-per-row float4 access
+    // touches 32 lines per instruction (32 L1 wavefronts; the first form of this kernel spent ~14 k of its 30 k cycles
+    // per chunk there). So rows travel through a per-warp 4 KB staging tile: global <-> tile with 8 lanes per row (4
+    // rows x 128 contiguous bytes per instruction), tile <-> registers with a lane per row; 16-byte units are XOR-
+    // swizzled by the row so that both sides are bank-conflict free.
+    constexpr int kPW = kHalf >= 32 ? 32 : 16;      // channels per pass
+    constexpr int kPasses = kHalf / kPW;
+    constexpr int kLPR = kPW / 4;                   // lanes per row on the global side (16-byte pieces)
+    constexpr int kRPI = 32 / kLPR;                 // rows per instruction
+    constexpr int kIts = 32 / kRPI;                 // instructions per pass and tensor
     const int quad = warp & 3, hh = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t tl = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw + a.o_stage) + warp * 256;  // 32 rows x 8 units of 16 bytes
+    const int grow = lane / kLPR, piece = lane % kLPR;  // global side: row inside the instruction, 16-byte piece
+    auto unit = [](int r, int j) { return r * 8 + (j ^ (r & 7)); };
     uint32_t par_d = 0;
-    float4 f[kHalf / 4], w[kHalf / 4];
-    // the row's 2 x 16 float4 loads are requested a whole chunk ahead: under the previous chunk's MMAs and drain
+    float4 g[kPasses][kIts];
+    // products f * lnw of the chunk's rows, requested a whole chunk ahead (under the previous chunk's MMAs and drain)
     auto request = [&](int c) -> int {
       const int p = (c < c_hi) ? __ldg(a.perm + c * kPeRows + row) : -1;
+      int cell = 0;
       if (p >= 0) {
         const int4 cc = __ldg(reinterpret_cast<const int4 *>(a.coors) + p);
-        const float4 *fp = reinterpret_cast<const float4 *>(a.feats + static_cast<size_t>(p) * kC + hh * kHalf);
-        const float4 *wp = reinterpret_cast<const float4 *>(a.lnw_cl + (static_cast<size_t>(cc.z) * a.nx + cc.w) * kC + hh * kHalf);
+        cell = cc.z * a.nx + cc.w;
+      }
 #pragma unroll
-        for (int q = 0; q < kHalf / 4; ++q) f[q] = __ldg(fp + q);
+      for (int it = 0; it < kIts; ++it) {
+        const int r = it * kRPI + grow;
+        const int pr = __shfl_sync(0xffffffffu, p, r), cr = __shfl_sync(0xffffffffu, cell, r);
 #pragma unroll
-        for (int q = 0; q < kHalf / 4; ++q) w[q] = __ldg(wp + q);
-      } else {
-#pragma unroll
-        for (int q = 0; q < kHalf / 4; ++q) f[q] = w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ps = 0; ps < kPasses; ++ps) {
+          if (pr >= 0) {
+            const int ch = hh * kHalf + ps * kPW + 4 * piece;
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(a.feats + static_cast<size_t>(pr) * kC + ch));
+            const float4 y = __ldg(reinterpret_cast<const float4 *>(a.lnw_cl + static_cast<size_t>(cr) * kC + ch));
+            g[ps][it] = make_float4(__fmul_rn(x.x, y.x), __fmul_rn(x.y, y.y), __fmul_rn(x.z, y.z), __fmul_rn(x.w, y.w));
+          } else {
+            g[ps][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
       }
       return p;
     };
@@ -224,19 +247,26 @@ k_pe_gemm(const __grid_constant__ PeArgs a) {
     for (int c = c_lo; c < c_hi; ++c) {
       const int p = p_next;
 #pragma unroll
-      for (int jb = 0; jb < kHalf / 16; ++jb) {
-        uint32_t hi[16], lo[16];
+      for (int ps = 0; ps < kPasses; ++ps) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 x = f[4 * jb + q], y = w[4 * jb + q];
-          split_tf32_alu(__fmul_rn(x.x, y.x), hi[4 * q + 0], lo[4 * q + 0]);
-          split_tf32_alu(__fmul_rn(x.y, y.y), hi[4 * q + 1], lo[4 * q + 1]);
-          split_tf32_alu(__fmul_rn(x.z, y.z), hi[4 * q + 2], lo[4 * q + 2]);
-          split_tf32_alu(__fmul_rn(x.w, y.w), hi[4 * q + 3], lo[4 * q + 3]);
+        for (int it = 0; it < kIts; ++it) stage[unit(it * kRPI + grow, piece)] = g[ps][it];
+        __syncwarp();
+#pragma unroll
+        for (int jb = 0; jb < kPW / 16; ++jb) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = stage[unit(lane, 4 * jb + q)];
+            split_tf32_alu(v.x, hi[4 * q + 0], lo[4 * q + 0]);
+            split_tf32_alu(v.y, hi[4 * q + 1], lo[4 * q + 1]);
+            split_tf32_alu(v.z, hi[4 * q + 2], lo[4 * q + 2]);
+            split_tf32_alu(v.w, hi[4 * q + 3], lo[4 * q + 3]);
+          }
+          const uint32_t col = static_cast<uint32_t>(hh * kHalf + ps * kPW + 16 * jb);
+          tmem_st16(tl + kColAH + col, hi);
+          tmem_st16(tl + kColAL + col, lo);
         }
-        const uint32_t col = static_cast<uint32_t>(hh * kHalf + 16 * jb);
-        tmem_st16(tl + kColAH + col, hi);
-        tmem_st16(tl + kColAL + col, lo);
+        __syncwarp();
       }
       tc_wait_st();
       tc_fence_before();
@@ -246,19 +276,37 @@ k_pe_gemm(const __grid_constant__ PeArgs a) {
       mbar_wait(bar_d, par_d);
       par_d ^= 1u;
       tc_fence_after();
+      // drain: D columns [hh E/2, (hh + 1) E/2) of the warp's 32 rows -> tile -> 128-byte row pieces of Z[pillar]
       const int Eh = E >> 1;
-      float *zrow = a.Z + static_cast<size_t>(p >= 0 ? p : 0) * E + hh * Eh;
-      for (int jb = 0; jb < Eh / 16; ++jb) {
-        uint32_t v[16];
-        tmem_ld16(tl + kColD + static_cast<uint32_t>(hh * Eh + 16 * jb), v);
-        tc_wait_ld();
-        if (p >= 0) {
-          float4 *out = reinterpret_cast<float4 *>(zrow + 16 * jb);
+      for (int c0 = 0; c0 < Eh; c0 += 32) {
+        const bool wide = c0 + 32 <= Eh;  // 32-column pass, or the 16-column tail (E / 2 is a multiple of 16)
+        if (wide) {
+          uint32_t v[32];
+          tmem_ld32(tl + kColD + static_cast<uint32_t>(hh * Eh + c0), v);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            stage[unit(lane, q)] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                               __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        } else {
+          uint32_t v[16];
+          tmem_ld16(tl + kColD + static_cast<uint32_t>(hh * Eh + c0), v);
+          tc_wait_ld();
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            out[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                 __uint_as_float(v[4 * q + 3]));
+            stage[unit(lane, q)] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                               __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
         }
+        __syncwarp();
+        const int lpr = wide ? 8 : 4, rpi = 32 / lpr;
+        const int dr = lane / lpr, dp = lane % lpr;
+        for (int it = 0; it < 32 / rpi; ++it) {
+          const int r = it * rpi + dr;
+          const int pr = __shfl_sync(0xffffffffu, p, r);
+          const float4 v = stage[unit(r, dp)];
+          if (pr >= 0) *reinterpret_cast<float4 *>(a.Z + static_cast<size_t>(pr) * E + hh * Eh + c0 + 4 * dp) = v;
+        }
+        __syncwarp();
       }
       tc_fence_before();  // D is read: the next chunk's MMAs (ordered after this warp's next arrival) may overwrite it
     }
@@ -395,7 +443,7 @@ bool pe_shape_ok(int batch, int C, int ny, int nx, int ps, int E) {
   if (batch < 1 || batch > MBEV_MAX_BATCH || ny < 1 || nx < 1 || ps < 1 || ps * ps > kPeMaxClasses) return false;
   if (C != 32 && C != 64 && C != 128) return false;            // A = hi + lo images of K = C columns in tensor memory
   if (E < 32 || E > 256 || (E % 32)) return false;             // two 16-column-batched halves; N of one tcgen05.mma
-  if (2u * static_cast<uint32_t>(E) * C * 4u + 64u > static_cast<uint32_t>(kPeSmemLimit)) return false;  // weight slab
+  if (2u * static_cast<uint32_t>(E) * C * 4u + (kPeWorkers / 32) * 4096u + 192u > static_cast<uint32_t>(kPeSmemLimit)) return false;  // weight slab + staging
   if (static_cast<int64_t>(ny) * nx * batch > 0x7fffffffLL) return false;
   return true;
 }
@@ -480,7 +528,8 @@ extern "C" int mbev_patch_embed_forward(const float *feats, const int32_t *coors
   a.nx = nx;
   a.ncls = ncls;
   a.img_bytes = static_cast<uint32_t>(E) * C * 4u;
-  a.o_bar = (2u * a.img_bytes + 127u) & ~127u;
+  a.o_stage = (2u * a.img_bytes + 127u) & ~127u;
+  a.o_bar = a.o_stage + (kPeWorkers / 32) * 4096u;
   a.smem_bytes = static_cast<int>(a.o_bar + 64);
   const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(w.slots / kPeRows, kNumSMs)));
   if (C == 128) {
