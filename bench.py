@@ -599,8 +599,11 @@ def run_ours(args):
                     F_.scatter_layernorm_forward(runner.feats, runner.cell_table, runner.pillar_base, B, runner.ny, runner.nx,
                                                  ln.weight, ln.bias, ln.eps, out=x)
 
+                    pad = (0, Wp * 4 - runner.nx, 0, Hp * 4 - runner.ny)  # PatchEmbed's corner padding
+
                     def dense():
-                        return pe.norm(pe.projection(x).flatten(2).transpose(1, 2))
+                        xp = torch.nn.functional.pad(x, pad) if (pad[1] or pad[3]) else x
+                        return pe.norm(pe.projection(xp).flatten(2).transpose(1, 2))
                     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                         ref = dense()
                         t_dense = ev_time(dense, 3, sync)
