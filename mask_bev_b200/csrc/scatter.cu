@@ -40,7 +40,7 @@ __device__ __forceinline__ void load_run_table(const int *__restrict__ table, co
   }
 }
 
-// `csplit` > 1 (small batches): a task is (run, channel chunk) so that one frame still fills the machine.
+// A task is (run, channel chunk of >= 8 planes): see the task order below.
 // One CTA per 8 tasks and NO grid-stride loop: runs cost very different amounts (0 ... 256 pillars) and the hardware
 // CTA scheduler balances them better than a persistent grid did (0.94 -> 0.88 ms on kitti_b16).
 __global__ void __launch_bounds__(kThreads)
@@ -51,9 +51,16 @@ k_scatter_run(const float *__restrict__ feats, const int *__restrict__ table, co
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   const int task = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (task >= num_runs * csplit) return;
-  const int run = num_runs - 1 - task / csplit;  // last frame first: its feature rows are the freshest in L2
-  const int ch0 = (task % csplit) * cper, ch1 = min(C, ch0 + cper);
-  const int b = run / runs_per_frame;
+  // Task order (frame, channel chunk, run), last frame first (its feature rows are the freshest in L2): consecutive warps
+  // write consecutive kilobytes of the same few planes, so the ~10 k warps in flight cover ~32 planes of one frame as
+  // sequential streams instead of 128 planes x a few runs — DRAM row locality is worth 11 % here (kitti_b16: 0.872 ->
+  // 0.779 ms = 6.97 TB/s, above the measured COPY bandwidth; a plain fill reaches 7.44 TB/s). 8 planes per task is the
+  // optimum: fewer and the per-task table read / empty-run test dominates (4 planes: 0.916 ms, 1 plane: 1.84 ms).
+  const int fb = task / (runs_per_frame * csplit), rem = task - fb * (runs_per_frame * csplit);
+  const int cc = rem / runs_per_frame;
+  const int b = (num_runs / runs_per_frame) - 1 - fb;
+  const int run = b * runs_per_frame + (rem - cc * runs_per_frame);
+  const int ch0 = cc * cper, ch1 = min(C, ch0 + cper);
   const int g0 = (run - b * runs_per_frame) * kRunCells + 4 * lane;
   int4 pid[2];
   bool any;
@@ -506,7 +513,8 @@ extern "C" int mbev_scatter_forward(const float *feats, const int32_t *cell_tabl
     const int rpf = (G + kRunCells - 1) / kRunCells;
     const int nr = rpf * batch;
     const int want_warps = kNumSMs * 6 * (kThreads / 32);
-    int cs = 1;  // small batches: split the channels of a run over several warps
+    int cs = 1;  // channel chunks per run: 8 planes per task (see k_scatter_run), more chunks only to fill the machine
+    while (c_out % (2 * cs) == 0 && c_out / (2 * cs) >= 8) cs *= 2;
     while (cs < 16 && nr * cs < want_warps && c_out % (8 * cs) == 0) cs *= 2;
     const int64_t tasks = static_cast<int64_t>(nr) * cs;
     const int blocks = static_cast<int>((tasks + kThreads / 32 - 1) / (kThreads / 32));
