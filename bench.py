@@ -482,6 +482,10 @@ def run_ours(args):
     t_vox = ev_time(runner.run_voxelize, iters, sync)
     t_pfn = ev_time(runner.run_pfn, iters, sync)
     t_sc = ev_time(runner.run_scatter, iters, sync)
+    # a plain fill of the same canvas: what a write-only stream reaches on this GPU (the roofline `peak` below is the
+    # driver's measured COPY bandwidth, which a pure write stream can exceed)
+    t_fill = ev_time(lambda: runner.canvas.zero_(), iters, sync)
+    runner.run_scatter()
     stream_ok = bool(runner.lib.mbev_scatter_stream_supported(Co, runner.ny, runner.nx, ctypes.c_void_p(runner.canvas.data_ptr())))
     t_st = {c: ev_time(lambda c=c: runner.run_scatter_stream(c), iters, sync) for c in (1, 2, 4, 8)} if stream_ok else {}
     t_nhwc = ev_time(runner.run_scatter_nhwc, iters, sync) if Co % 4 == 0 else None
@@ -503,7 +507,7 @@ def run_ours(args):
         "K1_voxelize": hbm(by_vox, t_vox),
         "K2_pfn": {**hbm(by_pfn, t_pfn), "alg_tflops_upstream_equiv": fl_pfn / t_pfn / 1e9, "fp32_fma_peak_tflops": 74.4,
                    "path": "tcgen05 3xTF32" if runner.lib.mbev_pfn_path(ctypes.byref(runner.params), T) == 2 else "fp32 FMA"},
-        "K3_scatter": {**hbm(by_sc, t_sc), "kernel": "k_scatter_run (registers -> st.global.cs.v4, machine-filling grid)"},
+        "K3_scatter": {**hbm(by_sc, t_sc), "kernel": "k_scatter_run (registers -> st.global.cs.v4; tasks ordered frame / 8-plane chunk / run: sequential DRAM streams)"},
     }
     for c, tt in t_st.items():
         kernels[f"K3_scatter_stream_{c}cta"] = {**hbm(by_sc, tt), "kernel": f"k_scatter_bulk (TMA bulk stores), {c} x 148 CTAs of 128 threads"}
@@ -626,6 +630,8 @@ def run_ours(args):
             "dominant_by_time": dom, "share_of_serial_step": k3["ms"] / (t_vox + t_pfn + k3["ms"]),
             "timed": "stand-alone launches (CUDA events on the launching stream, inputs resident)"
                      + ("; inside the pipelined step this kernel shares the SMs with K2 of the next batch" if use_stream else ""),
+            "fill_gbs": runner.canvas.numel() * 4 / t_fill / 1e6, "frac_of_fill": k3["gbs"] / (runner.canvas.numel() * 4 / t_fill / 1e6),
+            "fill_note": "torch fill kernel on the same canvas, timed live: the write-only ceiling (frac > 1 means above the COPY peak, not above the hardware)",
             "step_floor_bytes": by_floor, "step_frac": by_floor / step_ms / 1e6 / peak,
             "step_frac_note": "fused-path HBM floor (points read once + canvas written once) / ms_per_step / peak",
             "serial_step_frac": by_floor / (ms_serial / args.steps) / 1e6 / peak}

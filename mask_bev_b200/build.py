@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OUT_DIR = os.path.join(_HERE, "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libmask_bev_b200.so")
 SOURCES = ["api.cu", "voxelize.cu", "scatter.cu", "layernorm.cu", "pfn.cu", "pfn_bwd.cu", "patch_embed.cu"]
-HEADERS = ["common.cuh", "ln_stats.cuh", "tc_ptx.cuh", "pfn_tc.cuh", "pfn_tcw2.cuh", os.path.join("..", "..", "include", "mask_bev_b200.h")]
+HEADERS = ["common.cuh", "ln_stats.cuh", "tc_ptx.cuh", "rows_gemm_tc.cuh", "pfn_tc.cuh", "pfn_tcw2.cuh", os.path.join("..", "..", "include", "mask_bev_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "rows_gemm_tc.cuh"
 
 namespace mbev {
 namespace {
@@ -518,6 +519,7 @@ struct BwdWs {
   float *row_w, *X, *DZ, *DX, *Mx[MBEV_MAX_LAYERS], *Y[MBEV_MAX_LAYERS], *c12, *wpart;
   float *stats;  // (L, 4, MBEV_MAX_UNITS): scale, shift, mean, var recomputed by this pass (train mode)
   double *partials;
+  float *img_fwd[MBEV_MAX_LAYERS], *img_dx[MBEV_MAX_LAYERS];  // hi / lo TF32 images of W_l and W_l^T (tensor-core GEMMs)
   size_t bytes;
 };
 
@@ -547,8 +549,26 @@ BwdWs carve_bwd(void *ws, const MbevPfnParams *p, int64_t cap, int64_t rows_cap)
   w.wpart = c.take<float>(static_cast<size_t>(kSplitK) * umax * inmax);
   w.partials = c.take<double>(static_cast<size_t>(kDzBlocks) * 2 * umax);
   w.stats = c.take<float>(static_cast<size_t>(MBEV_MAX_LAYERS) * 4 * MBEV_MAX_UNITS);
+  for (int l = 0; l < p->num_layers; ++l) {
+    w.img_fwd[l] = c.take<float>(static_cast<size_t>(2) * p->units[l] * p->in_dim[l]);
+    w.img_dx[l] = c.take<float>(static_cast<size_t>(2) * p->units[l] * p->in_dim[l]);
+  }
   w.bytes = c.off;
   return w;
+}
+
+// The two row-space products of a layer, Y = X W^T (K = in, N = units) and dX = dY W (K = units, N = in), run as 3xTF32
+// tcgen05 GEMMs (rows_gemm_tc.cuh, the patch embedding's kernel without the gather) when the shapes fit: K in {64, 128},
+// N a multiple of 32 — every layer but the first of the configured stacks. fp32 parity as in the forward (a_l * w_l
+// dropped: <= 2^-22 relative); the FMA kernels remain for layer 0 (K = 10..12) and as `gemm_path = MBEV_GEMM_FMA`.
+// In TRAIN mode the recompute Y = X W^T stays on the FMA kernel: BatchNorm's backward subtracts sums that cancel and
+// amplifies the row error a thousandfold (torch's own fp32 gradients are 2e-3 from float64 on the [128,128,128] test
+// case); tensor-core rows — also with the fourth product a_l * w_l and a rounded a_l, measured — put dgamma at 6.4e-3,
+// twice the allowance, so it is the accumulation inside the tensor core, not the split, that costs the accuracy there.
+bool tc_rows_ok(const MbevPfnParams *p, int K, int N) {
+  if (p->gemm_path == MBEV_GEMM_FMA) return false;
+  PeArgs a{};
+  return (K == 64 || K == 128) && pe_gemm_plan(a, N, K);
 }
 
 int launch_gemm(const GemmK &g, int m_tiles_cap, int n, int splits, cudaStream_t stream) {
@@ -658,7 +678,14 @@ extern "C" int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_i
     g.B = params->weight[l]; g.sBk = 1; g.sBn = K;
     g.C = w.Y[l]; g.ldc = U;
     g.M = 0; g.N = U; g.K = K; g.m_dev = w.num_rows; g.k_dev = nullptr; g.split_stride = 0;
-    int st = launch_gemm(g, m_tiles_cap, U, 1, stream);
+    int st;
+    if (!train && tc_rows_ok(params, K, U)) {
+      k_pe_prep_weights<<<dim3((U * K + 255) / 256, 1), 256, 0, stream>>>(params->weight[l], U, K, 1, w.img_fwd[l], 0);
+      MBEV_CHECK_LAUNCH();
+      st = launch_rows_gemm(w.X, w.num_rows, rows_cap, K, U, w.img_fwd[l], w.Y[l], stream);
+    } else {
+      st = launch_gemm(g, m_tiles_cap, U, 1, stream);
+    }
     if (st) return st;
     if (train) {
       const int nls = std::max(1, 1024 / U);
@@ -717,7 +744,14 @@ extern "C" int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_i
       g.B = params->weight[l]; g.sBk = K; g.sBn = 1;
       g.C = w.DX; g.ldc = K;
       g.M = 0; g.N = K; g.K = U; g.m_dev = w.num_rows; g.k_dev = nullptr; g.split_stride = 0;
-      int st = launch_gemm(g, m_tiles_cap, K, 1, stream);
+      int st;
+      if (tc_rows_ok(params, U, K)) {  // B = W_l^T: (N = in, K = units)
+        k_pe_prep_weights<<<dim3((U * K + 255) / 256, 1), 256, 0, stream>>>(params->weight[l], K, U, 1, w.img_dx[l], 1);
+        MBEV_CHECK_LAUNCH();
+        st = launch_rows_gemm(w.DZ, w.num_rows, rows_cap, U, K, w.img_dx[l], w.DX, stream);
+      } else {
+        st = launch_gemm(g, m_tiles_cap, K, 1, stream);
+      }
       if (st) return st;
     }
   }
