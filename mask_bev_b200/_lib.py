@@ -125,6 +125,14 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
             _build.build()
         except Exception as e:  # noqa: BLE001
             raise MbevError(f"cannot build {LIB_PATH}: {e}. mask_bev_b200 has no CPU fallback.") from e
+    else:
+        try:
+            from . import build as _build
+            if _build.is_stale():
+                import warnings
+                warnings.warn(f"{LIB_PATH} is older than its sources; rebuild with `python -m mask_bev_b200.build --force`")
+        except Exception:  # noqa: BLE001 - a missing source tree next to a shipped library is fine
+            pass
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         try:

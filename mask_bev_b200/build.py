@@ -46,12 +46,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     extra = os.environ.get("MBEV_NVCC_EXTRA", "").split()  # developer builds (-DMBEV_K2_TRACE); never set by the product
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH + ".tmp", *srcs]
+    tmp = f"{LIB_PATH}.tmp.{os.getpid()}"  # per process: ranks of one torchrun job may build at the same time
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", tmp, *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    os.replace(tmp, LIB_PATH)  # atomic: a concurrent loader sees the old or the new library, never a partial one
     return LIB_PATH
 
 
