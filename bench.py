@@ -298,7 +298,7 @@ def train_block(args, enc, kwargs, rank, world, dev, barrier):
 
         def step(reduce=True):
             nonlocal g
-            tenc.zero_grad(set_to_none=False)
+            tenc.zero_grad()  # set_to_none=True, torch's and Lightning's default: the fresh LayerNorm gradients become .grad without a 655 MB zero + add pass
             y = tenc(frames)
             if g is None:
                 g = torch.randn_like(y)

@@ -33,7 +33,7 @@ extern "C" {
 #define MBEV_API
 #endif
 
-#define MBEV_ABI_VERSION 10
+#define MBEV_ABI_VERSION 11
 #define MBEV_MAX_BATCH 128  /* frames per call */
 #define MBEV_MAX_LAYERS 4   /* PFN layers */
 #define MBEV_MAX_UNITS 128  /* widest PFNLayer.units supported by the fused kernel */
@@ -193,6 +193,24 @@ MBEV_API int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_idx
                                const float *batch_stats, float eps, int train, const float *dfeats,
                                float *const *dweight, float *const *dgamma, float *const *dbeta, void *workspace,
                                size_t workspace_bytes, void *stream);
+
+/* A TRAINING STEP's pair (train-mode BatchNorm): the forward runs once in compact row space (fp32 FMA products, the
+ * rows BatchNorm's backward differentiates) and LEAVES its activations in `workspace`; the backward consumes them
+ * instead of recomputing the forward. Replaces the same reference lines as mbev_pfn_forward_train + mbev_pfn_backward
+ * (PFNLayer.forward in train mode and its autograd, mask_bev_encoders.py:119-120); outputs and tolerances are the same.
+ *   workspace  mbev_pfn_backward_workspace_bytes(params, T, pillar_capacity, rows_capacity_hint) bytes, caller-owned;
+ *              the caller must keep it untouched between the two calls and pass the SAME pillar_capacity, T,
+ *              rows_capacity_hint and params to both (the layout is a function of those). */
+MBEV_API int mbev_pfn_forward_train_rows(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
+                                         const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity,
+                                         int T, int64_t rows_capacity_hint, const MbevPfnParams *params,
+                                         const float *const *gamma, const float *const *beta, float eps, float *feats,
+                                         float *scale_shift_out, float *batch_stats_out, void *workspace,
+                                         size_t workspace_bytes, void *stream);
+MBEV_API int mbev_pfn_backward_rows(const int32_t *num_pillars_dev, int64_t pillar_capacity, int C, int T,
+                                    int64_t rows_capacity_hint, const MbevPfnParams *params, float eps,
+                                    const float *dfeats, float *const *dweight, float *const *dgamma,
+                                    float *const *dbeta, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3  scatter to the dense BEV canvas, one streaming pass (zeros and features written exactly once).

@@ -13,7 +13,7 @@ MAX_BATCH = 128
 MAX_LAYERS = 4
 MAX_UNITS = 128
 MAX_POINT_DIM = 8
-ABI_VERSION = 10
+ABI_VERSION = 11
 GEMM_AUTO, GEMM_FMA, GEMM_TCGEN05, GEMM_TCGEN05_BF16 = 0, 1, 2, 3
 LN_WALK_RUNS, LN_WALK_FRAMES = 0, 1
 
@@ -72,6 +72,10 @@ SIGNATURES = {
     "mbev_pfn_backward_workspace_bytes": (c_int, [_P, c_int, c_int64, c_int64, POINTER(c_size_t)]),
     "mbev_pfn_backward": (c_int, [_v, c_int, _v, _v, _v, _v, c_int64, c_int, c_int64, _P, _v, _v, c_float, c_int, _v,
                                   POINTER(_PTRS), POINTER(_PTRS), POINTER(_PTRS), _v, c_size_t, _v]),
+    "mbev_pfn_forward_train_rows": (c_int, [_v, c_int, _v, _v, _v, _v, c_int64, c_int, c_int64, _P, POINTER(_PTRS),
+                                            POINTER(_PTRS), c_float, _v, _v, _v, _v, c_size_t, _v]),
+    "mbev_pfn_backward_rows": (c_int, [_v, c_int64, c_int, c_int, c_int64, _P, c_float, _v, POINTER(_PTRS),
+                                       POINTER(_PTRS), POINTER(_PTRS), _v, c_size_t, _v]),
     "mbev_build_cell_table": (c_int, [_v, _v, c_int64, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_forward": (c_int, [_v, _v, c_int, c_int, c_int, c_int, _v, _v]),
     "mbev_scatter_stream_supported": (c_int, [c_int, c_int, c_int, _v]),

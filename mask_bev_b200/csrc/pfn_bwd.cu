@@ -12,10 +12,13 @@
 // from the forward call):
 //   k_row_offsets / k_fill_rows   compact row index: pillar -> [row_off[p], row_off[p+1])
 //   k_decorate_rows               X_0
-//   per layer  l = 0..L-1 :  Y_l = X_l W_l^T (k_gemm) ; m_l = segmented max of relu(bn(Y_l)) ; X_{l+1} = [a_l || m_l]
+//   per layer  l = 0..L-1 :  Y_l = X_l W_l^T ; m_l = segmented max of relu(bn(Y_l)) ; X_{l+1} = [a_l || m_l]
+//                            (every X_l is kept: dW_l needs it again and rebuilding it was a full row-space pass)
 //   per layer  l = L-1..0 :  k_dz (arg-max routing + ReLU mask + BN sums) ; k_bn_finalize (dgamma, dbeta) ;
-//                            k_dy ; dW_l = dY^T X_l (split-K, fixed-order reduce) ; dX = dY W_l
-// Every reduction has a fixed order => run-to-run identical gradients. fp32 FMA throughout (1e-5 parity).
+//                            k_dy ; dW_l = dY^T X_l (k_gemm_dw: split over row slices, fixed-order reduce) ; dX = dY W_l
+// Every reduction has a fixed order => run-to-run identical gradients. Products: dX (always) and the eval-mode recompute
+// run as 3xTF32 tcgen05 GEMMs (rows_gemm_tc.cuh); the train-mode recompute and dW stay on the fp32 FMA pipe (1e-5 parity
+// of gradients that BatchNorm's backward amplifies). The element-wise passes handle four units per thread.
 
 #include <algorithm>
 
@@ -30,49 +33,82 @@ constexpr int kThreads = 256;
 // ---------------------------------------------------------------------------------------------------
 // row space
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_row_offsets(const int *__restrict__ num_points, const int *__restrict__ num_pillars, const int T,
-              int *__restrict__ row_off, int *__restrict__ num_rows) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
+// Compact row index: row_off[p] = sum over pillars before p of (n + [n < T]). Two launches of 256-thread CTAs that own
+// 2048 consecutive pillars each (8 per thread): per-CTA totals, then every CTA re-reduces the totals before it and scans
+// its own pillars. (The single-CTA scan took 86 us for 88 k pillars and 0.3 ms for the 353 k of a 16-frame batch.)
+constexpr int kRowOffPer = 8;
+constexpr int kRowOffTile = 256 * kRowOffPer;
+
+__device__ __forceinline__ int row_count(const int *__restrict__ num_points, const int p, const int P, const int T) {
+  if (p >= P) return 0;
+  const int n = num_points[p];
+  return n + (n < T ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(256)
+k_row_part(const int *__restrict__ num_points, const int *__restrict__ num_pillars, const int T, int *__restrict__ tot) {
+  __shared__ int s_w[8];
   const int P = *num_pillars;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_carry = 0;
-  __syncthreads();
-  for (int base = 0; base < P; base += 1024) {
-    const int p = base + tid;
-    int v = 0;
-    if (p < P) {
-      const int n = num_points[p];
-      v = n + (n < T ? 1 : 0);
-    }
-    int x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, x, d);
-      if ((tid & 31) >= d) x += u;
-    }
-    if ((tid & 31) == 31) s_warp[tid >> 5] = x;
-    __syncthreads();
-    if (tid < 32) {
-      int y = s_warp[tid];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, y, d);
-        if (tid >= d) y += u;
-      }
-      s_warp[tid] = y;
-    }
-    __syncthreads();
-    const int excl = s_carry + x - v + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0);
-    if (p < P) row_off[p] = excl;
-    __syncthreads();
-    if (tid == 1023) s_carry = excl + v;
-    __syncthreads();
+  const int p0 = blockIdx.x * kRowOffTile + threadIdx.x * kRowOffPer;
+  if (blockIdx.x * kRowOffTile >= P) {  // grid sized by the capacity: nothing here
+    if (threadIdx.x == 0) tot[blockIdx.x] = 0;
+    return;
   }
-  if (tid == 0) {
-    row_off[P] = s_carry;
-    *num_rows = s_carry;  // R, at a host-known address
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < kRowOffPer; ++j) sum += row_count(num_points, p0 + j, P, T);
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_w[i];
+    tot[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_row_offsets(const int *__restrict__ num_points, const int *__restrict__ num_pillars, const int T,
+              const int *__restrict__ tot, int *__restrict__ row_off, int *__restrict__ num_rows) {
+  __shared__ int s_w[8], s_b[8];
+  const int P = *num_pillars;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int first = blockIdx.x * kRowOffTile;
+  if (first > P) return;  // (first == P: the CTA that writes the total when P is a multiple of the tile)
+  int base = 0;
+  for (int j = tid; j < static_cast<int>(blockIdx.x); j += 256) base += __ldg(tot + j);
+  base = __reduce_add_sync(0xffffffffu, base);
+  const int p0 = first + tid * kRowOffPer;
+  int v[kRowOffPer], sum = 0;
+#pragma unroll
+  for (int j = 0; j < kRowOffPer; ++j) {
+    v[j] = row_count(num_points, p0 + j, P, T);
+    sum += v[j];
+  }
+  int x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += u;
+  }
+  if (lane == 31) s_w[warp] = x;
+  if (lane == 0) s_b[warp] = base;
+  __syncthreads();
+  int excl = x - sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    excl += s_b[i];
+    if (i < warp) excl += s_w[i];
+  }
+#pragma unroll
+  for (int j = 0; j < kRowOffPer; ++j) {
+    if (p0 + j < P) row_off[p0 + j] = excl;
+    if (p0 + j == P) {  // one past the last pillar: the total
+      row_off[P] = excl;
+      *num_rows = excl;  // R, at a host-known address
+    }
+    excl += v[j];
   }
 }
 
@@ -293,14 +329,139 @@ k_gemm_rows(const __grid_constant__ GemmK g) {
   }
 }
 
-// fixed-order reduction of split-K partials into dst (count elements)
-__global__ void k_reduce_splits(const float *__restrict__ part, const int nsplit, const long long stride,
-                                const int count, float *__restrict__ dst) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// dW slice: part[z] (U, Kin) = sum over the rows of slice z of dY[r][:]^T X[r][:] — both factors row-major with the
+// reduction along rows, so a k-block is 16 whole rows of each (16-byte loads, no transposition). One CTA owns the WHOLE
+// (<= 128 x 128) output: BM x 128 tile, (BM/16) x 8 outputs per thread (16 FMAs per shared-memory load against 8 in
+// k_gemm's 4 x 4), next k-block's rows in flight while the current one is multiplied. Rows accumulate in order with one
+// fmaf per term, as in k_gemm: same partials bit for bit.
+template <int BM>
+__global__ void __launch_bounds__(256)
+k_gemm_dw(const float *__restrict__ DY, const float *__restrict__ X, const int U, const int Kin,
+          const int *__restrict__ num_rows, float *__restrict__ part, const long long split_stride) {
+  constexpr int BN = 128, BK = 16, TM = BM / 16, NA = BM / 64;
+  __shared__ __align__(16) float sA[BK][BM + 4];
+  __shared__ __align__(16) float sB[BK][BN + 4];
+  const int R = *num_rows;
+  const int nsplit = gridDim.x;
+  const int kper = ((R + nsplit - 1) / nsplit + BK - 1) / BK * BK;
+  const int k0 = min(R, static_cast<int>(blockIdx.x) * kper), k1 = min(R, k0 + kper);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[TM][8];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ra[NA], rb[2];
+  auto gload = [&](int kb) {
+#pragma unroll
+    for (int it = 0; it < NA; ++it) {
+      const int idx = tid + it * 256, row = idx / (BM / 4), c = (idx % (BM / 4)) * 4, r = kb + row;
+      ra[it] = (r < k1 && c < U) ? __ldg(reinterpret_cast<const float4 *>(DY + static_cast<size_t>(r) * U + c)) : z4;
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = tid + it * 256, row = idx >> 5, c = (idx & 31) * 4, r = kb + row;
+      rb[it] = (r < k1 && c < Kin) ? __ldg(reinterpret_cast<const float4 *>(X + static_cast<size_t>(r) * Kin + c)) : z4;
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int it = 0; it < NA; ++it) {
+      const int idx = tid + it * 256;
+      *reinterpret_cast<float4 *>(&sA[idx / (BM / 4)][(idx % (BM / 4)) * 4]) = ra[it];
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = tid + it * 256;
+      *reinterpret_cast<float4 *>(&sB[idx >> 5][(idx & 31) * 4]) = rb[it];
+    }
+  };
+  if (k0 < k1) gload(k0);
+  for (int kb = k0; kb < k1; kb += BK) {
+    __syncthreads();
+    sstore();
+    __syncthreads();
+    if (kb + BK < k1) gload(kb + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[TM], bv[8];
+#pragma unroll
+      for (int i4 = 0; i4 < TM; i4 += 4) {
+        const float4 a = *reinterpret_cast<const float4 *>(&sA[kk][ty * TM + i4]);
+        av[i4] = a.x; av[i4 + 1] = a.y; av[i4 + 2] = a.z; av[i4 + 3] = a.w;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 b = *reinterpret_cast<const float4 *>(&sB[kk][tx * 4 + 64 * h]);
+        bv[4 * h] = b.x; bv[4 * h + 1] = b.y; bv[4 * h + 2] = b.z; bv[4 * h + 3] = b.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  float *C = part + static_cast<long long>(blockIdx.x) * split_stride;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int u = ty * TM + i;
+    if (u >= U) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = tx * 4 + 64 * (j >> 2) + (j & 3);
+      if (n < Kin) C[static_cast<long long>(u) * Kin + n] = acc[i][j];
+    }
+  }
+}
+
+// dW slice of a NARROW layer (Kin <= 16: layer 0, whose input is the 9..13 decorated point features): the 64 x 64 tiles
+// of k_gemm waste 5/6 of their columns there (129 us per step for 0.4 GFLOP). Thread = (unit u, column group kg); it
+// keeps its <= 8 outputs in registers and walks the slice's rows in order (one fmaf per term: same partials as k_gemm).
+// Needs 256 % U == 0, U <= 128.
+__global__ void __launch_bounds__(256)
+k_dw_narrow(const float *__restrict__ DY, const float *__restrict__ X, const int U, const int Kin,
+            const int *__restrict__ num_rows, float *__restrict__ part, const long long split_stride) {
+  const int R = *num_rows;
+  const int nsplit = gridDim.x;
+  const int kper = ((R + nsplit - 1) / nsplit + 15) / 16 * 16;
+  const int k0 = min(R, static_cast<int>(blockIdx.x) * kper), k1 = min(R, k0 + kper);
+  const int u = threadIdx.x % U, kg = threadIdx.x / U, G = 256 / U;  // G >= 2 column groups
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 8
+  for (int r = k0; r < k1; ++r) {
+    const float dy = __ldg(DY + static_cast<size_t>(r) * U + u);
+    const float *x = X + static_cast<size_t>(r) * Kin;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kg + j * G;
+      if (k < Kin) acc[j] = fmaf(dy, __ldg(x + k), acc[j]);
+    }
+  }
+  float *C = part + static_cast<long long>(blockIdx.x) * split_stride;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = kg + j * G;
+    if (k < Kin) C[static_cast<long long>(u) * Kin + k] = acc[j];
+  }
+}
+
+// fixed-order reduction of split-K partials into dst (count elements): one WARP per element — lane j sums partials j,
+// j + 32, ... in that order, then a fixed xor-shuffle tree (deterministic; one thread per element walking all partials was
+// a chain of `nsplit` L2 round trips)
+__global__ void __launch_bounds__(256)
+k_reduce_splits(const float *__restrict__ part, const int nsplit, const long long stride, const int count,
+                float *__restrict__ dst) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= count) return;
   float s = 0.f;
-  for (int z = 0; z < nsplit; ++z) s += part[z * stride + i];
-  dst[i] = s;
+#pragma unroll 4
+  for (int z = lane; z < nsplit; z += 32) s += __ldg(part + z * stride + i);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0) dst[i] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -321,6 +482,40 @@ k_act_max(const float *__restrict__ Y, const int U, const float *__restrict__ sc
   }
 }
 
+// The same with four units per thread (U % 4 == 0): 16-byte accesses, four times the bytes in flight per thread — these
+// row-space passes are latency-bound, not bandwidth-bound (the scalar forms moved 1.8 - 2.5 TB/s). Same arithmetic per
+// element, so the results are bit-identical to the scalar kernels.
+// arg (optional): offset inside the pillar of the FIRST row attaining the max (torch.max routes the gradient there;
+// all-non-positive columns have m = 0 and route to row 0, whose ReLU mask then zeroes the gradient anyway).
+__global__ void __launch_bounds__(kThreads)
+k_act_max4(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ shift,
+           const int *__restrict__ row_off, const int *__restrict__ num_pillars, float *__restrict__ Mx,
+           uchar4 *__restrict__ arg) {
+  const int U4 = U >> 2;
+  const long long total = static_cast<long long>(*num_pillars) * U4;
+  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int p = static_cast<int>(i / U4), q = static_cast<int>(i - static_cast<long long>(p) * U4);
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + q);
+    const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift) + q);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar4 a = make_uchar4(0, 0, 0, 0);
+    const int r0 = row_off[p], r1 = row_off[p + 1];
+    for (int r = r0; r < r1; ++r) {
+      const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + static_cast<size_t>(r) * U) + q);
+      const float zx = fmaf(y.x, sc.x, sh.x), zy = fmaf(y.y, sc.y, sh.y), zz = fmaf(y.z, sc.z, sh.z),
+                  zw = fmaf(y.w, sc.w, sh.w);
+      const unsigned char t = static_cast<unsigned char>(r - r0);
+      if (zx > m.x) { m.x = zx; a.x = t; }
+      if (zy > m.y) { m.y = zy; a.y = t; }
+      if (zz > m.z) { m.z = zz; a.z = t; }
+      if (zw > m.w) { m.w = zw; a.w = t; }
+    }
+    reinterpret_cast<float4 *>(Mx)[i] = m;
+    if (arg) arg[i] = a;
+  }
+}
+
 // X_{l+1}[r] = [ relu(bn(Y_l[r])) || m_l[pillar(r)] ]   (R, 2U)
 __global__ void __launch_bounds__(kThreads)
 k_build_x(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ shift,
@@ -332,6 +527,31 @@ k_build_x(const float *__restrict__ Y, const int U, const float *__restrict__ sc
     const int r = static_cast<int>(i / (2 * U)), c = static_cast<int>(i - static_cast<long long>(r) * 2 * U);
     X[i] = (c < U) ? fmaxf(fmaf(Y[static_cast<size_t>(r) * U + c], scale[c], shift[c]), 0.f)
                    : Mx[static_cast<size_t>(row_pillar[r]) * U + (c - U)];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_build_x4(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ shift,
+           const float *__restrict__ Mx, const int *__restrict__ row_pillar, const int *__restrict__ num_rows,
+           float *__restrict__ X) {
+  const int U4 = U >> 2;
+  const long long total = static_cast<long long>(*num_rows) * 2 * U4;
+  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int r = static_cast<int>(i / (2 * U4)), q = static_cast<int>(i - static_cast<long long>(r) * 2 * U4);
+    float4 v;
+    if (q < U4) {
+      const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + static_cast<size_t>(r) * U) + q);
+      const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + q);
+      const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift) + q);
+      v.x = fmaxf(fmaf(y.x, sc.x, sh.x), 0.f);
+      v.y = fmaxf(fmaf(y.y, sc.y, sh.y), 0.f);
+      v.z = fmaxf(fmaf(y.z, sc.z, sh.z), 0.f);
+      v.w = fmaxf(fmaf(y.w, sc.w, sh.w), 0.f);
+    } else {
+      v = __ldg(reinterpret_cast<const float4 *>(Mx + static_cast<size_t>(row_pillar[r]) * U) + (q - U4));
+    }
+    reinterpret_cast<float4 *>(X)[i] = v;
   }
 }
 
@@ -473,6 +693,161 @@ k_dz(const float *__restrict__ Y, const int U, const float *__restrict__ scale, 
   }
 }
 
+// Four units per thread (U % 4 == 0): block = (U / 4, NL), 512 threads. Same per-element arithmetic and the same
+// first-row arg-max routing as k_dz; the fp64 lane sums are folded in lane order (fixed order, run-to-run identical).
+constexpr int kDz4Threads = 512;
+
+__global__ void __launch_bounds__(kDz4Threads)
+k_dz4(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ shift,
+      const float *__restrict__ mean, const float *__restrict__ var, const float eps, const float *__restrict__ Mx,
+      const float *__restrict__ dfeats, const float *__restrict__ dXnext, const int ldx,
+      const int *__restrict__ row_off, const int *__restrict__ num_pillars, float *__restrict__ DZ,
+      double *__restrict__ partials) {
+  extern __shared__ double s_sum[];  // [NL][2][U]
+  const int q = threadIdx.x, yl = threadIdx.y, NL = blockDim.y;
+  const int P = *num_pillars;
+  const int pillars_per_block = (P + gridDim.x - 1) / gridDim.x;
+  const int pa = min(P, blockIdx.x * pillars_per_block), pb = min(P, pa + pillars_per_block);
+  const float4 sc4 = __ldg(reinterpret_cast<const float4 *>(scale) + q);
+  const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(shift) + q);
+  const float4 mu4 = __ldg(reinterpret_cast<const float4 *>(mean) + q);
+  const float4 va4 = __ldg(reinterpret_cast<const float4 *>(var) + q);
+  const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+  const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+  const float rstd[4] = {rsqrtf(va4.x + eps), rsqrtf(va4.y + eps), rsqrtf(va4.z + eps), rsqrtf(va4.w + eps)};
+  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int p = pa + yl; p < pb; p += NL) {
+    const int r0 = row_off[p], r1 = row_off[p + 1];
+    float dm[4];
+    if (dXnext == nullptr) {
+      const float4 d = __ldg(reinterpret_cast<const float4 *>(dfeats + static_cast<size_t>(p) * U) + q);
+      dm[0] = d.x; dm[1] = d.y; dm[2] = d.z; dm[3] = d.w;
+    } else {
+      dm[0] = dm[1] = dm[2] = dm[3] = 0.f;
+      for (int r = r0; r < r1; ++r) {
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(dXnext + static_cast<size_t>(r) * ldx + U) + q);
+        dm[0] += d.x; dm[1] += d.y; dm[2] += d.z; dm[3] += d.w;
+      }
+    }
+    const float4 m4 = __ldg(reinterpret_cast<const float4 *>(Mx + static_cast<size_t>(p) * U) + q);
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w};
+    bool routed[4] = {false, false, false, false};
+    for (int r = r0; r < r1; ++r) {
+      const float4 y4 = __ldg(reinterpret_cast<const float4 *>(Y + static_cast<size_t>(r) * U) + q);
+      float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dXnext) a4 = __ldg(reinterpret_cast<const float4 *>(dXnext + static_cast<size_t>(r) * ldx) + q);
+      const float y[4] = {y4.x, y4.y, y4.z, y4.w};
+      float dA[4] = {a4.x, a4.y, a4.z, a4.w}, dz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float z = fmaf(y[j], sc[j], sh[j]);
+        const float a = fmaxf(z, 0.f);
+        if (!routed[j] && a == m[j]) {
+          dA[j] += dm[j];
+          routed[j] = true;
+        }
+        dz[j] = z > 0.f ? dA[j] : 0.f;
+        s1[j] += static_cast<double>(dz[j]);
+        s2[j] += static_cast<double>(dz[j]) * static_cast<double>((y[j] - mu[j]) * rstd[j]);
+      }
+      reinterpret_cast<float4 *>(DZ + static_cast<size_t>(r) * U)[q] = make_float4(dz[0], dz[1], dz[2], dz[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s_sum[(yl * 2 + 0) * U + 4 * q + j] = s1[j];
+    s_sum[(yl * 2 + 1) * U + 4 * q + j] = s2[j];
+  }
+  __syncthreads();
+  const int t = yl * blockDim.x + q;  // the first 2U threads fold one (sum, unit) column each
+  if (t < 2 * U) {
+    const int which = t / U, u = t - which * U;
+    double acc = 0.0;
+    for (int j = 0; j < NL; ++j) acc += s_sum[(j * 2 + which) * U + u];
+    partials[(static_cast<size_t>(blockIdx.x) * 2 + which) * U + u] = acc;
+  }
+}
+
+// k_dz4 split in two, so that no thread walks a pillar's rows twice behind dependent loads (k_dz4 stayed at the scalar
+// kernel's 174 us per layer of a 4-frame step: latency, not bytes):
+//   k_dm4      : dm[p][u] = sum over the pillar's rows of dXnext[r][U + u]  (gradient of the broadcast max; row order)
+//   k_dz_rows4 : one row per thread and iteration — dz = relu'(z) * (dXnext[r][u] + [r is the arg-max row] * dm[p][u]),
+//                BN sums in fp64 per thread, folded per block in lane order (fixed order, run-to-run identical).
+// The arg-max row comes from the forward (k_act_max4's `arg`), which is the first row attaining the max, as k_dz routes.
+__global__ void __launch_bounds__(kThreads)
+k_dm4(const float *__restrict__ dXnext, const int ldx, const int U, const int *__restrict__ row_off,
+      const int *__restrict__ num_pillars, float *__restrict__ DM) {
+  const int U4 = U >> 2;
+  const long long total = static_cast<long long>(*num_pillars) * U4;
+  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int p = static_cast<int>(i / U4), q = static_cast<int>(i - static_cast<long long>(p) * U4);
+    const int r0 = row_off[p], r1 = row_off[p + 1];
+    float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0; r < r1; ++r) {
+      const float4 d = __ldg(reinterpret_cast<const float4 *>(dXnext + static_cast<size_t>(r) * ldx + U) + q);
+      dm.x += d.x; dm.y += d.y; dm.z += d.z; dm.w += d.w;
+    }
+    reinterpret_cast<float4 *>(DM)[i] = dm;
+  }
+}
+
+__global__ void __launch_bounds__(kDz4Threads)
+k_dz_rows4(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ shift,
+           const float *__restrict__ mean, const float *__restrict__ var, const float eps,
+           const uchar4 *__restrict__ arg, const float *__restrict__ dm_src, const float *__restrict__ dXnext,
+           const int ldx, const int *__restrict__ row_off, const int *__restrict__ row_pillar,
+           const int *__restrict__ num_rows, float *__restrict__ DZ, double *__restrict__ partials) {
+  extern __shared__ double s_sum[];  // [NL][2][U]
+  const int q = threadIdx.x, yl = threadIdx.y, NL = blockDim.y, U4 = U >> 2;
+  const int R = *num_rows;
+  const int per = (R + gridDim.x - 1) / gridDim.x;
+  const int ra = min(R, static_cast<int>(blockIdx.x) * per), rb = min(R, ra + per);
+  const float4 sc4 = __ldg(reinterpret_cast<const float4 *>(scale) + q);
+  const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(shift) + q);
+  const float4 mu4 = __ldg(reinterpret_cast<const float4 *>(mean) + q);
+  const float4 va4 = __ldg(reinterpret_cast<const float4 *>(var) + q);
+  const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+  const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+  const float rstd[4] = {rsqrtf(va4.x + eps), rsqrtf(va4.y + eps), rsqrtf(va4.z + eps), rsqrtf(va4.w + eps)};
+  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+  for (int r = ra + yl; r < rb; r += NL) {
+    const int p = __ldg(row_pillar + r);
+    const int local = r - __ldg(row_off + p);
+    const float4 y4 = __ldg(reinterpret_cast<const float4 *>(Y + static_cast<size_t>(r) * U) + q);
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dXnext) a4 = __ldg(reinterpret_cast<const float4 *>(dXnext + static_cast<size_t>(r) * ldx) + q);
+    const float4 dm4 = __ldg(reinterpret_cast<const float4 *>(dm_src + static_cast<size_t>(p) * U) + q);
+    const uchar4 g4 = __ldg(arg + static_cast<size_t>(p) * U4 + q);
+    const float y[4] = {y4.x, y4.y, y4.z, y4.w}, dm[4] = {dm4.x, dm4.y, dm4.z, dm4.w};
+    const int g[4] = {g4.x, g4.y, g4.z, g4.w};
+    float dA[4] = {a4.x, a4.y, a4.z, a4.w}, dz[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float z = fmaf(y[j], sc[j], sh[j]);
+      if (local == g[j]) dA[j] += dm[j];
+      dz[j] = z > 0.f ? dA[j] : 0.f;
+      s1[j] += static_cast<double>(dz[j]);
+      s2[j] += static_cast<double>(dz[j]) * static_cast<double>((y[j] - mu[j]) * rstd[j]);
+    }
+    reinterpret_cast<float4 *>(DZ + static_cast<size_t>(r) * U)[q] = make_float4(dz[0], dz[1], dz[2], dz[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s_sum[(yl * 2 + 0) * U + 4 * q + j] = s1[j];
+    s_sum[(yl * 2 + 1) * U + 4 * q + j] = s2[j];
+  }
+  __syncthreads();
+  const int t = yl * blockDim.x + q;  // the first 2U threads fold one (sum, unit) column each
+  if (t < 2 * U) {
+    const int which = t / U, u = t - which * U;
+    double acc = 0.0;
+    for (int j = 0; j < NL; ++j) acc += s_sum[(j * 2 + which) * U + u];
+    partials[(static_cast<size_t>(blockIdx.x) * 2 + which) * U + u] = acc;
+  }
+}
+
 // One WARP per unit: lane j sums partials j, j+32, ... in that order, then a fixed xor-shuffle tree folds the 32 lane
 // sums — deterministic, and ~32x shorter than one thread walking all kDzBlocks partials (the serial form was the top
 // user kernel of a training step: ~99 us per launch).
@@ -514,10 +889,37 @@ k_dy(const float *__restrict__ Y, const int U, const float *__restrict__ scale, 
   }
 }
 
+__global__ void __launch_bounds__(kThreads)
+k_dy4(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ mean,
+      const float *__restrict__ var, const float eps, const float *__restrict__ c12, const float *__restrict__ row_w,
+      const int *__restrict__ num_rows, float *__restrict__ DZ) {
+  const int U4 = U >> 2;
+  const long long total = static_cast<long long>(*num_rows) * U4;
+  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int r = static_cast<int>(i / U4), q = static_cast<int>(i - static_cast<long long>(r) * U4);
+    const float4 y = __ldg(reinterpret_cast<const float4 *>(Y) + i);
+    float4 d = reinterpret_cast<const float4 *>(DZ)[i];
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + q);
+    const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean) + q);
+    const float4 va = __ldg(reinterpret_cast<const float4 *>(var) + q);
+    const float4 c1 = __ldg(reinterpret_cast<const float4 *>(c12) + q);
+    const float4 c2 = __ldg(reinterpret_cast<const float4 *>(c12 + U) + q);
+    const float w = row_w[r];
+    d.x = sc.x * (d.x - w * (c1.x + ((y.x - mu.x) * rsqrtf(va.x + eps)) * c2.x));
+    d.y = sc.y * (d.y - w * (c1.y + ((y.y - mu.y) * rsqrtf(va.y + eps)) * c2.y));
+    d.z = sc.z * (d.z - w * (c1.z + ((y.z - mu.z) * rsqrtf(va.z + eps)) * c2.z));
+    d.w = sc.w * (d.w - w * (c1.w + ((y.w - mu.w) * rsqrtf(va.w + eps)) * c2.w));
+    reinterpret_cast<float4 *>(DZ)[i] = d;
+  }
+}
+
 struct BwdWs {
-  int *row_off, *row_pillar, *num_rows;
-  float *row_w, *X, *DZ, *DX, *Mx[MBEV_MAX_LAYERS], *Y[MBEV_MAX_LAYERS], *c12, *wpart;
+  int *row_off, *row_pillar, *num_rows, *row_tot;
+  float *row_w, *X[MBEV_MAX_LAYERS], *DZ, *DX, *Mx[MBEV_MAX_LAYERS], *Y[MBEV_MAX_LAYERS], *c12, *wpart;  // X[l]: input rows of layer l, kept for dW_l
   float *stats;  // (L, 4, MBEV_MAX_UNITS): scale, shift, mean, var recomputed by this pass (train mode)
+  float *DM;                         // (cap, umax): gradient of a pillar's broadcast max (k_dm4)
+  uchar4 *Arg[MBEV_MAX_LAYERS];      // (cap, U_l / 4): arg-max row offset inside the pillar (k_act_max4)
   double *partials;
   float *img_fwd[MBEV_MAX_LAYERS], *img_dx[MBEV_MAX_LAYERS];  // hi / lo TF32 images of W_l and W_l^T (tensor-core GEMMs)
   size_t bytes;
@@ -536,9 +938,10 @@ BwdWs carve_bwd(void *ws, const MbevPfnParams *p, int64_t cap, int64_t rows_cap)
   }
   w.row_off = c.take<int>(static_cast<size_t>(cap) + 1);
   w.num_rows = c.take<int>(1);
+  w.row_tot = c.take<int>(static_cast<size_t>(cap) / kRowOffTile + 2);
   w.row_pillar = c.take<int>(static_cast<size_t>(rows_cap));
   w.row_w = c.take<float>(static_cast<size_t>(rows_cap));
-  w.X = c.take<float>(static_cast<size_t>(rows_cap) * inmax);
+  for (int l = 0; l < p->num_layers; ++l) w.X[l] = c.take<float>(static_cast<size_t>(rows_cap) * p->in_dim[l]);
   w.DZ = c.take<float>(static_cast<size_t>(rows_cap) * umax);
   w.DX = c.take<float>(static_cast<size_t>(rows_cap) * inmax);
   for (int l = 0; l < p->num_layers; ++l) {
@@ -546,6 +949,8 @@ BwdWs carve_bwd(void *ws, const MbevPfnParams *p, int64_t cap, int64_t rows_cap)
     w.Mx[l] = c.take<float>(static_cast<size_t>(cap) * p->units[l]);
   }
   w.c12 = c.take<float>(2 * umax);
+  w.DM = c.take<float>(static_cast<size_t>(cap) * umax);
+  for (int l = 0; l < p->num_layers; ++l) w.Arg[l] = c.take<uchar4>(static_cast<size_t>(cap) * ((p->units[l] + 3) / 4));
   w.wpart = c.take<float>(static_cast<size_t>(kSplitK) * umax * inmax);
   w.partials = c.take<double>(static_cast<size_t>(kDzBlocks) * 2 * umax);
   w.stats = c.take<float>(static_cast<size_t>(MBEV_MAX_LAYERS) * 4 * MBEV_MAX_UNITS);
@@ -574,11 +979,10 @@ bool tc_rows_ok(const MbevPfnParams *p, int K, int N) {
 int launch_gemm(const GemmK &g, int m_tiles_cap, int n, int splits, cudaStream_t stream) {
   if (splits == 1 && g.sAk == 1 && g.m_dev != nullptr && (g.sBn == 1 || g.sBk == 1)) {
     const int tiles = std::max(1, std::min((m_tiles_cap + 1) / 2, kNumSMs * 4));
-    if (n > 64) {
-      k_gemm_rows<128><<<dim3(tiles, (n + 127) / 128), 256, 0, stream>>>(g);
-    } else {
-      k_gemm_rows<64><<<dim3(tiles, (n + 63) / 64), 256, 0, stream>>>(g);
-    }
+    // 64-column tiles also for N = 128: the 128-column instantiation needs 165 registers = ONE 8-warp CTA per SM and ran
+    // at 29 TFLOP/s against 49 for two co-resident 64-column CTAs (ncu launch list of a training step); the A tile is
+    // read twice, from L2. Same k order per output element: bit-identical.
+    k_gemm_rows<64><<<dim3(tiles, (n + 63) / 64), 256, 0, stream>>>(g);
     MBEV_CHECK_LAUNCH();
     return MBEV_OK;
   }
@@ -588,16 +992,275 @@ int launch_gemm(const GemmK &g, int m_tiles_cap, int n, int splits, cudaStream_t
   return MBEV_OK;
 }
 
+
+// Statistics of the train-mode FORWARD in row space (mbev_pfn_forward_train_rows): gamma / beta are the layer's own
+// parameters; mean / biased variance over all P*T slots; the folded scale / shift go to the pass's own block (what the
+// backward reads) and to the caller's output blocks (running-statistics update, same contract as mbev_pfn_forward_train).
+__global__ void __launch_bounds__(256)
+k_row_stats_finalize_fwd(const double *__restrict__ partials, const int nblocks, const int U,
+                         const int *__restrict__ num_pillars, const int T, const float eps,
+                         const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ scale,
+                         float *__restrict__ shift, float *__restrict__ mean, float *__restrict__ var,
+                         float *__restrict__ scale_out, float *__restrict__ shift_out, float *__restrict__ mean_out,
+                         float *__restrict__ var_out) {
+  const int u = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (u >= U) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    s1 += partials[(static_cast<size_t>(b) * 2 + 0) * U + u];
+    s2 += partials[(static_cast<size_t>(b) * 2 + 1) * U + u];
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if (lane) return;
+  const double M = static_cast<double>(*num_pillars) * T;
+  const double mu = M > 0 ? s1 / M : 0.0;
+  double v = M > 0 ? s2 / M - mu * mu : 0.0;
+  if (v < 0) v = 0;
+  const double sc = static_cast<double>(gamma[u]) / sqrt(v + static_cast<double>(eps));
+  const float fsc = static_cast<float>(sc), fsh = static_cast<float>(static_cast<double>(beta[u]) - mu * sc);
+  const float fmu = static_cast<float>(mu), fv = static_cast<float>(v);
+  scale[u] = fsc; shift[u] = fsh; mean[u] = fmu; var[u] = fv;
+  scale_out[u] = fsc; shift_out[u] = fsh; mean_out[u] = fmu; var_out[u] = fv;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_copy_feats(const float4 *__restrict__ src, const int U4, const int *__restrict__ num_pillars, float4 *__restrict__ dst) {
+  const long long total = static_cast<long long>(*num_pillars) * U4;
+  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads)
+    dst[i] = src[i];
+}
+
+// One row-space pass = forward (keeps X_l, Y_l, m_l of every layer in the workspace) + backward over what it kept.
+// Three users: mbev_pfn_backward (recompute, then backward), mbev_pfn_forward_train_rows (the forward half as THE
+// train-mode forward of a training step) and mbev_pfn_backward_rows (the backward half over that workspace).
+struct RowsPass {
+  const MbevPfnParams *params;
+  BwdWs w;
+  DecoK dk;
+  int L, T, train;
+  int64_t rows_cap, cap;
+  float eps;
+  const int32_t *num_pillars_dev;
+  const float *scale_shift, *batch_stats;       // the fold / statistics of an earlier forward (recompute mode), else null
+  const float *const *gamma, *const *beta;      // forward mode: the layers' own BatchNorm parameters
+  float *scale_shift_out, *batch_stats_out, *feats_out;  // forward mode outputs
+  bool caller_aligned;
+  cudaStream_t stream;
+
+  const float *FSC(int l) const { return scale_shift + (2 * l) * MBEV_MAX_UNITS; }
+  const float *FSH(int l) const { return scale_shift + (2 * l + 1) * MBEV_MAX_UNITS; }
+  const float *FMEAN(int l) const { return batch_stats + (2 * l) * MBEV_MAX_UNITS; }
+  const float *FVAR(int l) const { return batch_stats + (2 * l + 1) * MBEV_MAX_UNITS; }
+  float *RST(int l, int which) const { return w.stats + (4 * l + which) * MBEV_MAX_UNITS; }
+  // train mode: scale / shift / mean / var come from THIS pass's rows (k_row_stats); eval mode: the forward's (running
+  // statistics, constants of the graph)
+  const float *SC(int l) const { return train ? RST(l, 0) : FSC(l); }
+  const float *SH(int l) const { return train ? RST(l, 1) : FSH(l); }
+  const float *MEAN(int l) const { return train ? RST(l, 2) : FMEAN(l); }
+  const float *VAR(int l) const { return train ? RST(l, 3) : FVAR(l); }
+  // four-units-per-thread element-wise kernels: U % 4 == 0 (<= 256 for k_dz4's fold) and 16-byte aligned caller tensors
+  bool vec4_ok(int U) const { return caller_aligned && U % 4 == 0 && U >= 4 && U <= 256 && kDz4Threads % (U / 4) == 0; }
+};
+
+constexpr int kEwBlocks = kNumSMs * 8;
+
+int rows_forward(const RowsPass &c, const float *rows, const int32_t *kept_idx, const int32_t *num_points,
+                 const int32_t *coors) {
+  const BwdWs &w = c.w;
+  cudaStream_t stream = c.stream;
+  const MbevPfnParams *params = c.params;
+  const int L = c.L, T = c.T;
+  const int m_tiles_cap = static_cast<int>(std::min<int64_t>((c.rows_cap + 63) / 64, 1 << 30));
+  {  // grid by the capacity (the pillar count lives on the device); one tile more so that row_off[P] always has an owner
+    const int tiles = static_cast<int>(c.cap / kRowOffTile + 1);
+    k_row_part<<<tiles, 256, 0, stream>>>(num_points, c.num_pillars_dev, T, w.row_tot);
+    MBEV_CHECK_LAUNCH();
+    k_row_offsets<<<tiles, 256, 0, stream>>>(num_points, c.num_pillars_dev, T, w.row_tot, w.row_off, w.num_rows);
+    MBEV_CHECK_LAUNCH();
+  }
+  k_decorate_rows<<<kEwBlocks, kThreads, 0, stream>>>(rows, kept_idx, num_points, coors, c.num_pillars_dev, w.row_off,
+                                                      c.dk, w.row_pillar, w.row_w, w.X[0]);
+  MBEV_CHECK_LAUNCH();
+  for (int l = 0; l < L; ++l) {
+    const int U = params->units[l], K = params->in_dim[l];
+    GemmK g{};  // Y_l (R,U) = X_l (R,K) * W_l^T ; W_l is (U,K) row-major => B(k,n) = W[n*K + k]
+    g.A = w.X[l]; g.sAm = K; g.sAk = 1;
+    g.B = params->weight[l]; g.sBk = 1; g.sBn = K;
+    g.C = w.Y[l]; g.ldc = U;
+    g.M = 0; g.N = U; g.K = K; g.m_dev = w.num_rows; g.k_dev = nullptr; g.split_stride = 0;
+    int st;
+    if (!c.train && tc_rows_ok(params, K, U)) {
+      k_pe_prep_weights<<<dim3((U * K + 255) / 256, 1), 256, 0, stream>>>(params->weight[l], U, K, 1, w.img_fwd[l], 0);
+      MBEV_CHECK_LAUNCH();
+      st = launch_rows_gemm(w.X[l], w.num_rows, c.rows_cap, K, U, w.img_fwd[l], w.Y[l], stream);
+    } else {
+      st = launch_gemm(g, m_tiles_cap, U, 1, stream);
+    }
+    if (st) return st;
+    if (c.train) {
+      const int nls = std::max(1, 1024 / U);
+      k_row_stats<<<kStatBlocks, dim3(U, nls), sizeof(double) * 2 * U * nls, stream>>>(w.Y[l], U, w.row_w, w.num_rows,
+                                                                                      w.partials);
+      MBEV_CHECK_LAUNCH();
+      if (c.gamma) {
+        k_row_stats_finalize_fwd<<<(U + 7) / 8, 256, 0, stream>>>(
+            w.partials, kStatBlocks, U, c.num_pillars_dev, T, c.eps, c.gamma[l], c.beta[l], c.RST(l, 0), c.RST(l, 1),
+            c.RST(l, 2), c.RST(l, 3), c.scale_shift_out + (2 * l) * MBEV_MAX_UNITS,
+            c.scale_shift_out + (2 * l + 1) * MBEV_MAX_UNITS, c.batch_stats_out + (2 * l) * MBEV_MAX_UNITS,
+            c.batch_stats_out + (2 * l + 1) * MBEV_MAX_UNITS);
+      } else {
+        k_row_stats_finalize<<<(U + 7) / 8, 256, 0, stream>>>(w.partials, kStatBlocks, U, c.num_pillars_dev, T, c.eps,
+                                                              c.FSC(l), c.FSH(l), c.FMEAN(l), c.FVAR(l), c.RST(l, 0),
+                                                              c.RST(l, 1), c.RST(l, 2), c.RST(l, 3));
+      }
+      MBEV_CHECK_LAUNCH();
+    }
+    const bool v4 = c.vec4_ok(U);
+    if (v4) k_act_max4<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.row_off, c.num_pillars_dev, w.Mx[l], w.Arg[l]);
+    else k_act_max<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.row_off, c.num_pillars_dev, w.Mx[l]);
+    MBEV_CHECK_LAUNCH();
+    if (l + 1 < L) {  // X_{l+1} = [a_l || m_l], kept until dW_{l+1} has been taken
+      if (v4) k_build_x4<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.Mx[l], w.row_pillar, w.num_rows, w.X[l + 1]);
+      else k_build_x<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.Mx[l], w.row_pillar, w.num_rows, w.X[l + 1]);
+      MBEV_CHECK_LAUNCH();
+    }
+  }
+  return MBEV_OK;
+}
+
+int rows_backward(const RowsPass &c, const float *dfeats, float *const *dweight, float *const *dgamma,
+                  float *const *dbeta) {
+  const BwdWs &w = c.w;
+  cudaStream_t stream = c.stream;
+  const MbevPfnParams *params = c.params;
+  const int L = c.L, T = c.T;
+  const int m_tiles_cap = static_cast<int>(std::min<int64_t>((c.rows_cap + 63) / 64, 1 << 30));
+  for (int l = L - 1; l >= 0; --l) {  // top layer first
+    const int U = params->units[l], K = params->in_dim[l];
+    const float *dxn = (l == L - 1) ? nullptr : w.DX;
+    const int ldx = (l == L - 1) ? 0 : params->in_dim[l + 1];
+    const bool v4 = c.vec4_ok(U) && (l != L - 1 || (reinterpret_cast<uintptr_t>(dfeats) & 15) == 0);
+    if (v4 && T < 255) {  // (the arg-max row offset is a byte: <= T rows + the virtual one)
+      const int nl = kDz4Threads / (U / 4);
+      if (dxn) {
+        k_dm4<<<kEwBlocks, kThreads, 0, stream>>>(dxn, ldx, U, w.row_off, c.num_pillars_dev, w.DM);
+        MBEV_CHECK_LAUNCH();
+      }
+      k_dz_rows4<<<kDzBlocks, dim3(U / 4, nl), sizeof(double) * 2 * U * nl, stream>>>(
+          w.Y[l], U, c.SC(l), c.SH(l), c.MEAN(l), c.VAR(l), c.eps, w.Arg[l], dxn ? w.DM : dfeats, dxn, ldx, w.row_off,
+          w.row_pillar, w.num_rows, w.DZ, w.partials);
+    } else if (v4) {
+      const int nl = kDz4Threads / (U / 4);
+      k_dz4<<<kDzBlocks, dim3(U / 4, nl), sizeof(double) * 2 * U * nl, stream>>>(
+          w.Y[l], U, c.SC(l), c.SH(l), c.MEAN(l), c.VAR(l), c.eps, w.Mx[l], dfeats, dxn, ldx, w.row_off,
+          c.num_pillars_dev, w.DZ, w.partials);
+    } else {
+      const int nl = std::max(1, kDzThreads / U);
+      k_dz<<<kDzBlocks, dim3(U, nl), sizeof(double) * 2 * U * nl, stream>>>(
+          w.Y[l], U, c.SC(l), c.SH(l), c.MEAN(l), c.VAR(l), c.eps, w.Mx[l], dfeats, dxn, ldx, w.row_off,
+          c.num_pillars_dev, w.DZ, w.partials);
+    }
+    MBEV_CHECK_LAUNCH();
+    k_bn_finalize<<<(U + 7) / 8, 256, 0, stream>>>(w.partials, kDzBlocks, U, c.num_pillars_dev, T, c.train, dgamma[l],
+                                                       dbeta[l], w.c12);
+    MBEV_CHECK_LAUNCH();
+    if (v4) k_dy4<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.MEAN(l), c.VAR(l), c.eps, w.c12, w.row_w, w.num_rows, w.DZ);
+    else k_dy<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.MEAN(l), c.VAR(l), c.eps, w.c12, w.row_w, w.num_rows, w.DZ);
+    MBEV_CHECK_LAUNCH();
+    {  // dW_l (U,K) = dY^T (U,R) * X_l (R,K): split over row slices, fixed-order reduce
+      const long long split_stride = static_cast<long long>(U) * K;
+      int nsplit = kSplitK;
+      if (U % 4 == 0 && K % 4 == 0 && U <= 128 && K <= 128 && K >= 32) {  // whole output in one CTA tile
+        if (U > 64) k_gemm_dw<128><<<kSplitK, 256, 0, stream>>>(w.DZ, w.X[l], U, K, w.num_rows, w.wpart, split_stride);
+        else k_gemm_dw<64><<<kSplitK, 256, 0, stream>>>(w.DZ, w.X[l], U, K, w.num_rows, w.wpart, split_stride);
+        MBEV_CHECK_LAUNCH();
+      } else if (K <= 16 && U <= 128 && 256 % U == 0) {
+        // a thread walks its slice's rows one after the other behind their loads: many short slices (as many as the
+        // partial-sum buffer holds, up to 16 CTAs per SM), not kSplitK long ones (measured: 321 us with 296 slices)
+        int umax = 0, inmax = 0;
+        for (int j = 0; j < L; ++j) {
+          umax = std::max(umax, params->units[j]);
+          inmax = std::max(inmax, params->in_dim[j]);
+        }
+        nsplit = static_cast<int>(std::min<long long>(kNumSMs * 16, static_cast<long long>(kSplitK) * umax * inmax / split_stride));
+        k_dw_narrow<<<nsplit, 256, 0, stream>>>(w.DZ, w.X[l], U, K, w.num_rows, w.wpart, split_stride);
+        MBEV_CHECK_LAUNCH();
+      } else {
+        GemmK g{};
+        g.A = w.DZ; g.sAm = 1; g.sAk = U;   // A(m=u, k=r) = DY[r*U + u]
+        g.B = w.X[l]; g.sBk = K; g.sBn = 1;  // B(k=r, n) = X_l[r*K + n]
+        g.C = w.wpart; g.ldc = K;
+        g.M = U; g.N = K; g.K = 0; g.m_dev = nullptr; g.k_dev = w.num_rows;
+        g.split_stride = split_stride;
+        int st = launch_gemm(g, (U + 63) / 64, K, kSplitK, stream);
+        if (st) return st;
+      }
+      k_reduce_splits<<<(U * K + 7) / 8, 256, 0, stream>>>(w.wpart, nsplit, split_stride, U * K, dweight[l]);
+      MBEV_CHECK_LAUNCH();
+    }
+    if (l > 0) {  // dX (R,K) = dY (R,U) * W_l (U,K)
+      GemmK g{};
+      g.A = w.DZ; g.sAm = U; g.sAk = 1;
+      g.B = params->weight[l]; g.sBk = K; g.sBn = 1;
+      g.C = w.DX; g.ldc = K;
+      g.M = 0; g.N = K; g.K = U; g.m_dev = w.num_rows; g.k_dev = nullptr; g.split_stride = 0;
+      int st;
+      if (tc_rows_ok(params, U, K)) {  // B = W_l^T: (N = in, K = units)
+        k_pe_prep_weights<<<dim3((U * K + 255) / 256, 1), 256, 0, stream>>>(params->weight[l], K, U, 1, w.img_dx[l], 1);
+        MBEV_CHECK_LAUNCH();
+        st = launch_rows_gemm(w.DZ, w.num_rows, c.rows_cap, U, K, w.img_dx[l], w.DX, stream);
+      } else {
+        st = launch_gemm(g, m_tiles_cap, K, 1, stream);
+      }
+      if (st) return st;
+    }
+  }
+  return MBEV_OK;
+}
+
+// R = sum_p (n_p + [n_p < T]) is only known on the device. Its host-side bound sizes the row buffers:
+// the caller may pass a tight `rows_capacity_hint` (e.g. points + pillar capacity); otherwise P_cap * (T + 1).
+int64_t rows_capacity(int64_t pillar_capacity, int T, int64_t hint) {
+  return hint > 0 ? hint : pillar_capacity * (static_cast<int64_t>(T) + 1);
+}
+
+int check_layers(const MbevPfnParams *params, int C, int T) {
+  if (!params) return MBEV_ERR_BAD_ARG;
+  const int L = params->num_layers;
+  if (L < 1 || L > MBEV_MAX_LAYERS || C < 3 || C > MBEV_MAX_POINT_DIM || T < 1) return MBEV_ERR_BAD_ARG;
+  for (int l = 0; l < L; ++l) {
+    if (!params->weight[l]) return MBEV_ERR_BAD_ARG;
+    if (params->units[l] > MBEV_MAX_UNITS || params->units[l] < 1) return MBEV_ERR_UNSUPPORTED;
+    if (params->in_dim[l] != (l ? 2 * params->units[l - 1] : params->in_dim[0])) return MBEV_ERR_BAD_ARG;
+  }
+  return MBEV_OK;
+}
+
+int make_deco(const MbevPfnParams *params, int C, int T, DecoK *out) {
+  DecoK dk;
+  dk.C = C; dk.T = T;
+  dk.cluster = params->with_cluster_center != 0;
+  dk.vcenter = params->with_voxel_center != 0;
+  dk.dist = params->with_distance != 0;
+  dk.legacy = params->legacy != 0;
+  dk.vcd = params->voxel_center_dims;
+  dk.D0 = C + (dk.cluster ? 3 : 0) + (dk.vcenter ? dk.vcd : 0) + (dk.dist ? 1 : 0);
+  if (dk.D0 != params->in_dim[0]) return MBEV_ERR_BAD_ARG;
+  dk.vx = params->vx; dk.vy = params->vy; dk.vz = params->vz;
+  dk.xo = params->x_offset; dk.yo = params->y_offset; dk.zo = params->z_offset;
+  *out = dk;
+  return MBEV_OK;
+}
+
 }  // namespace
 }  // namespace mbev
 
 using namespace mbev;
-
-// R = sum_p (n_p + [n_p < T]) is only known on the device. Its host-side bound sizes the row buffers:
-// the caller may pass a tight `rows_capacity_hint` (e.g. points + pillar capacity); otherwise P_cap * (T + 1).
-static int64_t rows_capacity(int64_t pillar_capacity, int T, int64_t hint) {
-  return hint > 0 ? hint : pillar_capacity * (static_cast<int64_t>(T) + 1);
-}
 
 extern "C" int mbev_pfn_backward_workspace_bytes(const MbevPfnParams *params, int T, int64_t pillar_capacity,
                                                  int64_t rows_capacity_hint, size_t *bytes) {
@@ -617,14 +1280,12 @@ extern "C" int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_i
   if (!params || !num_points || !coors || !num_pillars_dev || !scale_shift || !batch_stats || !dfeats || !dweight ||
       !dgamma || !dbeta || !workspace)
     return MBEV_ERR_BAD_ARG;
+  int st = check_layers(params, C, T);
+  if (st) return st;
   const int L = params->num_layers;
-  if (L < 1 || L > MBEV_MAX_LAYERS || C < 3 || C > MBEV_MAX_POINT_DIM || T < 1) return MBEV_ERR_BAD_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  for (int l = 0; l < L; ++l) {
-    if (!dweight[l] || !dgamma[l] || !dbeta[l] || !params->weight[l]) return MBEV_ERR_BAD_ARG;
-    if (params->units[l] > MBEV_MAX_UNITS || params->units[l] < 1) return MBEV_ERR_UNSUPPORTED;
-    if (params->in_dim[l] != (l ? 2 * params->units[l - 1] : params->in_dim[0])) return MBEV_ERR_BAD_ARG;
-  }
+  for (int l = 0; l < L; ++l)
+    if (!dweight[l] || !dgamma[l] || !dbeta[l]) return MBEV_ERR_BAD_ARG;
   if (pillar_capacity <= 0) {
     for (int l = 0; l < L; ++l) {
       MBEV_CUDA(cudaMemsetAsync(dweight[l], 0, sizeof(float) * params->units[l] * params->in_dim[l], stream));
@@ -634,126 +1295,95 @@ extern "C" int mbev_pfn_backward(const float *rows, int C, const int32_t *kept_i
     return MBEV_OK;
   }
   if (!rows) return MBEV_ERR_BAD_ARG;
-  const int64_t rows_cap = rows_capacity(pillar_capacity, T, rows_capacity_hint);
-  if (rows_cap * MBEV_MAX_UNITS > 0x7fffffffLL * 4) return MBEV_ERR_UNSUPPORTED;
-  const BwdWs w = carve_bwd(workspace, params, pillar_capacity, rows_cap);
-  if (workspace_bytes < w.bytes) return MBEV_ERR_WORKSPACE;
+  RowsPass c{};
+  c.rows_cap = rows_capacity(pillar_capacity, T, rows_capacity_hint);
+  c.cap = pillar_capacity;
+  if (c.rows_cap * MBEV_MAX_UNITS > 0x7fffffffLL * 4) return MBEV_ERR_UNSUPPORTED;
+  c.w = carve_bwd(workspace, params, pillar_capacity, c.rows_cap);
+  if (workspace_bytes < c.w.bytes) return MBEV_ERR_WORKSPACE;
+  st = make_deco(params, C, T, &c.dk);
+  if (st) return st;
+  c.params = params; c.L = L; c.T = T; c.train = train; c.eps = eps; c.num_pillars_dev = num_pillars_dev;
+  c.scale_shift = scale_shift; c.batch_stats = batch_stats; c.stream = stream;
+  c.caller_aligned = ((reinterpret_cast<uintptr_t>(scale_shift) | reinterpret_cast<uintptr_t>(batch_stats)) & 15) == 0;
+  st = rows_forward(c, rows, kept_idx, num_points, coors);  // recompute: keeps X_l, Y_l and m_l of every layer
+  if (st) return st;
+  return rows_backward(c, dfeats, dweight, dgamma, dbeta);
+}
 
-  DecoK dk;
-  dk.C = C; dk.T = T;
-  dk.cluster = params->with_cluster_center != 0;
-  dk.vcenter = params->with_voxel_center != 0;
-  dk.dist = params->with_distance != 0;
-  dk.legacy = params->legacy != 0;
-  dk.vcd = params->voxel_center_dims;
-  dk.D0 = C + (dk.cluster ? 3 : 0) + (dk.vcenter ? dk.vcd : 0) + (dk.dist ? 1 : 0);
-  if (dk.D0 != params->in_dim[0]) return MBEV_ERR_BAD_ARG;
-  dk.vx = params->vx; dk.vy = params->vy; dk.vz = params->vz;
-  dk.xo = params->x_offset; dk.yo = params->y_offset; dk.zo = params->z_offset;
-
-  const int ew_blocks = kNumSMs * 8;
-  const int m_tiles_cap = static_cast<int>(std::min<int64_t>((rows_cap + 63) / 64, 1 << 30));
-  // train mode: scale / shift / mean / var come from THIS pass's rows (k_row_stats); eval mode: the forward's (running
-  // statistics, constants of the graph)
-  auto FSC = [&](int l) { return scale_shift + (2 * l) * MBEV_MAX_UNITS; };
-  auto FSH = [&](int l) { return scale_shift + (2 * l + 1) * MBEV_MAX_UNITS; };
-  auto FMEAN = [&](int l) { return batch_stats + (2 * l) * MBEV_MAX_UNITS; };
-  auto FVAR = [&](int l) { return batch_stats + (2 * l + 1) * MBEV_MAX_UNITS; };
-  auto RST = [&](int l, int which) { return w.stats + (4 * l + which) * MBEV_MAX_UNITS; };
-  auto SC = [&](int l) -> const float * { return train ? RST(l, 0) : FSC(l); };
-  auto SH = [&](int l) -> const float * { return train ? RST(l, 1) : FSH(l); };
-  auto MEAN = [&](int l) -> const float * { return train ? RST(l, 2) : FMEAN(l); };
-  auto VAR = [&](int l) -> const float * { return train ? RST(l, 3) : FVAR(l); };
-
-  // ---- row space + forward recompute (keeps Y_l and m_l of every layer) --------------------------------
-  k_row_offsets<<<1, 1024, 0, stream>>>(num_points, num_pillars_dev, T, w.row_off, w.num_rows);
-  MBEV_CHECK_LAUNCH();
-  k_decorate_rows<<<ew_blocks, kThreads, 0, stream>>>(rows, kept_idx, num_points, coors, num_pillars_dev, w.row_off, dk,
-                                                      w.row_pillar, w.row_w, w.X);
-  MBEV_CHECK_LAUNCH();
-  for (int l = 0; l < L; ++l) {
-    const int U = params->units[l], K = params->in_dim[l];
-    GemmK g{};  // Y_l (R,U) = X_l (R,K) * W_l^T ; W_l is (U,K) row-major => B(k,n) = W[n*K + k]
-    g.A = w.X; g.sAm = K; g.sAk = 1;
-    g.B = params->weight[l]; g.sBk = 1; g.sBn = K;
-    g.C = w.Y[l]; g.ldc = U;
-    g.M = 0; g.N = U; g.K = K; g.m_dev = w.num_rows; g.k_dev = nullptr; g.split_stride = 0;
-    int st;
-    if (!train && tc_rows_ok(params, K, U)) {
-      k_pe_prep_weights<<<dim3((U * K + 255) / 256, 1), 256, 0, stream>>>(params->weight[l], U, K, 1, w.img_fwd[l], 0);
-      MBEV_CHECK_LAUNCH();
-      st = launch_rows_gemm(w.X, w.num_rows, rows_cap, K, U, w.img_fwd[l], w.Y[l], stream);
-    } else {
-      st = launch_gemm(g, m_tiles_cap, U, 1, stream);
-    }
-    if (st) return st;
-    if (train) {
-      const int nls = std::max(1, 1024 / U);
-      k_row_stats<<<kStatBlocks, dim3(U, nls), sizeof(double) * 2 * U * nls, stream>>>(w.Y[l], U, w.row_w, w.num_rows,
-                                                                                      w.partials);
-      MBEV_CHECK_LAUNCH();
-      k_row_stats_finalize<<<(U + 7) / 8, 256, 0, stream>>>(w.partials, kStatBlocks, U, num_pillars_dev, T, eps, FSC(l),
-                                                            FSH(l), FMEAN(l), FVAR(l), RST(l, 0), RST(l, 1), RST(l, 2),
-                                                            RST(l, 3));
-      MBEV_CHECK_LAUNCH();
-    }
-    k_act_max<<<ew_blocks, kThreads, 0, stream>>>(w.Y[l], U, SC(l), SH(l), w.row_off, num_pillars_dev, w.Mx[l]);
+// The train-mode forward of a TRAINING STEP: the row-space forward above run once, as the forward — statistics from the
+// layers' own gamma / beta, features out — with every activation left in the workspace, which the caller keeps until
+// mbev_pfn_backward_rows. The step then computes the PFN forward once instead of three times (tensor-core forward with its
+// L statistics passes + K2''s recompute), and forward and backward see the very same rows (fp32 FMA products).
+extern "C" int mbev_pfn_forward_train_rows(const float *rows, int C, const int32_t *kept_idx, const int32_t *num_points,
+                                           const int32_t *coors, const int32_t *num_pillars_dev, int64_t pillar_capacity,
+                                           int T, int64_t rows_capacity_hint, const MbevPfnParams *params,
+                                           const float *const *gamma, const float *const *beta, float eps, float *feats,
+                                           float *scale_shift_out, float *batch_stats_out, void *workspace,
+                                           size_t workspace_bytes, void *stream_) {
+  if (!params || !num_points || !coors || !num_pillars_dev || !gamma || !beta || !feats || !scale_shift_out ||
+      !batch_stats_out || !workspace)
+    return MBEV_ERR_BAD_ARG;
+  int st = check_layers(params, C, T);
+  if (st) return st;
+  const int L = params->num_layers;
+  for (int l = 0; l < L; ++l)
+    if (!gamma[l] || !beta[l]) return MBEV_ERR_BAD_ARG;
+  if (pillar_capacity <= 0) return MBEV_OK;
+  if (!rows) return MBEV_ERR_BAD_ARG;
+  RowsPass c{};
+  c.rows_cap = rows_capacity(pillar_capacity, T, rows_capacity_hint);
+  c.cap = pillar_capacity;
+  if (c.rows_cap * MBEV_MAX_UNITS > 0x7fffffffLL * 4) return MBEV_ERR_UNSUPPORTED;
+  c.w = carve_bwd(workspace, params, pillar_capacity, c.rows_cap);
+  if (workspace_bytes < c.w.bytes) return MBEV_ERR_WORKSPACE;
+  st = make_deco(params, C, T, &c.dk);
+  if (st) return st;
+  c.params = params; c.L = L; c.T = T; c.train = 1; c.eps = eps; c.num_pillars_dev = num_pillars_dev;
+  c.gamma = gamma; c.beta = beta; c.scale_shift_out = scale_shift_out; c.batch_stats_out = batch_stats_out;
+  c.stream = static_cast<cudaStream_t>(stream_);
+  c.caller_aligned = true;  // statistics live in the workspace
+  st = rows_forward(c, rows, kept_idx, num_points, coors);
+  if (st) return st;
+  const int U = params->units[L - 1];
+  if (U % 4 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
+    k_copy_feats<<<kEwBlocks, kThreads, 0, c.stream>>>(reinterpret_cast<const float4 *>(c.w.Mx[L - 1]), U / 4,
+                                                       num_pillars_dev, reinterpret_cast<float4 *>(feats));
     MBEV_CHECK_LAUNCH();
-    if (l + 1 < L) {
-      k_build_x<<<ew_blocks, kThreads, 0, stream>>>(w.Y[l], U, SC(l), SH(l), w.Mx[l], w.row_pillar, w.num_rows, w.X);
-      MBEV_CHECK_LAUNCH();
-    }
-  }
-  // ---- backward, top layer first ------------------------------------------------------------------------
-  for (int l = L - 1; l >= 0; --l) {
-    const int U = params->units[l], K = params->in_dim[l];
-    const int nl = std::max(1, kDzThreads / U);
-    k_dz<<<kDzBlocks, dim3(U, nl), sizeof(double) * 2 * U * nl, stream>>>(
-        w.Y[l], U, SC(l), SH(l), MEAN(l), VAR(l), eps, w.Mx[l], dfeats, (l == L - 1) ? nullptr : w.DX,
-        (l == L - 1) ? 0 : params->in_dim[l + 1], w.row_off, num_pillars_dev, w.DZ, w.partials);
-    MBEV_CHECK_LAUNCH();
-    k_bn_finalize<<<(U + 7) / 8, 256, 0, stream>>>(w.partials, kDzBlocks, U, num_pillars_dev, T, train, dgamma[l],
-                                                       dbeta[l], w.c12);
-    MBEV_CHECK_LAUNCH();
-    k_dy<<<ew_blocks, kThreads, 0, stream>>>(w.Y[l], U, SC(l), MEAN(l), VAR(l), eps, w.c12, w.row_w, w.num_rows, w.DZ);
-    MBEV_CHECK_LAUNCH();
-    // X_l: layer 0 = decorated rows, else [a_{l-1} || m_{l-1}]
-    if (l == 0) {
-      k_decorate_rows<<<ew_blocks, kThreads, 0, stream>>>(rows, kept_idx, num_points, coors, num_pillars_dev, w.row_off,
-                                                          dk, w.row_pillar, w.row_w, w.X);
-    } else {
-      k_build_x<<<ew_blocks, kThreads, 0, stream>>>(w.Y[l - 1], params->units[l - 1], SC(l - 1), SH(l - 1), w.Mx[l - 1],
-                                                    w.row_pillar, w.num_rows, w.X);
-    }
-    MBEV_CHECK_LAUNCH();
-    {  // dW_l (U,K) = dY^T (U,R) * X_l (R,K): split-K over rows, fixed-order reduce
-      GemmK g{};
-      g.A = w.DZ; g.sAm = 1; g.sAk = U;   // A(m=u, k=r) = DY[r*U + u]
-      g.B = w.X; g.sBk = K; g.sBn = 1;    // B(k=r, n) = X[r*K + n]
-      g.C = w.wpart; g.ldc = K;
-      g.M = U; g.N = K; g.K = 0; g.m_dev = nullptr; g.k_dev = w.num_rows;
-      g.split_stride = static_cast<long long>(U) * K;
-      int st = launch_gemm(g, (U + 63) / 64, K, kSplitK, stream);
-      if (st) return st;
-      k_reduce_splits<<<(U * K + 255) / 256, 256, 0, stream>>>(w.wpart, kSplitK, g.split_stride, U * K, dweight[l]);
-      MBEV_CHECK_LAUNCH();
-    }
-    if (l > 0) {  // dX (R,K) = dY (R,U) * W_l (U,K)
-      GemmK g{};
-      g.A = w.DZ; g.sAm = U; g.sAk = 1;
-      g.B = params->weight[l]; g.sBk = K; g.sBn = 1;
-      g.C = w.DX; g.ldc = K;
-      g.M = 0; g.N = K; g.K = U; g.m_dev = w.num_rows; g.k_dev = nullptr; g.split_stride = 0;
-      int st;
-      if (tc_rows_ok(params, U, K)) {  // B = W_l^T: (N = in, K = units)
-        k_pe_prep_weights<<<dim3((U * K + 255) / 256, 1), 256, 0, stream>>>(params->weight[l], K, U, 1, w.img_dx[l], 1);
-        MBEV_CHECK_LAUNCH();
-        st = launch_rows_gemm(w.DZ, w.num_rows, rows_cap, U, K, w.img_dx[l], w.DX, stream);
-      } else {
-        st = launch_gemm(g, m_tiles_cap, K, 1, stream);
-      }
-      if (st) return st;
-    }
+  } else {
+    MBEV_CUDA(cudaMemcpyAsync(feats, c.w.Mx[L - 1], sizeof(float) * static_cast<size_t>(pillar_capacity) * U,
+                              cudaMemcpyDeviceToDevice, c.stream));
   }
   return MBEV_OK;
+}
+
+extern "C" int mbev_pfn_backward_rows(const int32_t *num_pillars_dev, int64_t pillar_capacity, int C, int T,
+                                      int64_t rows_capacity_hint, const MbevPfnParams *params, float eps,
+                                      const float *dfeats, float *const *dweight, float *const *dgamma,
+                                      float *const *dbeta, void *workspace, size_t workspace_bytes, void *stream_) {
+  if (!params || !num_pillars_dev || !dfeats || !dweight || !dgamma || !dbeta || !workspace) return MBEV_ERR_BAD_ARG;
+  int st = check_layers(params, C, T);
+  if (st) return st;
+  const int L = params->num_layers;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  for (int l = 0; l < L; ++l)
+    if (!dweight[l] || !dgamma[l] || !dbeta[l]) return MBEV_ERR_BAD_ARG;
+  if (pillar_capacity <= 0) {
+    for (int l = 0; l < L; ++l) {
+      MBEV_CUDA(cudaMemsetAsync(dweight[l], 0, sizeof(float) * params->units[l] * params->in_dim[l], stream));
+      MBEV_CUDA(cudaMemsetAsync(dgamma[l], 0, sizeof(float) * params->units[l], stream));
+      MBEV_CUDA(cudaMemsetAsync(dbeta[l], 0, sizeof(float) * params->units[l], stream));
+    }
+    return MBEV_OK;
+  }
+  RowsPass c{};
+  c.rows_cap = rows_capacity(pillar_capacity, T, rows_capacity_hint);
+  c.cap = pillar_capacity;
+  if (c.rows_cap * MBEV_MAX_UNITS > 0x7fffffffLL * 4) return MBEV_ERR_UNSUPPORTED;
+  c.w = carve_bwd(workspace, params, pillar_capacity, c.rows_cap);  // the SAME carve as the forward's: same arguments
+  if (workspace_bytes < c.w.bytes) return MBEV_ERR_WORKSPACE;
+  c.params = params; c.L = L; c.T = T; c.train = 1; c.eps = eps; c.num_pillars_dev = num_pillars_dev;
+  c.stream = stream;
+  c.caller_aligned = true;
+  return rows_backward(c, dfeats, dweight, dgamma, dbeta);
 }

@@ -280,6 +280,56 @@ def pfn_backward(rows, kept_idx, num_points, coors, num_pillars_dev, capacity, T
     return dws, dgs, dbs
 
 
+def pfn_forward_train_rows(rows, kept_idx, num_points, coors, num_pillars_dev, capacity, T, cfg: PfnConfig,
+                           weights, gammas, betas, rows_capacity: int = 0):
+    """Train-mode forward of a training step in compact row space (mbev_pfn_forward_train_rows): returns
+    (feats, scale_shift, batch_stats, saved) — `saved` is the workspace holding every layer's rows, which
+    `pfn_backward_rows` consumes instead of recomputing the forward."""
+    lib = _lib.load()
+    _need_cuda(rows, "features")
+    dev = rows.device
+    L = len(cfg.units)
+    weights = [_f32c(w) for w in weights]
+    gammas = [_f32c(g) for g in gammas]
+    betas = [_f32c(b) for b in betas]
+    params = _pfn_struct(cfg, weights, None, None)
+    nbytes = ctypes.c_size_t()
+    check(lib.mbev_pfn_backward_workspace_bytes(ctypes.byref(params), T, capacity, rows_capacity,
+                                                ctypes.byref(nbytes)), "pfn_backward_workspace_bytes")
+    saved = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
+    feats = torch.empty((capacity, cfg.units[-1]), dtype=torch.float32, device=dev)
+    scale_shift = torch.zeros((L, 2, MAX_UNITS), dtype=torch.float32, device=dev)
+    batch_stats = torch.zeros((L, 2, MAX_UNITS), dtype=torch.float32, device=dev)
+    g_arr, b_arr = ptr_array(gammas), ptr_array(betas)
+    with torch.cuda.device(dev):
+        check(lib.mbev_pfn_forward_train_rows(ptr(rows), cfg.in_channels, ptr(kept_idx), ptr(num_points), ptr(coors),
+                                              ptr(num_pillars_dev), capacity, T, rows_capacity, ctypes.byref(params),
+                                              ctypes.byref(g_arr), ctypes.byref(b_arr), cfg.eps, ptr(feats),
+                                              ptr(scale_shift), ptr(batch_stats), ptr(saved), saved.numel(),
+                                              _stream()), "pfn_forward_train_rows")
+    return feats, scale_shift, batch_stats, saved
+
+
+def pfn_backward_rows(saved, num_pillars_dev, capacity, T, cfg: PfnConfig, weights, dfeats, rows_capacity: int = 0):
+    """Parameter gradients from the rows `pfn_forward_train_rows` kept (same capacity / T / rows_capacity / cfg)."""
+    lib = _lib.load()
+    dev = saved.device
+    L = len(cfg.units)
+    weights = [_f32c(w) for w in weights]
+    params = _pfn_struct(cfg, weights, None, None)
+    dws = [torch.empty((cfg.units[l], cfg.in_dims[l]), dtype=torch.float32, device=dev) for l in range(L)]
+    dgs = [torch.empty((cfg.units[l],), dtype=torch.float32, device=dev) for l in range(L)]
+    dbs = [torch.empty((cfg.units[l],), dtype=torch.float32, device=dev) for l in range(L)]
+    dfeats = _f32c(dfeats)
+    dw_arr, dg_arr, db_arr = ptr_array(dws), ptr_array(dgs), ptr_array(dbs)
+    with torch.cuda.device(dev):
+        check(lib.mbev_pfn_backward_rows(ptr(num_pillars_dev), capacity, cfg.in_channels, T, rows_capacity,
+                                         ctypes.byref(params), cfg.eps, ptr(dfeats), ctypes.byref(dw_arr),
+                                         ctypes.byref(dg_arr), ctypes.byref(db_arr), ptr(saved), saved.numel(),
+                                         _stream()), "pfn_backward_rows")
+    return dws, dgs, dbs
+
+
 # ------------------------------------------------------------------------------------------------------
 # scatter
 # ------------------------------------------------------------------------------------------------------

@@ -52,7 +52,16 @@ class _PfnFunction(torch.autograd.Function):
         if not isinstance(ctx, _NullCtx) and cfg.gemm_path == 0 and not net.autograd_tensor_cores:
             # opt-out: forward on the fp32 FMA pipe, bit-consistent with what K2' recomputes (round 1's default).
             cfg.gemm_path = 1
-        if training:
+        # compact row bound without a host sync: every real row is a stored point (<= rows.shape[0] of them) and
+        # there is at most one virtual row per pillar
+        rows_capacity = int(min(capacity * (T + 1), rows.shape[0] + capacity))
+        ctx.saved_rows = None
+        if training and not isinstance(ctx, _NullCtx) and net.train_rows:
+            # a training step: the forward runs ONCE, in row space, and keeps its rows for the backward
+            feats, scale_shift, batch_stats, ctx.saved_rows = F_.pfn_forward_train_rows(
+                rows, kept_idx, num_points, coors, npil_dev, capacity, T, cfg, weights, gammas, betas, rows_capacity)
+            net._update_running_stats(batch_stats, npil_dev, T)
+        elif training:
             feats, scale_shift, batch_stats = F_.pfn_forward_train(rows, kept_idx, num_points, coors, npil_dev,
                                                                   capacity, T, cfg, weights, gammas, betas)
             net._update_running_stats(batch_stats, npil_dev, T)
@@ -64,9 +73,7 @@ class _PfnFunction(torch.autograd.Function):
         ctx.save_for_backward(rows, kept_idx if kept_idx is not None else torch.empty(0, device=rows.device),
                               num_points, coors, npil_dev, scale_shift, batch_stats, *weights)
         ctx.has_kept = kept_idx is not None
-        # compact row bound without a host sync: every real row is a stored point (<= rows.shape[0] of them) and
-        # there is at most one virtual row per pillar
-        ctx.rows_capacity = int(min(capacity * (T + 1), rows.shape[0] + capacity))
+        ctx.rows_capacity = rows_capacity
         return feats
 
     @staticmethod
@@ -75,6 +82,11 @@ class _PfnFunction(torch.autograd.Function):
         rows, kept_idx, num_points, coors, npil_dev, scale_shift, batch_stats = saved[:7]
         L = len(ctx.cfg.units)
         weights = saved[7:7 + L]
+        if ctx.saved_rows is not None:
+            dws, dgs, dbs = F_.pfn_backward_rows(ctx.saved_rows, npil_dev, ctx.capacity, ctx.T, ctx.cfg, weights, dfeats,
+                                                 ctx.rows_capacity)
+            ctx.saved_rows = None  # the rows (GBs at full batch sizes) are released with the step
+            return (None,) * 8 + tuple(dws) + tuple(dgs) + tuple(dbs)
         dws, dgs, dbs = F_.pfn_backward(rows, kept_idx if ctx.has_kept else None, num_points, coors, npil_dev,
                                         ctx.capacity, ctx.T, ctx.cfg, weights, scale_shift, batch_stats,
                                         ctx.training, dfeats, ctx.rows_capacity)
@@ -124,6 +136,11 @@ class PillarFeatureNet(nn.Module):
         # self-consistent although the two passes differ by ~1e-6 (with the forward's statistics reused, round 1 measured
         # train-mode gradients at 2x torch's own fp32 error). False: FMA forward, bit-consistent with the recompute.
         self.autograd_tensor_cores = True
+        # train mode under autograd: run the forward once in compact row space (fp32 FMA rows — the ones BatchNorm's
+        # backward has to differentiate) and keep the rows for the backward, instead of the tensor-core forward with its L
+        # statistics passes followed by K2''s recompute of the same rows. False: the recompute pair (no memory held
+        # between forward and backward).
+        self.train_rows = True
 
     # -- helpers ------------------------------------------------------------------------------------
     def _config(self) -> F_.PfnConfig:

@@ -84,7 +84,7 @@ def main():
     masks, classes = synthetic_masks(args.batch, enc._num_voxel_y, enc._num_voxel_x, 100 + rank, dev)
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()
         canvas = enc(frames)                                     # K1, K2, K3 + LayerNorm
         out = head(pixel_values=canvas, mask_labels=masks, class_labels=classes)
         out.loss.backward()                                      # ... their backward kernels; DDP reduces the head
@@ -93,7 +93,7 @@ def main():
         return out.loss
 
     def front_end_only():
-        enc.zero_grad(set_to_none=False)
+        enc.zero_grad()
         canvas = enc(frames)
         canvas.backward(torch.ones_like(canvas))
 

@@ -19,7 +19,7 @@ enc = M.MaskBevEncoder(**encoder_kwargs(name)).to(dev).train()
 frames = [torch.from_numpy(f).to(dev) for f in gen_batch(name, batch=nf)]
 g = None
 for it in range(3):
-    enc.zero_grad(set_to_none=False)
+    enc.zero_grad()
     y = enc(frames)
     if g is None:
         g = torch.randn_like(y)

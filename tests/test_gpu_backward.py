@@ -37,11 +37,12 @@ def _l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-def _run_grads(chans, T, training, n_points, seeds, seed_w=11):
+def _run_grads(chans, T, training, n_points, seeds, seed_w=11, train_rows=True):
     kw = ref_test_kwargs(feat_channels=chans, T=T)
     enc, orc = encoder_pair(kw, seed=seed_w)
     o64 = _oracle64(orc, kw)
     enc = enc.to(DEV).train(training)
+    enc._voxel_encoder.train_rows = train_rows
     o64.pfn.train(training)
     orc.pfn.train(training)
     voxels, nump, coors, _ = orc.voxelize(_frames(n_points, 4, seeds))
@@ -80,6 +81,17 @@ def test_pfn_param_grads(chans, T, training, n_points):
             f"chans={chans} P={P}")
     print(f"P={P} chans={chans} train={training}: worst vs f64 {max(r[0] for r in res):.2e}, vs torch-f32 "
           f"{max(r[3] for r in res):.2e} (torch f32 vs f64 {max(r[1] for r in res):.2e})")
+
+
+@pytest.mark.parametrize("chans,T", [((16, 32, 64), 20), ((128, 128, 128), 32)])
+def test_pfn_param_grads_recompute_pair(chans, T):
+    """train_rows = False: tensor-core train forward + K2' recomputing the rows (mbev_pfn_forward_train +
+    mbev_pfn_backward) — the pair that holds no memory between forward and backward — to the same bar as the default
+    (row-space forward keeping its rows, mbev_pfn_forward_train_rows + mbev_pfn_backward_rows)."""
+    P, res = _run_grads(chans, T, True, 12000, (1, 2), train_rows=False)
+    for i, (e64, e32_64, l2, e32) in enumerate(res):
+        assert min(e64, e32) <= max(GRAD_TOL, 1.5 * e32_64), (
+            f"param {i}: vs f64 {e64:.3e}, vs torch-f32 {e32:.3e} (torch f32 vs f64 {e32_64:.3e}) chans={chans} P={P}")
 
 
 def test_encoder_fused_training_step_grads_and_determinism():

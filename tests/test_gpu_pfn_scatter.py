@@ -177,6 +177,38 @@ def test_pfn_train_mode_batch_stats(chans):
         assert_close(mine.running_var.cpu().numpy(), layer.norm.running_var.numpy(), tol=1e-5, what="running_var")
 
 
+@pytest.mark.parametrize("chans", [(64,), (128, 128, 128), (16, 32, 64)])
+def test_pfn_train_rows_forward_under_autograd(chans):
+    """A training step's forward (train mode, grad enabled) runs once in row space and keeps its rows
+    (mbev_pfn_forward_train_rows): features, running statistics and the folded statistics must match the oracle's
+    train-mode forward exactly as the tensor-core train forward does, and a no-grad call must agree with it."""
+    kw = ref_test_kwargs(feat_channels=chans, T=32)
+    enc, orc = encoder_pair(kw, seed=6)
+    enc = enc.to(DEV).train()
+    orc.pfn.train()
+    frames = _frames(30000, 4, seeds=(3, 4))
+    voxels, nump, coors, _ = orc.voxelize(frames)
+    orc64 = oracle64_of(orc, kw)
+    with torch.no_grad():
+        ref = orc.encode(voxels, nump, coors).numpy()
+        ref64 = orc64.encode(voxels.astype(np.float64), nump, coors).numpy()
+    assert enc._voxel_encoder.train_rows
+    args = (torch.from_numpy(voxels).to(DEV), torch.from_numpy(nump).to(DEV), torch.from_numpy(coors).to(DEV))
+    out = enc.encode(*args)                       # grad enabled: the row-space forward
+    assert out.requires_grad
+    assert_close_arbitrated(out.detach().cpu().numpy(), ref, ref64, what=f"pfn train rows {chans}")
+    for l, layer in enumerate(orc.pfn.pfn_layers):
+        mine = enc._voxel_encoder.pfn_layers[l].norm
+        assert int(mine.num_batches_tracked) == int(layer.norm.num_batches_tracked) == 1
+        assert_close(mine.running_mean.cpu().numpy(), layer.norm.running_mean.numpy(), tol=1e-5, what="running_mean")
+        assert_close(mine.running_var.cpu().numpy(), layer.norm.running_var.numpy(), tol=1e-5, what="running_var")
+    with torch.no_grad():
+        nograd = enc.encode(*args)                # the tensor-core (or FMA) train forward without saved rows
+    assert_close(nograd.cpu().numpy(), out.detach().cpu().numpy(), tol=1e-5, what="train forward: no-grad vs rows")
+    out2 = enc.encode(*args)
+    assert torch.equal(out2.detach(), out.detach()), "row-space train forward must be bit-identical run to run"
+
+
 def test_cpu_input_is_rejected_loudly():
     import mask_bev_b200 as M
     kw = ref_test_kwargs()
