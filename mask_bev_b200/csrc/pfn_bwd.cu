@@ -256,15 +256,8 @@ k_gemm_rows(const __grid_constant__ GemmK g) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int n0 = blockIdx.y * BN;
-  for (int mt = blockIdx.x; mt * BM < M; mt += gridDim.x) {
-    const int m0 = mt * BM;
-    float acc[8][TN];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    float ra[8], rb[BN / 16];
-    auto gload = [&](int kb) {
+  float ra[8], rb[BN / 16];
+  auto gload = [&](int m0, int kb) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) {  // A tile 128 x 16: 16 consecutive k of one row per 16 threads
         const int idx = tid + it * 256;
@@ -280,25 +273,35 @@ k_gemm_rows(const __grid_constant__ GemmK g) {
         const int n = n0 + nn, k = kb + kk;
         rb[it] = (n < N && k < K) ? __ldg(g.B + static_cast<long long>(k) * g.sBk + static_cast<long long>(n) * g.sBn) : 0.f;
       }
-    };
-    auto sstore = [&]() {
+  };
+  auto sstore = [&]() {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = tid + it * 256;
-        sA[idx & 15][idx >> 4] = ra[it];
-      }
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + it * 256;
+      sA[idx & 15][idx >> 4] = ra[it];
+    }
 #pragma unroll
-      for (int it = 0; it < BN / 16; ++it) {
-        const int idx = tid + it * 256;
-        if (g.sBn == 1) sB[idx / BN][idx % BN] = rb[it]; else sB[idx & 15][idx >> 4] = rb[it];
-      }
-    };
-    gload(0);
+    for (int it = 0; it < BN / 16; ++it) {
+      const int idx = tid + it * 256;
+      if (g.sBn == 1) sB[idx / BN][idx % BN] = rb[it]; else sB[idx & 15][idx >> 4] = rb[it];
+    }
+  };
+  if (static_cast<int>(blockIdx.x) * BM < M) gload(blockIdx.x * BM, 0);
+  for (int mt = blockIdx.x; mt * BM < M; mt += gridDim.x) {
+    const int m0 = mt * BM;
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
     for (int kb = 0; kb < K; kb += BK) {
       __syncthreads();  // the previous block's readers are done with the tiles
       sstore();
       __syncthreads();
-      if (kb + BK < K) gload(kb + BK);
+      // the next k-block's rows — or, under the last k-block, the NEXT TILE's first rows (K = 64 / 128 is only 4 - 8
+      // k-blocks: no load latency exposed at the start of a tile) — are in flight during the products
+      if (kb + BK < K) gload(m0, kb + BK);
+      else if ((mt + static_cast<int>(gridDim.x)) * BM < M) gload((mt + gridDim.x) * BM, 0);
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) {
         const float4 a0 = *reinterpret_cast<const float4 *>(&sA[kk][ty * 8]);
@@ -530,6 +533,44 @@ k_act_max4(const float *__restrict__ Y, const int U, const float *__restrict__ s
   }
 }
 
+// k_act_max4 and the row pass X_{l+1} = [a_l || m_l] (k_build_x) in one pillar pass (layers that feed another layer): the second walk over the pillar's rows
+// re-reads Y from L1 / L2 and writes X_{l+1}[r] = [ relu(bn(Y_l[r])) || m ] — one DRAM read of Y and one launch less.
+__global__ void __launch_bounds__(kThreads)
+k_act_max_build4(const float *__restrict__ Y, const int U, const float *__restrict__ scale,
+                 const float *__restrict__ shift, const int *__restrict__ row_off, const int *__restrict__ num_pillars,
+                 float *__restrict__ Mx, uchar4 *__restrict__ arg, float *__restrict__ X) {
+  const int U4 = U >> 2;
+  const long long total = static_cast<long long>(*num_pillars) * U4;
+  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int p = static_cast<int>(i / U4), q = static_cast<int>(i - static_cast<long long>(p) * U4);
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + q);
+    const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift) + q);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar4 a = make_uchar4(0, 0, 0, 0);
+    const int r0 = row_off[p], r1 = row_off[p + 1];
+    for (int r = r0; r < r1; ++r) {
+      const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + static_cast<size_t>(r) * U) + q);
+      const float zx = fmaf(y.x, sc.x, sh.x), zy = fmaf(y.y, sc.y, sh.y), zz = fmaf(y.z, sc.z, sh.z),
+                  zw = fmaf(y.w, sc.w, sh.w);
+      const unsigned char t = static_cast<unsigned char>(r - r0);
+      if (zx > m.x) { m.x = zx; a.x = t; }
+      if (zy > m.y) { m.y = zy; a.y = t; }
+      if (zz > m.z) { m.z = zz; a.z = t; }
+      if (zw > m.w) { m.w = zw; a.w = t; }
+    }
+    reinterpret_cast<float4 *>(Mx)[i] = m;
+    arg[i] = a;
+    for (int r = r0; r < r1; ++r) {
+      const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + static_cast<size_t>(r) * U) + q);
+      float4 *x = reinterpret_cast<float4 *>(X + static_cast<size_t>(r) * 2 * U);
+      x[q] = make_float4(fmaxf(fmaf(y.x, sc.x, sh.x), 0.f), fmaxf(fmaf(y.y, sc.y, sh.y), 0.f),
+                         fmaxf(fmaf(y.z, sc.z, sh.z), 0.f), fmaxf(fmaf(y.w, sc.w, sh.w), 0.f));
+      x[U4 + q] = m;
+    }
+  }
+}
+
 // X_{l+1}[r] = [ relu(bn(Y_l[r])) || m_l[pillar(r)] ]   (R, 2U)
 __global__ void __launch_bounds__(kThreads)
 k_build_x(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ shift,
@@ -541,31 +582,6 @@ k_build_x(const float *__restrict__ Y, const int U, const float *__restrict__ sc
     const int r = static_cast<int>(i / (2 * U)), c = static_cast<int>(i - static_cast<long long>(r) * 2 * U);
     X[i] = (c < U) ? fmaxf(fmaf(Y[static_cast<size_t>(r) * U + c], scale[c], shift[c]), 0.f)
                    : Mx[static_cast<size_t>(row_pillar[r]) * U + (c - U)];
-  }
-}
-
-__global__ void __launch_bounds__(kThreads)
-k_build_x4(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ shift,
-           const float *__restrict__ Mx, const int *__restrict__ row_pillar, const int *__restrict__ num_rows,
-           float *__restrict__ X) {
-  const int U4 = U >> 2;
-  const long long total = static_cast<long long>(*num_rows) * 2 * U4;
-  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
-    const int r = static_cast<int>(i / (2 * U4)), q = static_cast<int>(i - static_cast<long long>(r) * 2 * U4);
-    float4 v;
-    if (q < U4) {
-      const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + static_cast<size_t>(r) * U) + q);
-      const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + q);
-      const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift) + q);
-      v.x = fmaxf(fmaf(y.x, sc.x, sh.x), 0.f);
-      v.y = fmaxf(fmaf(y.y, sc.y, sh.y), 0.f);
-      v.z = fmaxf(fmaf(y.z, sc.z, sh.z), 0.f);
-      v.w = fmaxf(fmaf(y.w, sc.w, sh.w), 0.f);
-    } else {
-      v = __ldg(reinterpret_cast<const float4 *>(Mx + static_cast<size_t>(row_pillar[r]) * U) + (q - U4));
-    }
-    reinterpret_cast<float4 *>(X)[i] = v;
   }
 }
 
@@ -806,7 +822,7 @@ k_dm4(const float *__restrict__ dXnext, const int ldx, const int U, const int *_
   }
 }
 
-__global__ void __launch_bounds__(kDz4Threads)
+__global__ void __launch_bounds__(kDz4Threads, 2)  // <= 64 registers: two 512-thread CTAs per SM (83 registers left one)
 k_dz_rows4(const float *__restrict__ Y, const int U, const float *__restrict__ scale, const float *__restrict__ shift,
            const float *__restrict__ mean, const float *__restrict__ var, const float eps,
            const uchar4 *__restrict__ arg, const float *__restrict__ dm_src, const float *__restrict__ dXnext,
@@ -1135,12 +1151,17 @@ int rows_forward(const RowsPass &c, const float *rows, const int32_t *kept_idx, 
       MBEV_CHECK_LAUNCH();
     }
     const bool v4 = c.vec4_ok(U);
+    if (v4 && l + 1 < L) {  // max, arg-max row and X_{l+1} = [a_l || m_l] in one pillar pass
+      k_act_max_build4<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.row_off, c.num_pillars_dev,
+                                                          w.Mx[l], w.Arg[l], w.X[l + 1]);
+      MBEV_CHECK_LAUNCH();
+      continue;
+    }
     if (v4) k_act_max4<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.row_off, c.num_pillars_dev, w.Mx[l], w.Arg[l]);
     else k_act_max<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.row_off, c.num_pillars_dev, w.Mx[l]);
     MBEV_CHECK_LAUNCH();
     if (l + 1 < L) {  // X_{l+1} = [a_l || m_l], kept until dW_{l+1} has been taken
-      if (v4) k_build_x4<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.Mx[l], w.row_pillar, w.num_rows, w.X[l + 1]);
-      else k_build_x<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.Mx[l], w.row_pillar, w.num_rows, w.X[l + 1]);
+      k_build_x<<<kEwBlocks, kThreads, 0, stream>>>(w.Y[l], U, c.SC(l), c.SH(l), w.Mx[l], w.row_pillar, w.num_rows, w.X[l + 1]);
       MBEV_CHECK_LAUNCH();
     }
   }

@@ -180,13 +180,27 @@ class PillarFeatureNet(nn.Module):
         """BatchNorm1d bookkeeping: momentum update with the unbiased variance, M = P*T slots. No host sync. A step
         without any pillar (every point filtered out) leaves the buffers untouched (nn.BatchNorm1d raises on an
         empty input; silently decaying the statistics towards zero would be worse than either)."""
-        M = npil_dev.to(torch.float32) * float(T)
+        M = npil_dev.to(torch.float32).reshape(()) * float(T)   # (npil_dev is a 1-element tensor: 0-dim from here on)
         live = (M > 0).to(torch.float32)
         unbias = M / torch.clamp(M - 1.0, min=1.0)
-        for l, layer in enumerate(self.pfn_layers):
-            bn, U = layer.norm, layer.units
-            if not bn.track_running_stats:
-                continue
+        bns = [(l, layer.norm, layer.units) for l, layer in enumerate(self.pfn_layers) if layer.norm.track_running_stats]
+        if not bns:
+            return
+        moms = {bn.momentum for _, bn, _ in bns}
+        if len(moms) == 1 and None not in moms and all(bn.running_mean.dtype == torch.float32 for _, bn, _ in bns):
+            # one momentum for all layers (the configured case): the same arithmetic, running = running * (1 - mom) +
+            # new * mom, as a handful of multi-tensor launches instead of ~14 small ones per layer
+            mom = live * moms.pop()
+            new = batch_stats * mom                      # (L, 2, MAX_UNITS): mean * mom, var * mom
+            new[:, 1] *= unbias                          # unbiased variance
+            running = [t for _, bn, _ in bns for t in (bn.running_mean, bn.running_var)]
+            update = [new[l, j, :U] for l, _, U in bns for j in (0, 1)]
+            torch._foreach_mul_(running, 1.0 - mom)
+            torch._foreach_add_(running, update)
+            torch._foreach_add_([bn.num_batches_tracked for _, bn, _ in bns],
+                                live.to(bns[0][1].num_batches_tracked.dtype).reshape(()))
+            return
+        for l, bn, U in bns:
             bn.num_batches_tracked += live.to(bn.num_batches_tracked.dtype).reshape(())
             if bn.momentum is not None:
                 mom = live * bn.momentum

@@ -1,34 +1,27 @@
 #!/bin/bash
-# Round-2e probe (1 GPU): sparse-run scatter (bf16: in the default library; fp32: second library built with
-# -DMBEV_K3_SPARSE_F32) — bit-identity tests and K3 timings of both — and the training step under torch.profiler.
-tag=${1:-r2e}
+# Round-2e closing check (1 GPU) of the final tree: full parity suite, smoke, the headline bench line with the training
+# block, the 16-frame training block, the training step under torch.profiler. usage: bash scripts/gpu_r2e_quick.sh [tag]
+tag=${1:-r2f}
 mkdir -p gpurun_out
-run_bench() {  # $1 = label
-  for wl in kitti_b16 waymo_b32; do
-    timeout 300 python bench.py --workload $wl --steps 30 --warmup 5 --no-cpu-baseline --no-layernorm --no-train > gpurun_out/${tag}_q_$1_$wl.json 2> gpurun_out/${tag}_q_$1_$wl.err
-  done
-}
-timeout 600 python -m pytest tests/test_gpu_pfn_scatter.py tests/test_gpu_full_size.py -m gpu -q -p no:cacheprovider --timeout 600 2>&1 | tail -25 > gpurun_out/${tag}_pytest_default.log
-tail -4 gpurun_out/${tag}_pytest_default.log
-run_bench default
-if [ -f _variants/lib_sparse32.so ]; then
-  cp _variants/lib_sparse32.so mask_bev_b200/_C/libmask_bev_b200.so
-  timeout 600 python -m pytest tests/test_gpu_pfn_scatter.py tests/test_gpu_full_size.py tests/test_gpu_reference_run.py -m gpu -q -p no:cacheprovider --timeout 600 2>&1 | tail -25 > gpurun_out/${tag}_pytest_sparse32.log
-  tail -4 gpurun_out/${tag}_pytest_sparse32.log
-  run_bench sparse32
-  cp _variants/lib_default.so mask_bev_b200/_C/libmask_bev_b200.so
-fi
+rm -f gpurun_out/parity_elementwise.jsonl
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 600 2>&1 | tail -8 > gpurun_out/${tag}_pytest.log
+tail -3 gpurun_out/${tag}_pytest.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log
+timeout 600 python bench.py --steps 30 --warmup 5 --train > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err || tail -5 gpurun_out/${tag}_bench.err
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-layernorm --train --train-batch 16 > gpurun_out/${tag}_bench_train16.json 2> gpurun_out/${tag}_bench_train16.err || tail -5 gpurun_out/${tag}_bench_train16.err
 python - <<PY
 import json
-for v in ("default", "sparse32"):
-    for w in ("kitti_b16", "waymo_b32"):
-        f = "${tag}_q_%s_%s" % (v, w)
-        try:
-            d = json.load(open(f"gpurun_out/{f}.json"))
-        except Exception as e:
-            print(f, "FAILED", e); continue
-        print(f, "ms/step %.3f serial %.3f fps %.0f e2e %.0f | K3 %.4f frac %.3f of_fill %.3f | bf16 K3 %.4f" % (
-            d["ms_per_step"], d["serial_ms_per_step"], d["value"], d["e2e"]["value"], d["kernels"]["K3_scatter"]["ms"],
-            d["roofline"]["frac"], d["roofline"].get("frac_of_fill", 0), d["bf16_canvas"]["K3_scatter_bf16_ms"]))
+for f in ("${tag}_bench", "${tag}_bench_train16"):
+    try:
+        d = json.load(open(f"gpurun_out/{f}.json"))
+    except Exception as e:
+        print(f, "FAILED", e); continue
+    k = d["kernels"]
+    print(f, "ms/step %.3f serial %.3f fps %.0f e2e %.0f step_frac %.3f roof %.3f | K1 %.4f K2 %.4f K3 %.4f" % (
+        d["ms_per_step"], d["serial_ms_per_step"], d["value"], d["e2e"]["value"], d["roofline"]["step_frac"],
+        d["roofline"]["frac"], k["K1_voxelize"]["ms"], k["K2_pfn"]["ms"], k["K3_scatter"]["ms"]))
+    if d.get("train"): print("   train", {a: b for a, b in d["train"].items() if a != "what"})
+    if d.get("cpu_baseline"): print("   cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"])
 PY
-timeout 200 python scripts/gpu_train_profile.py kitti_b16 4 > gpurun_out/${tag}_train_profile.txt 2>&1; head -30 gpurun_out/${tag}_train_profile.txt | cut -c1-110
+timeout 200 python scripts/gpu_train_profile.py kitti_b16 4 > gpurun_out/${tag}_train_profile.txt 2>&1; head -8 gpurun_out/${tag}_train_profile.txt | cut -c1-110
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_train_launches.csv python scripts/gpu_train_launches.py kitti_b16 4 > gpurun_out/${tag}_ncu_train.log 2>&1

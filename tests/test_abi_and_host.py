@@ -315,3 +315,31 @@ def test_training_configs_fixture_matches_the_reference_when_present():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.collect() == _training_configs()
+
+
+def test_running_stats_update_matches_the_batchnorm_formula():
+    """PillarFeatureNet._update_running_stats (multi-tensor form): running = (1 - m) * running + m * new with the unbiased
+    variance over M = P*T slots, num_batches_tracked += 1; a step without pillars leaves the buffers untouched. Pure
+    torch, so it runs on the CPU (the kernels only produce `batch_stats`)."""
+    import copy
+
+    import torch
+    from mask_bev_b200.pillar_encoder import PillarFeatureNet
+    torch.manual_seed(0)
+    net = PillarFeatureNet(4, (128, 128, 128), with_distance=True, norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01))
+    ref = copy.deepcopy(net)
+    bs = torch.rand(3, 2, 128)
+    P, T = 1234, 32
+    net._update_running_stats(bs, torch.tensor([P], dtype=torch.int32), T)   # a 1-element tensor, as the kernels hand it over
+    M = P * T
+    for l, (mine, layer) in enumerate(zip(net.pfn_layers, ref.pfn_layers)):
+        bn, U = layer.norm, layer.units
+        bn.running_mean.mul_(1 - 0.01).add_(bs[l, 0, :U] * 0.01)
+        bn.running_var.mul_(1 - 0.01).add_(bs[l, 1, :U] * (M / (M - 1)) * 0.01)
+        assert int(mine.norm.num_batches_tracked) == 1
+        assert torch.allclose(mine.norm.running_mean, bn.running_mean, rtol=1e-6, atol=0)
+        assert torch.allclose(mine.norm.running_var, bn.running_var, rtol=1e-6, atol=0)
+    before = [l.norm.running_var.clone() for l in net.pfn_layers]
+    net._update_running_stats(bs, torch.tensor([0], dtype=torch.int32), T)
+    for b, l in zip(before, net.pfn_layers):
+        assert torch.equal(b, l.norm.running_var) and int(l.norm.num_batches_tracked) == 1
