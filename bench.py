@@ -327,7 +327,8 @@ def train_block(args, enc, kwargs, rank, world, dev, barrier):
         out["step_overlapped_ms" if overlap else "step_serial_ms"] = ms
         dp.close()
     nbytes = gradient_bytes(tenc)
-    out.update({"what": "encoder training step (train-mode BN, fused scatter+LayerNorm fwd/bwd) + gradient allreduce; "
+    out.update({"what": "encoder training step (train-mode BN; row-space PFN forward whose rows the backward reuses, fused "
+                        "scatter+LayerNorm fwd/bwd; zero_grad() = set_to_none) + gradient allreduce; "
                         "overlapped = the LayerNorm-gradient allreduce is issued from a post-accumulate hook and runs "
                         "under the PFN backward",
                 "frames_per_gpu": tb, "allreduce_bytes_per_rank": nbytes, "collectives_per_step": rep.collectives if rep else 0,

@@ -343,3 +343,43 @@ def test_running_stats_update_matches_the_batchnorm_formula():
     net._update_running_stats(bs, torch.tensor([0], dtype=torch.int32), T)
     for b, l in zip(before, net.pfn_layers):
         assert torch.equal(b, l.norm.running_var) and int(l.norm.num_batches_tracked) == 1
+
+
+def test_training_step_pair_validates_its_arguments_without_gpu():
+    """mbev_pfn_forward_train_rows / mbev_pfn_backward_rows (ABI v11): host-side argument checks return before any launch
+    — null pointers and a workspace smaller than mbev_pfn_backward_workspace_bytes are refused, an empty step is a no-op."""
+    import torch
+    from mask_bev_b200 import _lib
+    from mask_bev_b200 import functional as F_
+    lib = _lib.load()
+    assert lib.mbev_abi_version() == 11
+    cfg = F_.PfnConfig(in_channels=4, units=[64, 64, 128], in_dims=[11, 128, 128], with_cluster_center=True,
+                       with_voxel_center=True, with_distance=True, legacy=True, voxel_center_dims=3, vx=0.16, vy=0.16,
+                       vz=40.0, x_offset=-39.92, y_offset=-39.92, z_offset=0.0, eps=1e-3, gemm_path=0)
+    ws = [torch.zeros(u, k) for u, k in zip(cfg.units, cfg.in_dims)]
+    params = F_._pfn_struct(cfg, ws, None, None)
+    n = ctypes.c_size_t()
+    assert lib.mbev_pfn_backward_workspace_bytes(ctypes.byref(params), 32, 1000, 5000, ctypes.byref(n)) == 0
+    rows = 5000 * (11 + 128 + 128 + 64 + 64 + 128) * 4   # X_l and Y_l of every layer are kept for the backward
+    assert n.value > rows
+    fake = ctypes.c_void_p(256)   # never dereferenced: every call below returns from the host-side checks
+    three = (ctypes.c_void_p * F_.MAX_LAYERS)(256, 256, 256)
+    none = ctypes.c_void_p(None)
+    # forward: null workspace / null gamma array
+    assert lib.mbev_pfn_forward_train_rows(fake, 4, fake, fake, fake, fake, 1000, 32, 5000, ctypes.byref(params), three,
+                                           three, 1e-3, fake, fake, fake, none, n.value, none) == -1
+    assert lib.mbev_pfn_forward_train_rows(fake, 4, fake, fake, fake, fake, 1000, 32, 5000, ctypes.byref(params), None,
+                                           three, 1e-3, fake, fake, fake, fake, n.value, none) == -1
+    # workspace too small -> MBEV_ERR_WORKSPACE (-3); empty step (capacity 0) -> OK without touching anything
+    assert lib.mbev_pfn_forward_train_rows(fake, 4, fake, fake, fake, fake, 1000, 32, 5000, ctypes.byref(params), three,
+                                           three, 1e-3, fake, fake, fake, fake, 1024, none) == -3
+    assert lib.mbev_pfn_forward_train_rows(fake, 4, fake, fake, fake, fake, 0, 32, 0, ctypes.byref(params), three,
+                                           three, 1e-3, fake, fake, fake, fake, 1024, none) == 0
+    # backward: null dfeats, short workspace, inconsistent layer chain
+    assert lib.mbev_pfn_backward_rows(fake, 1000, 4, 32, 5000, ctypes.byref(params), 1e-3, none, three, three, three,
+                                      fake, n.value, none) == -1
+    assert lib.mbev_pfn_backward_rows(fake, 1000, 4, 32, 5000, ctypes.byref(params), 1e-3, fake, three, three, three,
+                                      fake, 1024, none) == -3
+    params.in_dim[1] = 64
+    assert lib.mbev_pfn_backward_rows(fake, 1000, 4, 32, 5000, ctypes.byref(params), 1e-3, fake, three, three, three,
+                                      fake, n.value, none) == -1
