@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2e closing check (1 GPU) of the final tree: full parity suite, smoke, the headline bench line with the training
-# block, the 16-frame training block, the training step under torch.profiler. usage: bash scripts/gpu_r2e_quick.sh [tag]
+# block, the 16-frame training block, the training step under torch.profiler. usage: bash scripts/gpu_r2f.sh [tag]
 tag=${1:-r2f}
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_elementwise.jsonl
