@@ -419,13 +419,13 @@ k_gemm_dw(const float *__restrict__ DY, const float *__restrict__ X, const int U
 }
 
 // dW slice of a NARROW layer (Kin <= 16: layer 0, whose input is the 9..13 decorated point features): the 64 x 64 tiles
-// of k_gemm waste 5/6 of their columns there (129 us per 4-frame step for 0.4 GFLOP). One THREAD per output element
-// (u, k) — U * Kin <= 1024 threads, two outputs per thread above that — and rows through shared memory in tiles of 32
-// (16-byte loads of whole dY rows, all of a tile in flight at once); per row a thread issues two shared-memory loads and
-// one fmaf, rows in order (same partials as k_gemm). Two earlier forms — thread = (u, column group) with 8 predicated
-// accumulators, from global memory or from these tiles — compiled to ~80 instructions per row and warp (predicates
-// re-materialised around every load) and took 196 - 321 us. Needs U % 4 == 0, U * Kin <= 2048.
-__global__ void __launch_bounds__(1024)
+// of k_gemm waste 5/6 of their columns there (129 us per 4-frame step for 0.4 GFLOP). One thread per (four consecutive
+// units, input column k): U / 4 * Kin <= 512 threads; rows through shared memory in tiles of 32 (16-byte loads of whole
+// dY rows, all of a tile in flight at once); per row a thread issues one 16-byte and one 4-byte shared-memory load and
+// four fmaf, rows in order (same partials as k_gemm). Earlier forms: thread = (u, column group) with 8 predicated
+// accumulators compiled to ~80 instructions per row and warp (196 - 321 us); one thread per output element was bound by
+// the shared-memory pipe (two wavefronts per 32 products, 93 us). Needs U % 4 == 0, U <= 128, Kin <= 16.
+__global__ void __launch_bounds__(512)
 k_dw_narrow(const float *__restrict__ DY, const float *__restrict__ X, const int U, const int Kin,
             const int *__restrict__ num_rows, float *__restrict__ part, const long long split_stride) {
   constexpr int TR = 32;
@@ -435,34 +435,37 @@ k_dw_narrow(const float *__restrict__ DY, const float *__restrict__ X, const int
   const int nsplit = gridDim.x;
   const int kper = ((R + nsplit - 1) / nsplit + TR - 1) / TR * TR;
   const int k0 = min(R, static_cast<int>(blockIdx.x) * kper), k1 = min(R, k0 + kper);
-  const int tid = threadIdx.x, nthr = blockDim.x, nout = U * Kin;
-  const int o0 = tid, o1 = tid + nthr;
-  const bool has0 = o0 < nout, has1 = o1 < nout;
-  const int ka = has0 ? o0 / U : 0, ua = has0 ? o0 % U : 0;
-  const int kb1 = has1 ? o1 / U : 0, ub = has1 ? o1 % U : 0;
-  float acc0 = 0.f, acc1 = 0.f;
+  const int tid = threadIdx.x, nthr = blockDim.x, U4 = U >> 2;
+  const bool has = tid < U4 * Kin;
+  const int k = has ? tid / U4 : 0, ug = has ? tid % U4 : 0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int kb = k0; kb < k1; kb += TR) {
     const int rows = min(TR, k1 - kb);
     const float4 *src = reinterpret_cast<const float4 *>(DY + static_cast<size_t>(kb) * U);
-    for (int i = tid; i < rows * U / 4; i += nthr) reinterpret_cast<float4 *>(sDY)[i] = __ldg(src + i);
+    for (int i = tid; i < rows * U4; i += nthr) reinterpret_cast<float4 *>(sDY)[i] = __ldg(src + i);
     const float *xs = X + static_cast<size_t>(kb) * Kin;
     for (int i = tid; i < rows * Kin; i += nthr) sX[i] = __ldg(xs + i);
     __syncthreads();
-    if (has1) {
-#pragma unroll 4
-      for (int r = 0; r < rows; ++r) {
-        acc0 = fmaf(sDY[r * U + ua], sX[r * Kin + ka], acc0);
-        acc1 = fmaf(sDY[r * U + ub], sX[r * Kin + kb1], acc1);
-      }
-    } else if (has0) {
+    if (has) {
 #pragma unroll 8
-      for (int r = 0; r < rows; ++r) acc0 = fmaf(sDY[r * U + ua], sX[r * Kin + ka], acc0);
+      for (int r = 0; r < rows; ++r) {
+        const float4 dy = reinterpret_cast<const float4 *>(sDY)[r * U4 + ug];
+        const float x = sX[r * Kin + k];
+        acc.x = fmaf(dy.x, x, acc.x);
+        acc.y = fmaf(dy.y, x, acc.y);
+        acc.z = fmaf(dy.z, x, acc.z);
+        acc.w = fmaf(dy.w, x, acc.w);
+      }
     }
     __syncthreads();
   }
-  float *C = part + static_cast<long long>(blockIdx.x) * split_stride;
-  if (has0) C[static_cast<long long>(ua) * Kin + ka] = acc0;
-  if (has1) C[static_cast<long long>(ub) * Kin + kb1] = acc1;
+  if (has) {
+    float *C = part + static_cast<long long>(blockIdx.x) * split_stride + static_cast<long long>(4 * ug) * Kin + k;
+    C[0] = acc.x;
+    C[Kin] = acc.y;
+    C[2 * Kin] = acc.z;
+    C[3 * Kin] = acc.w;
+  }
 }
 
 // fixed-order reduction of split-K partials into dst (count elements): one WARP per element — lane j sums partials j,
@@ -1215,8 +1218,14 @@ int rows_backward(const RowsPass &c, const float *dfeats, float *const *dweight,
         else k_gemm_dw<64><<<kSplitK, 256, 0, stream>>>(w.DZ, w.X[l], U, K, w.num_rows, w.wpart, split_stride);
         MBEV_CHECK_LAUNCH();
       } else if (K <= 16 && U <= 128 && U % 4 == 0) {
-        const int threads = std::min(1024, (U * K + 31) / 32 * 32);
-        k_dw_narrow<<<kSplitK, threads, 0, stream>>>(w.DZ, w.X[l], U, K, w.num_rows, w.wpart, split_stride);
+        int umax = 0, inmax = 0;  // as many row slices as the partial-sum buffer holds, up to 6 small CTAs per SM
+        for (int j = 0; j < L; ++j) {
+          umax = std::max(umax, params->units[j]);
+          inmax = std::max(inmax, params->in_dim[j]);
+        }
+        nsplit = static_cast<int>(std::min<long long>(kNumSMs * 6, static_cast<long long>(kSplitK) * umax * inmax / split_stride));
+        const int threads = (U / 4 * K + 31) / 32 * 32;
+        k_dw_narrow<<<nsplit, threads, 0, stream>>>(w.DZ, w.X[l], U, K, w.num_rows, w.wpart, split_stride);
         MBEV_CHECK_LAUNCH();
       } else {
         GemmK g{};
