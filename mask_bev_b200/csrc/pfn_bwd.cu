@@ -1012,9 +1012,9 @@ bool tc_rows_ok(const MbevPfnParams *p, int K, int N) {
 int launch_gemm(const GemmK &g, int m_tiles_cap, int n, int splits, cudaStream_t stream) {
   if (splits == 1 && g.sAk == 1 && g.m_dev != nullptr && (g.sBn == 1 || g.sBk == 1)) {
     const int tiles = std::max(1, std::min((m_tiles_cap + 1) / 2, kNumSMs * 4));
-    // 64-column tiles also for N = 128: the 128-column instantiation needs 165 registers = ONE 8-warp CTA per SM and ran
-    // at 29 TFLOP/s against 49 for two co-resident 64-column CTAs (ncu launch list of a training step); the A tile is
-    // read twice, from L2. Same k order per output element: bit-identical.
+    // 64-column tiles also for N = 128: the 128-column instantiation needs 165 registers = ONE 8-warp CTA per SM (343 us
+    // for the 128 -> 128 layer of a 4-frame step against 322 us for two co-resident 64-column CTAs; ncu launch lists); the
+    // A tile is read twice, from L2. Same k order per output element: bit-identical.
     k_gemm_rows<64><<<dim3(tiles, (n + 63) / 64), 256, 0, stream>>>(g);
     MBEV_CHECK_LAUNCH();
     return MBEV_OK;
