@@ -52,8 +52,8 @@ def _worker(rank, world, port, q):
         # overlap=True: large gradients leave from a post-accumulate hook during backward, the rest at the end
         net = _toy_net()
         odp = FrontEndDataParallel(net, overlap=True, small_bucket_bytes=100)   # the (4, 8) weight counts as large
-        for step in range(2):   # twice: the pending list must be reset between steps
-            net.zero_grad(set_to_none=False)
+        for step in range(3):   # repeatedly: the pending list must be reset between steps; both zero_grad modes — kept
+            net.zero_grad(set_to_none=(step != 0))   # .grad tensors, then torch's default (fresh .grad from the hook on)
             net(_toy_input(rank)).sum().backward()
             orep = odp.reduce_gradients()
         odp.close()
